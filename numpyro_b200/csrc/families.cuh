@@ -1,0 +1,206 @@
+// Potentials of the registered model families, fused for the engine.
+//
+// Replaces jax.value_and_grad(potential_fn) (numpyro/infer/hmc_util.py:242-252) over
+// potential_energy (infer/util.py:333-358) for: diagonal Gaussian (test target), non-centred
+// eight schools (README.md:100-110), and the GLM family -- plain / hierarchical / horseshoe --
+// with Bernoulli-logit, Poisson-log or Normal likelihood (examples/covtype.py:66-71,
+// examples/horseshoe_regression.py:37-78).  Log-prob formulas: distributions/continuous.py
+// Normal :2975-2989, Cauchy :390-406, HalfCauchy :1148-1150, Exponential :715-726, Gamma
+// :813-831; discrete.py :263 (-> distributions/util.py:317-320), :1361-1388; the exp-transform
+// Jacobian of infer/util.py:325-329 / transforms.py:641-646.  Gradients are hand-derived
+// (checked against the fp64 oracle to rtol 1e-5 and by finite differences in tests/).
+//
+// A GLM evaluation is split in three so that the O(N*D) part can be executed by whichever kernel
+// fits the problem (in-warp loop, HBM-streaming pass, tcgen05 GEMM):
+//   glm_coef   : beta_j = s_j(z) * u_j                              O(D), per chain
+//   likelihood : eta = X beta;  nll = sum_n l(eta_n, y_n);  gbeta = X^T dl/deta   <- the hot op
+//   glm_finish : priors, Jacobians and the chain rule back to z     O(D), per chain
+#pragma once
+#include "common.cuh"
+
+namespace b2 {
+
+enum Family { FAM_DIAG_GAUSSIAN = 0, FAM_EIGHT_SCHOOLS = 1, FAM_GLM = 2 };
+enum Likelihood { LIK_BERNOULLI = 0, LIK_POISSON = 1, LIK_NORMAL = 2 };
+enum ScalePrior { SCALE_NONE = 0, SCALE_HALFCAUCHY = 1, SCALE_EXPONENTIAL = 2 };
+
+struct FamilySpec {
+    int32_t family;
+    int32_t D;                 // latent dimension (flat, sorted-site order)
+    // data
+    long long N; int32_t Dx;   // X [N, Dx] row-major, y [N]
+    const float* X; const float* y;
+    const float* aux0; const float* aux1;   // gaussian: mu, sigma; eight schools: sigma_j, y_j
+    const float* ylgam;        // poisson: lgamma(y + 1), precomputed at create()
+    // GLM structure; offsets into z (-1 = site absent).  Sorted-site layouts:
+    //   plain: coefs | horseshoe: lambdas, (prec_obs), tau, unscaled_betas | hierarchical: coefs, tau
+    int32_t likelihood, off_lambda, off_tau, off_prec, off_u, gscale, g0, g1;
+    float tau_scale, mu_scale;
+};
+
+constexpr float kLogSqrt2Pi = 0.918938533204672742f;
+constexpr float kLog2 = 0.693147180559945309f;
+constexpr float kLogPi = 1.144729885849400174f;
+
+#if defined(__CUDA_ARCH__)
+B2_D void lane_sync() { __syncwarp(); }
+#else
+inline void lane_sync() {}
+#endif
+
+// ---- per-observation loss: value and d/d eta of the negative log-likelihood ------------------
+B2_HD void glm_loss(int lik, float eta, float y, float ylg, float& loss, float& dl) {
+    if (lik == LIK_BERNOULLI) {          // binary_cross_entropy_with_logits (distributions/util.py:317-320)
+        const float e = expf(-fabsf(eta));
+        loss = fmaxf(eta, 0.0f) + log1pf(e) - eta * y;
+        const float s = 1.0f / (1.0f + e);                 // sigmoid(|eta|)
+        dl = ((eta >= 0.0f) ? s : (1.0f - s)) - y;         // sigmoid(eta) - y
+    } else if (lik == LIK_POISSON) {     // Poisson.log_prob (discrete.py:1388) with rate = exp(eta)
+        const float r = expf(eta);
+        loss = r + ylg - y * eta;
+        dl = r - y;
+    } else {                             // Normal: 0.5 * res^2 (precision applied in glm_finish)
+        const float res = eta - y;
+        loss = 0.5f * res * res;
+        dl = res;
+    }
+}
+
+B2_HD float glm_scale_at(const FamilySpec& f, const float* z, int j) {
+    float s = 1.0f;
+    if (f.off_lambda >= 0) s = s * expf(z[f.off_lambda + j]);
+    if (f.gscale != SCALE_NONE && j >= f.g0 && j < f.g1) s = s * expf(z[f.off_tau]);
+    return s;
+}
+
+B2_HD void glm_coef(const FamilySpec& f, const float* z, float* beta) {
+    B2_FOR_D(j, f.Dx) beta[j] = glm_scale_at(f, z, j) * z[f.off_u + j];
+}
+
+// nll / gbeta are the raw likelihood sums (for LIK_NORMAL: 0.5*sum res^2 and X^T res).
+B2_HD void glm_finish(const FamilySpec& f, const float* z, float nll, const float* gbeta, float& u_out, float* g) {
+    const int Dx = f.Dx;
+    float prec = 1.0f;
+    if (f.likelihood == LIK_NORMAL) prec = expf(z[f.off_prec]);
+    // coefficient block: u ~ N(0, 1)
+    float acc = lane_sum(Dx, [&](int j) { const float u = z[f.off_u + j]; return 0.5f * u * u; });
+    float U = acc + (float)Dx * kLogSqrt2Pi;
+    B2_FOR_D(j, Dx) g[f.off_u + j] = z[f.off_u + j] + glm_scale_at(f, z, j) * (prec * gbeta[j]);
+    if (f.off_lambda >= 0) {             // lambdas ~ HalfCauchy(1), z = log lambda
+        float a = lane_sum(Dx, [&](int j) {
+            const float zl = z[f.off_lambda + j];
+            return log1pf(expf(2.0f * zl)) - zl;
+        });
+        U = U + a + (float)Dx * (kLogPi - kLog2);
+        B2_FOR_D(j, Dx) {
+            const float zl = z[f.off_lambda + j];
+            const float l2 = expf(2.0f * zl);
+            const float beta = glm_scale_at(f, z, j) * z[f.off_u + j];
+            // d/dz of [log1p(l2) - zl] = 2*l2/(1+l2) - 1; inf/inf guarded
+            const float frac = is_inf(l2) ? 1.0f : (l2 / (1.0f + l2));
+            g[f.off_lambda + j] = beta * (prec * gbeta[j]) + 2.0f * frac - 1.0f;
+        }
+    }
+    if (f.gscale != SCALE_NONE) {        // global scale tau, z = log tau
+        const float zt = z[f.off_tau];
+        const float tau = expf(zt);
+        const float dot = lane_sum(Dx, [&](int j) {
+            if (j < f.g0 || j >= f.g1) return 0.0f;
+            return (glm_scale_at(f, z, j) * z[f.off_u + j]) * (prec * gbeta[j]);
+        });
+        float pr, dpr;
+        if (f.gscale == SCALE_HALFCAUCHY) {
+            const float q = (tau / f.tau_scale) * (tau / f.tau_scale);
+            pr = kLogPi - kLog2 + logf(f.tau_scale) + log1pf(q) - zt;
+            const float frac = is_inf(q) ? 1.0f : (q / (1.0f + q));
+            dpr = 2.0f * frac - 1.0f;
+        } else {
+            const float rate = 1.0f / f.tau_scale;
+            pr = rate * tau - logf(rate) - zt;
+            dpr = rate * tau - 1.0f;
+        }
+        U = U + pr;
+        if (lane_first() == 0) g[f.off_tau] = dot + dpr;
+    }
+    if (f.likelihood == LIK_NORMAL) {    // sigma = prec^-1/2, prec ~ Gamma(3, 1), z = log prec
+        const float zp = z[f.off_prec];
+        const float Nf = (float)f.N;
+        U = U + prec * nll - 0.5f * Nf * zp + Nf * kLogSqrt2Pi;
+        U = U + (prec - 3.0f * zp + 0.693147180559945309f);          // -[2 zp - prec - lgamma(3)] - zp
+        if (lane_first() == 0) g[f.off_prec] = prec * nll - 0.5f * Nf + prec - 3.0f;
+    } else {
+        U = U + nll;
+    }
+    u_out = U;
+}
+
+// ---- whole potential inside one warp (tiny models, regime R1) ---------------------------------
+// scratch: >= N + Dx floats private to the chain (residuals, beta), gtmp: D floats.
+B2_HD void potential_inwarp(const FamilySpec& f, const float* z, float* scratch, float& u_out, float* g) {
+    if (f.family == FAM_DIAG_GAUSSIAN) {
+        const float* mu = f.aux0; const float* sg = f.aux1;
+        u_out = 0.5f * lane_sum(f.D, [&](int d) { const float t = (z[d] - mu[d]) / sg[d]; return t * t; });
+        B2_FOR_D(d, f.D) g[d] = ((z[d] - mu[d]) / sg[d]) / sg[d];
+        return;
+    }
+    if (f.family == FAM_EIGHT_SCHOOLS) {  // z = [mu, log tau, theta_base[J]]
+        const int J = f.D - 2;
+        const float* sg = f.aux0; const float* y = f.aux1;
+        const float mu = z[0], zt = z[1];
+        const float tau = expf(zt);
+        float s_res2, s_d;                 // sum 0.5*res^2 + log sigma ; sum dtheta
+        lane_sum2(J, [&](int j, float& a, float& b) {
+            const float res = (y[j] - (mu + tau * z[2 + j])) / sg[j];
+            a = 0.5f * res * res + logf(sg[j]);
+            b = res / sg[j];
+        }, s_res2, s_d);
+        float s_tb2, s_dtb;
+        lane_sum2(J, [&](int j, float& a, float& b) {
+            const float tb = z[2 + j];
+            const float res = (y[j] - (mu + tau * tb)) / sg[j];
+            a = 0.5f * tb * tb;
+            b = (res / sg[j]) * tb;
+        }, s_tb2, s_dtb);
+        const float ms = f.mu_scale, ts = f.tau_scale;
+        const float q = (tau / ts) * (tau / ts);
+        float U = 0.5f * (mu / ms) * (mu / ms) + logf(ms) + kLogSqrt2Pi;
+        U = U + (kLogPi - kLog2 + logf(ts) + log1pf(q) - zt);
+        U = U + s_tb2 + s_res2 + 2.0f * (float)J * kLogSqrt2Pi;
+        u_out = U;
+        const float frac = is_inf(q) ? 1.0f : (q / (1.0f + q));
+        if (lane_first() == 0) {
+            g[0] = mu / (ms * ms) - s_d;
+            g[1] = 2.0f * frac - 1.0f - s_dtb * tau;
+        }
+        B2_FOR_D(j, J) {
+            const float tb = z[2 + j];
+            const float res = (y[j] - (mu + tau * tb)) / sg[j];
+            g[2 + j] = tb - (res / sg[j]) * tau;
+        }
+        return;
+    }
+    // FAM_GLM, small N: lanes over rows for eta / residuals, then lanes over columns for X^T r
+    float* beta = scratch; float* resid = scratch + f.Dx;
+    glm_coef(f, z, beta);
+    lane_sync();
+    const int N = (int)f.N, Dx = f.Dx;
+    const float nll = lane_sum(N, [&](int n) {
+        const float* x = f.X + (size_t)n * Dx;
+        float eta = 0.0f;
+        for (int j = 0; j < Dx; ++j) eta = fmaf(x[j], beta[j], eta);
+        float loss, dl;
+        glm_loss(f.likelihood, eta, f.y[n], f.ylgam ? f.ylgam[n] : 0.0f, loss, dl);
+        resid[n] = dl;
+        return loss;
+    });
+    lane_sync();
+    B2_FOR_D(j, Dx) {
+        float a = 0.0f;
+        for (int n = 0; n < N; ++n) a = fmaf(f.X[(size_t)n * Dx + j], resid[n], a);
+        beta[j] = a;                          // reuse as gbeta (own lane's slots only)
+    }
+    lane_sync();
+    glm_finish(f, z, nll, beta, u_out, g);
+}
+
+}  // namespace b2

@@ -1,0 +1,532 @@
+// Per-chain NUTS/HMC state machine ("tick"): everything numpyro does between two evaluations of
+// the potential's gradient, for one chain, executed by one warp (or by the host simulator).
+//
+// The reference expresses a transition as three nested lax.while_loops around value_and_grad
+// (numpyro/infer/hmc_util.py:1155-1179 doubling, :999-1065 leaves, :961-981 checkpoint scan) and
+// batches chains with vmap, so every chain idles on the slowest one at every level.  Here the
+// loops are turned inside out: a chain is an explicit state machine that is handed one
+// (potential, gradient) pair per tick and answers with the next position to evaluate.  Chains are
+// therefore fully asynchronous -- each rolls straight from one transition into the next -- while
+// the expensive gradient can be produced for all chains together by whichever kernel suits the
+// model (in-warp for tiny models, one streaming pass over X for tall data, a GEMM for many chains).
+//
+// Reference functions folded into this file:
+//   a2  velocity_verlet            hmc_util.py:262-311      -> leap_begin / leap_finish
+//   a4  euclidean_kinetic_energy   hmc_util.py:1183-1200    -> kinetic()
+//   a5  momentum_generator         hmc.py:92-110            -> draw_momentum()
+//   a6  build_tree                 hmc_util.py:1088-1180    -> begin_transition / begin_doubling
+//   a7  _iterative_build_subtree   hmc_util.py:984-1085, _build_basetree :851-894 -> on_leaf()
+//   a8  _combine_tree + kernels    hmc_util.py:749-848      -> on_leaf() / finish_doubling()
+//   a9  ckpt index + U-turn checks hmc_util.py:710-746,941-981
+//   a10 _nuts_next / sample_kernel hmc.py:416-530, _hmc_next :364-414 -> finish_transition()
+//   a11 warmup_adapter, dual_averaging, welford_covariance   hmc_util.py:60-239,518-707
+//   a12 find_reasonable_step_size  hmc_util.py:314-384      -> PH_HEUR
+//   a13 init_kernel / find_valid_initial_params  hmc.py:193-362, infer/util.py:366-508 -> PH_INIT
+//   a15 fori_collect index arithmetic  numpyro/util.py:368-403 -> collect()
+#pragma once
+#include "common.cuh"
+#include "detmath.cuh"
+#include "prng.cuh"
+
+namespace b2 {
+
+constexpr int kMaxDepthAlloc = 12;     // checkpoint rows allocated per chain (max_tree_depth <= 12)
+constexpr int kMaxSites = 8;
+
+enum VecField {
+    V_Z = 0, V_G, V_IMM, V_SQRTM, V_WF_MEAN, V_WF_M2,
+    V_ZL, V_RL, V_GL, V_ZR, V_RR, V_GR, V_ZP, V_GP, V_RSUM,
+    V_ZS, V_RS, V_GS, V_ZPS, V_GPS, V_RSUMS,
+    V_R0,                               // momentum at the start of the transition (HMC / heuristic)
+    V_CKPT_R,                           // kMaxDepthAlloc rows
+    V_CKPT_RSUM = V_CKPT_R + kMaxDepthAlloc,
+    V_COUNT = V_CKPT_RSUM + kMaxDepthAlloc
+};
+
+enum Phase { PH_DONE = 0, PH_INIT = 1, PH_LEAF = 2, PH_HMC = 3, PH_HEUR = 4 };
+
+// Per-chain scalars (mirrors HMCState hmc.py:31-48 + HMCAdaptState hmc_util.py:18-30 + the live
+// TreeInfo scalars hmc_util.py:36-57).  Plain ints/floats so the host can read it back verbatim.
+struct ChainCtl {
+    // HMCState
+    int32_t i; uint32_t key[2];
+    float pe, energy;
+    int32_t num_steps; float accept_prob, mean_accept_prob; int32_t diverging;
+    // HMCAdaptState
+    float step_size;
+    float da_x_t, da_x_avg, da_g_avg, da_prox; int32_t da_t;
+    int32_t mm_n, window_idx; uint32_t wa_key[2];
+    // transition in flight
+    int32_t phase;
+    float eps, energy0; int32_t max_depth;
+    uint32_t key_next[2], k_loop[2];
+    int32_t depth, n_total, turning, t_div; float weight, sum_acc, prop_pe, prop_energy;
+    int32_t going_right, n_sub, sub_div; float sub_weight, sub_sum_acc, sub_prop_pe, sub_prop_energy;
+    uint32_t k_sub[2], k_fin[2];
+    // init / heuristic / HMC scratch
+    int32_t init_tries; uint32_t k_init[2];
+    int32_t hmc_left, hmc_n;
+    float heur_step; int32_t heur_dir, heur_last; uint32_t heur_key[2]; int32_t heur_at_init, heur_t;
+    // output cursor + totals
+    int32_t n_collected; int32_t init_failed;
+    unsigned long long total_leapfrogs;
+};
+
+struct TickCfg {
+    int32_t D;
+    int32_t num_warmup, total_iters;        // a chain is PH_DONE once i == total_iters
+    int32_t md_warm, md_post;               // max_tree_depth (warm-up, post warm-up)
+    float target_accept, init_step_size;
+    int32_t adapt_step, adapt_mass, regularize, model_built, find_heuristic;
+    int32_t algo;                           // 0 NUTS, 1 HMC
+    int32_t hmc_num_steps; float traj_len;  // HMC: fixed num_steps (>0) or trajectory_length
+    int32_t num_windows; int32_t window_end[16];
+    int32_t collect_start, thinning, S;     // fori_collect: start_idx, thinning, collection size
+    int32_t init_given; float init_radius;
+    int32_t n_sites; int32_t site_off[kMaxSites], site_size[kMaxSites];   // latent sites, trace order
+};
+
+struct OutBufs {                            // all [C][S] except z [C][S][D]; null = not collected
+    float* z; int32_t* diverging; int32_t* num_steps;
+    float* accept_prob; float* mean_accept_prob; float* pe; float* energy; float* step_size;
+};
+
+struct ChainVecs {
+    float* base; int field_stride;
+    B2_HD float* v(int f) const { return base + (size_t)f * field_stride; }
+};
+
+B2_HD Key mk(const uint32_t* p) { Key k; k.a = p[0]; k.b = p[1]; return k; }
+B2_HD void st(uint32_t* p, Key k) { p[0] = k.a; p[1] = k.b; }
+B2_HD float clip_max1(float p) { return (p > 1.0f) ? 1.0f : p; }      // jnp.clip(p, None, 1): NaN kept
+
+B2_HD float kinetic(int D, const float* imm, const float* r) {
+    return 0.5f * lane_sum(D, [&](int d) { return (imm[d] * r[d]) * r[d]; });
+}
+
+// hmc_util.py:710-746
+B2_HD bool is_turning(int D, const float* imm, const float* r_left, const float* r_right, const float* r_sum) {
+    float l, r;
+    lane_sum2(D, [&](int d, float& a, float& b) {
+        const float s = r_sum[d] - (r_left[d] + r_right[d]) / 2.0f;
+        a = (imm[d] * r_left[d]) * s;
+        b = (imm[d] * r_right[d]) * s;
+    }, l, r);
+    return (l <= 0.0f) || (r <= 0.0f);
+}
+
+// first half of velocity_verlet (hmc_util.py:300-304): r_half and the new position
+B2_HD void leap_begin(int D, float eps, const float* imm, const float* z, const float* r, const float* g,
+                      float* z_out, float* r_half_out) {
+    const float half = 0.5f * eps;
+    B2_FOR_D(d, D) {
+        const float rh = r[d] - half * g[d];
+        r_half_out[d] = rh;
+        z_out[d] = z[d] + eps * (imm[d] * rh);
+    }
+}
+
+struct Tick {
+    const TickCfg& cfg;
+    ChainCtl& c;
+    ChainVecs vs;
+    OutBufs out;
+    int chain, C;
+
+    B2_HD float* v(int f) const { return vs.v(f); }
+    B2_HD int D() const { return cfg.D; }
+
+    B2_HD void copy(int dst, int src) const {
+        float* a = v(dst); const float* b = v(src);
+        B2_FOR_D(d, cfg.D) a[d] = b[d];
+    }
+
+    // ---------------------------------------------------------------- momentum (hmc.py:92-110)
+    B2_HD void draw_momentum(Key k, float* r) const {
+        if (cfg.model_built) k = split_at(k, 0);           // one-block dict -> split(key, 1)[0]
+        const float* sm = v(V_SQRTM);
+        B2_FOR_D(d, cfg.D) r[d] = sm[d] * normal_at(k, (uint32_t)d);
+    }
+
+    // ---------------------------------------------------------------- init (infer/util.py:417-481)
+    B2_HD void init_draw() {
+        Key key = mk(c.k_init);
+        Key sub = split_at(key, 1); key = split_at(key, 0);
+        float* z = v(V_ZS);
+        for (int s = 0; s < cfg.n_sites; ++s) {
+            const int off = cfg.site_off[s], n = cfg.site_size[s];
+            B2_FOR_D(j, n) z[off + j] = uniform_at(sub, (uint32_t)j, -cfg.init_radius, cfg.init_radius);
+            sub = split_at(key, 1); key = split_at(key, 0);
+        }
+        st(c.k_init, key);
+    }
+
+    // Called once per chain before the first gradient.  ``chain_key`` is the row of
+    // split(user_key, C) (mcmc.py:670-671); z0 != null means init_params were supplied.
+    B2_HD void begin(Key chain_key, const float* z0) {
+        Key rng = split_at(chain_key, 0), k_init = split_at(chain_key, 1);      // hmc.py:744-750
+        st(c.key, rng); st(c.k_init, k_init);
+        c.i = 0; c.init_tries = 0; c.init_failed = 0; c.n_collected = 0; c.total_leapfrogs = 0ull;
+        c.num_steps = 0; c.accept_prob = 0.0f; c.mean_accept_prob = 0.0f; c.diverging = 0;
+        if (z0) { float* z = v(V_ZS); B2_FOR_D(d, cfg.D) z[d] = z0[d]; }
+        else init_draw();
+        c.phase = PH_INIT;
+    }
+
+    // ---------------------------------------------------------------- init_kernel (hmc.py:193-362)
+    B2_HD void finish_init(float u, const float* g) {
+        copy(V_Z, V_ZS);
+        float* gg = v(V_G);
+        B2_FOR_D(d, cfg.D) gg[d] = g[d];
+        c.pe = u;
+        const Key rng = mk(c.key);
+        const Key k_hmc = split_at(rng, 0), k_wa = split_at(rng, 1), k_mom = split_at(rng, 2);   // :335
+        const Key wk = split_at(k_wa, 0), k_ss = split_at(k_wa, 1);                           // hmc_util.py:565
+        st(c.key, k_hmc); st(c.wa_key, wk);
+        float* imm = v(V_IMM); float* sm = v(V_SQRTM); float* mean = v(V_WF_MEAN); float* m2 = v(V_WF_M2);
+        B2_FOR_D(d, cfg.D) { imm[d] = 1.0f; sm[d] = 1.0f; mean[d] = 0.0f; m2[d] = 0.0f; }
+        c.mm_n = 0; c.window_idx = 0;
+        c.step_size = cfg.init_step_size;
+        // initial energy uses a throw-away momentum (hmc.py:340-343)
+        float* r = v(V_R0);
+        draw_momentum(k_mom, r);
+        c.energy = c.pe + kinetic(cfg.D, imm, r);
+        if (cfg.adapt_step && cfg.find_heuristic) { heur_begin(k_ss, 1); return; }
+        da_reinit(d_log(10.0f * c.step_size));                                               // :576
+        begin_transition();
+    }
+
+    B2_HD void da_reinit(float prox) { c.da_x_t = 0.0f; c.da_x_avg = 0.0f; c.da_g_avg = 0.0f; c.da_t = 0; c.da_prox = prox; }
+
+    // ---------------------------------------------------------------- find_reasonable_step_size
+    // hmc_util.py:314-384 as a resumable loop: each trial needs one leapfrog from (z, g).
+    B2_HD void heur_begin(Key k, int at_init) {
+        c.heur_step = c.step_size; c.heur_dir = 0; c.heur_last = 0; st(c.heur_key, k); c.heur_at_init = at_init;
+        heur_next();
+    }
+    B2_HD void heur_next() {
+        const float tiny = 1.17549435e-38f, fmax = 3.40282347e+38f;
+        const bool not_small = (c.heur_step > tiny) || (c.heur_dir >= 0);
+        const bool not_large = (c.heur_step < fmax) || (c.heur_dir <= 0);
+        const bool go = not_small && not_large && ((c.heur_last == 0) || (c.heur_dir == c.heur_last));
+        if (!go) { heur_done(); return; }
+        const Key key = mk(c.heur_key);
+        const Key k_mom = split_at(key, 1); st(c.heur_key, split_at(key, 0));
+        const float scale = (c.heur_dir > 0) ? 2.0f : ((c.heur_dir < 0) ? 0.5f : 1.0f);
+        c.heur_step = scale * c.heur_step;
+        // NB: the reference hands *inverse_mass_matrix* to momentum_generator here
+        // (hmc_util.py:355 vs hmc.py:92), so r = M^-1 * eps, not M^1/2 * eps.
+        float* r0 = v(V_R0);
+        { Key km = cfg.model_built ? split_at(k_mom, 0) : k_mom; const float* imm = v(V_IMM);
+          B2_FOR_D(d, cfg.D) r0[d] = imm[d] * normal_at(km, (uint32_t)d); }
+        leap_begin(cfg.D, c.heur_step, v(V_IMM), v(V_Z), r0, v(V_G), v(V_ZS), v(V_RS));
+        c.phase = PH_HEUR;
+    }
+    B2_HD void on_heur(float u, const float* g) {
+        const float half = 0.5f * c.heur_step;
+        float* rs = v(V_RS);
+        B2_FOR_D(d, cfg.D) rs[d] = rs[d] - half * g[d];
+        const float e_cur = kinetic(cfg.D, v(V_IMM), v(V_R0)) + c.pe;
+        const float e_new = kinetic(cfg.D, v(V_IMM), rs) + u;
+        const float delta = e_new - e_cur;
+        const int new_dir = (d_log(0.8f) < -delta) ? 1 : -1;
+        c.heur_last = c.heur_dir; c.heur_dir = new_dir;
+        heur_next();
+    }
+    B2_HD void heur_done() {
+        c.step_size = c.heur_step;
+        if (c.heur_at_init) da_reinit(d_log(10.0f * c.step_size));
+        else { da_reinit(d_log(10.0f) + d_log(c.step_size)); collect(c.heur_t); }
+        begin_transition();
+    }
+
+    // ---------------------------------------------------------------- sample_kernel (hmc.py:459-530)
+    B2_HD void begin_transition() {
+        if (c.i >= cfg.total_iters) { c.phase = PH_DONE; return; }
+        const Key key = mk(c.key);
+        const Key k_mom = split_at(key, 1), k_tr = split_at(key, 2);
+        st(c.key_next, split_at(key, 0));
+        float* r = v(V_R0);
+        draw_momentum(k_mom, r);
+        c.eps = c.step_size;
+        c.energy0 = c.pe + kinetic(cfg.D, v(V_IMM), r);
+        if (cfg.algo == 1) { hmc_begin(k_tr); return; }
+        // build_tree root (hmc_util.py:1129-1153)
+        const float* z = v(V_Z); const float* g = v(V_G);
+        float *zl = v(V_ZL), *rl = v(V_RL), *gl = v(V_GL), *zr = v(V_ZR), *rr = v(V_RR), *gr = v(V_GR);
+        float *zp = v(V_ZP), *gp = v(V_GP), *rs = v(V_RSUM);
+        B2_FOR_D(d, cfg.D) {
+            const float zz = z[d], gg = g[d], rv = r[d];
+            zl[d] = zz; zr[d] = zz; zp[d] = zz; gl[d] = gg; gr[d] = gg; gp[d] = gg; rl[d] = rv; rr[d] = rv; rs[d] = rv;
+        }
+        c.depth = 0; c.n_total = 0; c.turning = 0; c.t_div = 0; c.weight = 0.0f; c.sum_acc = 0.0f;
+        c.prop_pe = c.pe; c.prop_energy = c.energy0;
+        c.max_depth = (c.i < cfg.num_warmup) ? cfg.md_warm : cfg.md_post;
+        st(c.k_loop, k_tr);
+        if (c.depth < c.max_depth) begin_doubling(); else finish_transition();
+    }
+
+    // one iteration of build_tree's while loop up to the first leapfrog (hmc_util.py:1159-1162, :920)
+    B2_HD void begin_doubling() {
+        const Key k = mk(c.k_loop);
+        const Key k_dir = split_at(k, 1), k_dbl = split_at(k, 2);
+        st(c.k_loop, split_at(k, 0));
+        c.going_right = (uniform01_at(k_dir, 0) < 0.5f) ? 1 : 0;
+        st(c.k_sub, split_at(k_dbl, 0)); st(c.k_fin, split_at(k_dbl, 1));
+        c.n_sub = 0; c.sub_div = 0; c.sub_weight = 0.0f; c.sub_sum_acc = 0.0f;
+        const float e = c.going_right ? c.eps : -c.eps;
+        if (c.going_right) leap_begin(cfg.D, e, v(V_IMM), v(V_ZR), v(V_RR), v(V_GR), v(V_ZS), v(V_RS));
+        else leap_begin(cfg.D, e, v(V_IMM), v(V_ZL), v(V_RL), v(V_GL), v(V_ZS), v(V_RS));
+        c.phase = PH_LEAF;
+    }
+
+    // one iteration of _iterative_build_subtree's loop body, after the gradient arrived
+    B2_HD void on_leaf(float u, const float* g) {
+        const int Dn = cfg.D;
+        const float e = c.going_right ? c.eps : -c.eps;
+        const float half = 0.5f * e;
+        const float* imm = v(V_IMM);
+        float *zs = v(V_ZS), *rs = v(V_RS), *gs = v(V_GS);
+        B2_FOR_D(d, Dn) { const float gg = g[d]; gs[d] = gg; rs[d] = rs[d] - half * gg; }
+        c.total_leapfrogs += 1ull;
+        // _build_basetree (hmc_util.py:866-875)
+        const float energy_new = u + kinetic(Dn, imm, rs);
+        float delta = energy_new - c.energy0;
+        if (is_nan(delta)) delta = f_inf();
+        const float leaf_w = -delta;
+        const int leaf_div = (delta > 1000.0f) ? 1 : 0;
+        const float leaf_acc = clip_max1(d_exp(-delta));
+        const Key ks = mk(c.k_sub);
+        const Key k_leaf = split_at(ks, 1); st(c.k_sub, split_at(ks, 0));
+        const int leaf_idx = c.n_sub;
+        float *zps = v(V_ZPS), *gps = v(V_GPS), *rsum_s = v(V_RSUMS);
+        if (leaf_idx == 0) {
+            B2_FOR_D(d, Dn) { zps[d] = zs[d]; gps[d] = gs[d]; rsum_s[d] = rs[d]; }
+            c.sub_prop_pe = u; c.sub_prop_energy = energy_new;
+            c.sub_weight = leaf_w; c.sub_sum_acc = leaf_acc;
+        } else {                                                   // _combine_tree, uniform kernel
+            const float p = d_expit(leaf_w - c.sub_weight);
+            const bool take = uniform01_at(k_leaf, 0) < p;
+            if (take) {
+                B2_FOR_D(d, Dn) { zps[d] = zs[d]; gps[d] = gs[d]; }
+                c.sub_prop_pe = u; c.sub_prop_energy = energy_new;
+            }
+            B2_FOR_D(d, Dn) rsum_s[d] = rsum_s[d] + rs[d];
+            c.sub_weight = d_logaddexp(c.sub_weight, leaf_w);
+            c.sub_sum_acc = c.sub_sum_acc + leaf_acc;
+        }
+        c.sub_div = leaf_div;
+        c.n_sub = leaf_idx + 1;
+        // checkpoints + iterative U-turn (hmc_util.py:941-981, 1034-1058)
+        const uint32_t n = (uint32_t)leaf_idx;
+        const int idx_max = popc32(n >> 1);
+        const int idx_min = idx_max - popc32((~n & (n + 1u)) - 1u) + 1;
+        if ((leaf_idx & 1) == 0) {
+            float* cr = v(V_CKPT_R + idx_max); float* cs = v(V_CKPT_RSUM + idx_max);
+            B2_FOR_D(d, Dn) { cr[d] = rs[d]; cs[d] = rsum_s[d]; }
+        }
+        bool sub_turning = false;
+        for (int i = idx_max; i >= idx_min && !sub_turning; --i) {
+            const float* cr = v(V_CKPT_R + i); const float* cs = v(V_CKPT_RSUM + i);
+            float l, r;
+            lane_sum2(Dn, [&](int d, float& a, float& b) {
+                const float sub = (rsum_s[d] - cs[d]) + cr[d];
+                const float s = sub - (cr[d] + rs[d]) / 2.0f;
+                a = (imm[d] * cr[d]) * s;
+                b = (imm[d] * rs[d]) * s;
+            }, l, r);
+            sub_turning = (l <= 0.0f) || (r <= 0.0f);
+        }
+        if (c.n_sub < (1 << c.depth) && !sub_turning && !c.sub_div) {      // next leaf of this subtree
+            leap_begin(Dn, e, imm, zs, rs, gs, zs, rs);
+            return;
+        }
+        finish_doubling(sub_turning);
+    }
+
+    // _combine_tree with the biased kernel (hmc_util.py:936-938, 767-848)
+    B2_HD void finish_doubling(bool sub_turning) {
+        const int Dn = cfg.D;
+        const float *zs = v(V_ZS), *rs = v(V_RS), *gs = v(V_GS), *rsum_s = v(V_RSUMS);
+        float *zo = v(c.going_right ? V_ZR : V_ZL), *ro = v(c.going_right ? V_RR : V_RL), *go = v(c.going_right ? V_GR : V_GL);
+        float* rsum = v(V_RSUM);
+        B2_FOR_D(d, Dn) { zo[d] = zs[d]; ro[d] = rs[d]; go[d] = gs[d]; rsum[d] = rsum[d] + rsum_s[d]; }
+        float p = clip_max1(d_exp(c.sub_weight - c.weight));
+        if (sub_turning || c.sub_div) p = 0.0f;
+        const bool turning = sub_turning || is_turning(Dn, v(V_IMM), v(V_RL), v(V_RR), rsum);
+        const bool take = uniform01_at(mk(c.k_fin), 0) < p;
+        if (take) {
+            copy(V_ZP, V_ZPS); copy(V_GP, V_GPS);
+            c.prop_pe = c.sub_prop_pe; c.prop_energy = c.sub_prop_energy;
+        }
+        c.depth += 1;
+        c.weight = d_logaddexp(c.weight, c.sub_weight);
+        c.t_div = c.sub_div; c.turning = turning ? 1 : 0;
+        c.sum_acc = c.sum_acc + c.sub_sum_acc;
+        c.n_total += c.n_sub;
+        if (c.depth < c.max_depth && !c.turning && !c.t_div) begin_doubling();
+        else finish_transition();
+    }
+
+    // ---------------------------------------------------------------- plain HMC (hmc.py:364-414)
+    B2_HD void hmc_begin(Key k_tr) {
+        st(c.k_fin, k_tr);
+        int n = cfg.hmc_num_steps;
+        if (n <= 0) {
+            n = (int)ceilf(cfg.traj_len / c.eps);
+            c.eps = cfg.traj_len / (float)n;
+        }
+        c.hmc_n = n; c.hmc_left = n;
+        if (n <= 0) { hmc_finish(c.pe); return; }
+        leap_begin(cfg.D, c.eps, v(V_IMM), v(V_Z), v(V_R0), v(V_G), v(V_ZS), v(V_RS));
+        c.phase = PH_HMC;
+    }
+    B2_HD void on_hmc(float u, const float* g) {
+        const float half = 0.5f * c.eps;
+        float *rs = v(V_RS), *gs = v(V_GS);
+        B2_FOR_D(d, cfg.D) { const float gg = g[d]; gs[d] = gg; rs[d] = rs[d] - half * gg; }
+        c.total_leapfrogs += 1ull;
+        c.hmc_left -= 1;
+        if (c.hmc_left > 0) { leap_begin(cfg.D, c.eps, v(V_IMM), v(V_ZS), rs, gs, v(V_ZS), rs); return; }
+        hmc_finish(u);
+    }
+    B2_HD void hmc_finish(float u_new) {
+        const float e_old = c.energy0;
+        const float e_new = (c.hmc_n > 0) ? (u_new + kinetic(cfg.D, v(V_IMM), v(V_RS))) : e_old;
+        float delta = e_new - e_old;
+        if (is_nan(delta)) delta = f_inf();
+        const float acc = clip_max1(d_exp(-delta));
+        const bool take = (uniform01_at(mk(c.k_fin), 0) < acc) && (c.hmc_n > 0);
+        if (take) { copy(V_ZP, V_ZS); copy(V_GP, V_GS); c.prop_pe = u_new; c.prop_energy = e_new; }
+        else { copy(V_ZP, V_Z); copy(V_GP, V_G); c.prop_pe = c.pe; c.prop_energy = e_old; }
+        c.t_div = (delta > 1000.0f) ? 1 : 0;
+        c.n_total = c.hmc_n;
+        finish_transition_common(acc);
+    }
+
+    // ---------------------------------------------------------------- end of sample_kernel
+    B2_HD void finish_transition() {
+        finish_transition_common(c.sum_acc / (float)c.n_total);     // hmc.py:441
+    }
+    B2_HD void finish_transition_common(float accept_prob) {
+        copy(V_Z, V_ZP); copy(V_G, V_GP);
+        c.pe = c.prop_pe; c.energy = c.prop_energy;
+        c.num_steps = c.n_total; c.accept_prob = accept_prob; c.diverging = c.t_div;
+        const int t = c.i;
+        const bool in_warmup = t < cfg.num_warmup;
+        const int itr = t + 1;
+        const int n = in_warmup ? itr : (itr - cfg.num_warmup);
+        c.mean_accept_prob = c.mean_accept_prob + (accept_prob - c.mean_accept_prob) / (float)n;   // :511-513
+        c.i = itr; st(c.key, mk(c.key_next));
+        c.heur_t = t;
+        if (in_warmup && adapt_update(t, accept_prob)) return;     // heuristic pending: heur_done() collects
+        collect(t);
+        begin_transition();
+    }
+
+    // fori_collect (numpyro/util.py:386-403): iteration t fills slot (t - start) / thinning; the
+    // last writer of a slot wins, i.e. the iteration with (t - start + 1) % thinning == 0.
+    B2_HD void collect(int t) {
+        if (t < cfg.collect_start || cfg.S <= 0) return;
+        const int rel = t - cfg.collect_start;
+        if ((rel + 1) % cfg.thinning != 0) return;
+        const int idx = rel / cfg.thinning;
+        if (idx >= cfg.S) return;
+        const size_t o = (size_t)chain * cfg.S + idx;
+        if (out.z) { float* dst = out.z + o * cfg.D; const float* z = v(V_Z); B2_FOR_D(d, cfg.D) dst[d] = z[d]; }
+        if (lane_first() == 0) {
+            if (out.diverging) out.diverging[o] = c.diverging;
+            if (out.num_steps) out.num_steps[o] = c.num_steps;
+            if (out.accept_prob) out.accept_prob[o] = c.accept_prob;
+            if (out.mean_accept_prob) out.mean_accept_prob[o] = c.mean_accept_prob;
+            if (out.pe) out.pe[o] = c.pe;
+            if (out.energy) out.energy[o] = c.energy;
+            if (out.step_size) out.step_size[o] = c.step_size;
+        }
+        c.n_collected = idx + 1;
+    }
+
+    // ---------------------------------------------------------------- warmup_adapter.update_fn
+    // hmc_util.py:637-705.  Returns true when the step-size heuristic took over (a gradient is
+    // pending and begin_transition will be called from heur_done()).
+    B2_HD bool adapt_update(int t, float accept_prob) {
+        const Key wk = mk(c.wa_key);
+        const Key k_ss = split_at(wk, 1); st(c.wa_key, split_at(wk, 0));
+        if (cfg.adapt_step) {
+            // dual_averaging.update_fn (hmc_util.py:113-128), t0 = 10, kappa = 0.75, gamma = 0.05
+            const float g = cfg.target_accept - accept_prob;
+            const int tt = c.da_t + 1;
+            const float tf = (float)(tt + 10);
+            c.da_g_avg = (1.0f - 1.0f / tf) * c.da_g_avg + g / tf;
+            c.da_x_t = c.da_prox - (sqrtf((float)tt) / 0.05f) * c.da_g_avg;
+            const float w = d_pow((float)tt, -0.75f);
+            c.da_x_avg = (1.0f - w) * c.da_x_avg + w * c.da_x_t;
+            c.da_t = tt;
+            const float ls = (t == cfg.num_warmup - 1) ? c.da_x_avg : c.da_x_t;
+            float s = d_exp(ls);
+            if (s < 1.17549435e-38f) s = 1.17549435e-38f;           // jnp.clip(step, tiny, max)
+            if (s > 3.40282347e+38f) s = 3.40282347e+38f;
+            c.step_size = s;
+        }
+        const bool middle = (c.window_idx > 0) && (c.window_idx < cfg.num_windows - 1);
+        const int Dn = cfg.D;
+        if (cfg.adapt_mass && middle) {                              // welford update (:178-195)
+            const float* z = v(V_Z); float* mean = v(V_WF_MEAN); float* m2 = v(V_WF_M2);
+            c.mm_n += 1;
+            const float nf = (float)c.mm_n;
+            B2_FOR_D(d, Dn) {
+                const float pre = z[d] - mean[d];
+                const float mu = mean[d] + pre / nf;
+                const float post = z[d] - mu;
+                mean[d] = mu; m2[d] = m2[d] + pre * post;
+            }
+        }
+        const int widx = (c.window_idx < cfg.num_windows) ? c.window_idx : (cfg.num_windows - 1);
+        const bool at_end = (t == cfg.window_end[widx]);
+        if (at_end) c.window_idx += 1;
+        if (!(at_end && middle)) return false;
+        if (cfg.adapt_mass) {                                        // mm_final (:197-237) + re-init
+            float* imm = v(V_IMM); float* sm = v(V_SQRTM); float* mean = v(V_WF_MEAN); float* m2 = v(V_WF_M2);
+            const float nf = (float)c.mm_n;
+            const float nm1 = (float)(c.mm_n - 1);
+            const float n5 = (float)(c.mm_n + 5);
+            const float scale = nf / n5;
+            const float shrink = 1e-3f * (5.0f / n5);
+            B2_FOR_D(d, Dn) {
+                float cov = m2[d] / nm1;
+                if (cfg.regularize) cov = scale * cov + shrink;
+                imm[d] = cov;
+                sm[d] = 1.0f / sqrtf(cov);
+                mean[d] = 0.0f; m2[d] = 0.0f;
+            }
+            c.mm_n = 0;
+        }
+        if (cfg.adapt_step) {
+            if (cfg.find_heuristic) { heur_begin(k_ss, 0); return true; }
+            da_reinit(d_log(10.0f) + d_log(c.step_size));
+        }
+        return false;
+    }
+
+    // ---------------------------------------------------------------- dispatcher
+    // Feed the potential/gradient evaluated at V_ZS; on return either phase == PH_DONE or V_ZS
+    // holds the next position to evaluate.
+    B2_HD void advance(float u, const float* g) {
+        switch (c.phase) {
+        case PH_INIT: {
+            const bool bad = !is_finite(u) || lane_any(cfg.D, [&](int d) { return !is_finite(g[d]); });
+            c.init_tries += 1;
+            if (bad && !cfg.init_given && c.init_tries < 100) { init_draw(); return; }
+            if (bad) c.init_failed = 1;
+            finish_init(u, g);
+            return;
+        }
+        case PH_LEAF: on_leaf(u, g); return;
+        case PH_HMC: on_hmc(u, g); return;
+        case PH_HEUR: on_heur(u, g); return;
+        default: return;
+        }
+    }
+};
+
+}  // namespace b2

@@ -121,7 +121,9 @@ def find_reasonable_step_size(potential: Callable, imm, sqrt_m, z, pe, g, init_s
                 break
             key, k_mom = prng.split(key)
             step = F(F(2.0) ** direction * step)
-            r = (sqrt_m * prng.normal(momentum_key_fn(k_mom), d)).astype(F)
+            # NB: the reference passes inverse_mass_matrix as momentum_generator's mass_matrix_sqrt
+            # argument here (hmc_util.py:355), so r = M^-1 * eps.
+            r = (imm * prng.normal(momentum_key_fn(k_mom), d)).astype(F)
             _, r_new, pe_new, _ = leapfrog(potential, step, imm, z, r, g)
             e_cur = F(kinetic_energy(imm, r) + pe)
             e_new = F(kinetic_energy(imm, r_new) + pe_new)
