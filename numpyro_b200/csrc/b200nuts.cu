@@ -1,0 +1,487 @@
+// C ABI of the B200 NUTS/HMC engine (declared in include/b200nuts.h) + the small kernels:
+// chain begin/resume, regime R1 (one warp per chain, whole run in one launch), parity hooks.
+// The streaming engine (regime R2) lives in stream_engine.cuh.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false --extended-lambda -lineinfo
+// (-fmad=false: the tree/adaptation bookkeeping follows the det-f32 convention; hot loops issue
+// their FMAs explicitly).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <mutex>
+#include "engine.cuh"
+#include "stream_engine.cuh"
+
+using namespace b2;
+
+// ------------------------------------------------------------------------------------------------
+struct B200Nuts {
+    B200NutsConfig cfg; FamilySpec fam; SiteLayout sites; TickCfg tick;
+    int C = 0, D = 0, Dp = 0, regime = 0, device = 0, num_sms = 0;
+    bool inited = false;
+    ChainCtl* ctl = nullptr; float* vecs = nullptr; float* gtmp = nullptr; float* scratch = nullptr;
+    uint32_t* keys = nullptr;
+    // R2
+    float* partial = nullptr; float* beta = nullptr; StreamSync* sync = nullptr;
+    int grid = 0, rho = 1, stages = 4, tile_rows = 192, dpl = 0, vecs_in_smem = 0; size_t smem = 0;
+    long long launches = 0;
+    std::string err;
+    std::mutex mu;
+};
+
+static std::string g_create_err;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return B200NUTS_ECUDA;                                                                 \
+        }                                                                                          \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// small kernels
+__global__ void k_chain_begin(TickCfg cfg, ChainCtl* ctl, float* vecs, int C, int Dp, const uint32_t* keys,
+                              const float* z0) {
+    const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (chain >= C) return;
+    ChainCtl c; memset(&c, 0, sizeof(c));
+    ChainVecs cv; cv.base = vecs + (size_t)chain * Dp; cv.field_stride = C * Dp;
+    OutBufs none; memset(&none, 0, sizeof(none));
+    Tick t{cfg, c, cv, none, chain, C};
+    Key k; k.a = keys[2 * chain]; k.b = keys[2 * chain + 1];
+    t.begin(k, z0 ? z0 + (size_t)chain * cfg.D : nullptr);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) ctl[chain] = c;
+}
+
+__global__ void k_chain_resume(TickCfg cfg, ChainCtl* ctl, float* vecs, int C, int Dp) {
+    const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (chain >= C) return;
+    ChainCtl c = ctl[chain];
+    __syncwarp();
+    if (c.phase != PH_DONE || c.init_failed || c.i >= cfg.total_iters) return;
+    ChainVecs cv; cv.base = vecs + (size_t)chain * Dp; cv.field_stride = C * Dp;
+    OutBufs none; memset(&none, 0, sizeof(none));
+    Tick t{cfg, c, cv, none, chain, C};
+    t.begin_transition();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) ctl[chain] = c;
+}
+
+// Regime R1: each warp runs its chain to completion; the potential is evaluated inside the warp.
+__global__ void __launch_bounds__(128) k_warp_run(TickCfg cfg, FamilySpec fam, OutBufs out, ChainCtl* ctl, float* vecs,
+                                                  float* gtmp, float* scratch, long long scratch_stride, int C, int Dp) {
+    const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (chain >= C) return;
+    ChainCtl c = ctl[chain];
+    ChainVecs cv; cv.base = vecs + (size_t)chain * Dp; cv.field_stride = C * Dp;
+    Tick t{cfg, c, cv, out, chain, C};
+    float* g = gtmp + (size_t)chain * Dp;
+    float* scr = scratch ? scratch + (size_t)chain * scratch_stride : nullptr;
+    while (c.phase != PH_DONE) {
+        __syncwarp();
+        float u;
+        potential_inwarp(fam, cv.v(V_ZS), scr, u, g);
+        __syncwarp();
+        t.advance(u, g);
+    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) ctl[chain] = c;
+}
+
+__global__ void k_potential_warp(FamilySpec fam, const float* z, float* U, float* g, float* scratch,
+                                 long long scratch_stride, int C) {
+    const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (chain >= C) return;
+    float u;
+    potential_inwarp(fam, z + (size_t)chain * fam.D, scratch ? scratch + (size_t)chain * scratch_stride : nullptr, u,
+                     g + (size_t)chain * fam.D);
+    if ((threadIdx.x & 31) == 0) U[chain] = u;
+}
+
+// velocity_verlet halves for the leapfrog parity hook (numpyro/infer/hmc_util.py:289-309)
+__global__ void k_leap_pre(int C, int D, const float* eps, const float* imm, float* z, float* r, const float* g) {
+    const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (chain >= C) return;
+    const size_t o = (size_t)chain * D;
+    leap_begin(D, eps[chain], imm + o, z + o, r + o, g + o, z + o, r + o);
+}
+__global__ void k_leap_post(int C, int D, const float* eps, float* r, const float* g) {
+    const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (chain >= C) return;
+    const size_t o = (size_t)chain * D;
+    const float half = 0.5f * eps[chain];
+    B2_FOR_D(d, D) r[o + d] = r[o + d] - half * g[o + d];
+}
+
+// postprocess_fn: constrained latent sites (flat order) followed by the deterministic block
+__global__ void k_constrain(FamilySpec f, const float* z, long long n, float* out, int Dc) {
+    const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const float* zr = z + row * f.D; float* o = out + row * Dc;
+    if (f.family == FAM_DIAG_GAUSSIAN) { B2_FOR_D(d, f.D) o[d] = zr[d]; return; }
+    if (f.family == FAM_EIGHT_SCHOOLS) {
+        const int J = f.D - 2;
+        const float tau = expf(zr[1]);
+        B2_FOR_D(d, f.D) o[d] = (d == 1) ? tau : zr[d];
+        B2_FOR_D(j, J) o[f.D + j] = zr[0] + tau * zr[2 + j];        // theta = mu + tau * theta_base
+        return;
+    }
+    B2_FOR_D(d, f.D) {
+        const bool pos = (f.off_lambda >= 0 && d >= f.off_lambda && d < f.off_lambda + f.Dx) ||
+                         (d == f.off_tau) || (d == f.off_prec);
+        o[d] = pos ? expf(zr[d]) : zr[d];
+    }
+    if (Dc > f.D) { B2_FOR_D(j, f.Dx) o[f.D + j] = glm_scale_at(f, zr, j) * zr[f.off_u + j]; }   // betas
+}
+
+__global__ void k_lgamma_sum(const float* y, long long n, double* out) {
+    double a = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        a += lgamma((double)y[i] + 1.0);
+    for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, a);
+}
+
+__global__ void k_prng_split(const uint32_t* keys, long long n_keys, int num, uint32_t* out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_keys * num) return;
+    const long long kidx = i / num; const uint32_t j = (uint32_t)(i % num);
+    Key k; k.a = keys[2 * kidx]; k.b = keys[2 * kidx + 1];
+    const Key o = split_at(k, j);
+    out[2 * i] = o.a; out[2 * i + 1] = o.b;
+}
+__global__ void k_prng_draw(int kind, uint32_t ka, uint32_t kb, long long n, float lo, float hi, void* out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Key k; k.a = ka; k.b = kb;
+    if (kind == 0) ((uint32_t*)out)[i] = bits_at(k, (uint32_t)i);
+    else if (kind == 1) ((float*)out)[i] = uniform_at(k, (uint32_t)i, lo, hi);
+    else ((float*)out)[i] = normal_at(k, (uint32_t)i);
+}
+__global__ void k_detmath(int op, const float* x, long long n, float* out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = x[i];
+    out[i] = op == 0 ? d_exp(v) : op == 1 ? d_log(v) : op == 2 ? d_log1p(v) : op == 3 ? d_expit(v) : d_erfinv(v);
+}
+
+// ------------------------------------------------------------------------------------------------
+static int choose_rho(int D) {
+    static const int cand[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 48};
+    for (int r : cand) {
+        bool seen[4] = {false, false, false, false}; bool okk = true;
+        for (int k = 0; k < 4 && okk; ++k) {
+            const int off = (int)(((long long)D * r * k) % 32);
+            if (off % 8 != 0 || seen[off / 8]) okk = false; else seen[off / 8] = true;
+        }
+        if (okk) return r;
+    }
+    return 1;
+}
+
+static int stream_launch(B200Nuts* h, int mode, const OutBufs& out, const float* z_in, float* u_out, float* g_out,
+                         cudaStream_t st) {
+    StreamParams p; memset(&p, 0, sizeof(p));
+    p.cfg = h->tick; p.cfg.D = h->D; p.fam = h->fam; p.out = out; p.C = h->C; p.Dp = h->Dp; p.mode = mode;
+    p.ctl = h->ctl; p.vecs = h->vecs; p.partial = h->partial; p.beta = h->beta; p.sync = h->sync;
+    p.z_in = z_in; p.u_out = u_out; p.g_out = g_out; p.rho = h->rho; p.stages = h->stages; p.tile_rows = h->tile_rows;
+    p.vecs_in_smem = h->vecs_in_smem; p.spin_limit = 6000000000LL;
+    CK(cudaMemsetAsync(h->sync, 0, sizeof(StreamSync), st));
+    void* args[] = {&p};
+    const void* fn = nullptr;
+    switch (h->dpl) {
+    case 2: fn = (const void*)stream_engine_kernel<2>; break;
+    case 4: fn = (const void*)stream_engine_kernel<4>; break;
+    case 7: fn = (const void*)stream_engine_kernel<7>; break;
+    default: fn = (const void*)stream_engine_kernel<8>; break;
+    }
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    CK(cudaLaunchCooperativeKernel(fn, dim3(h->grid), dim3(kStreamThreads), args, h->smem, st));
+    h->launches += 1;
+    return 0;
+}
+
+static int check_stream_abort(B200Nuts* h, cudaStream_t st) {
+    StreamSync s;
+    CK(cudaMemcpyAsync(&s, h->sync, sizeof(s), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (s.abort_flag) { h->err = "stream engine aborted: inter-pass exchange timed out"; return B200NUTS_ECUDA; }
+    return 0;
+}
+
+extern "C" {
+
+const char* b200nuts_last_error(const B200Nuts* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+int b200nuts_dim(const B200Nuts* h) { return h ? h->D : B200NUTS_EINVAL; }
+int b200nuts_regime(const B200Nuts* h) { return h ? h->regime : B200NUTS_EINVAL; }
+int64_t b200nuts_launch_count(const B200Nuts* h) { return h ? h->launches : 0; }
+
+int b200nuts_constrained_dim(const B200Nuts* h) {
+    if (!h) return B200NUTS_EINVAL;
+    if (h->fam.family == FAM_EIGHT_SCHOOLS) return h->D + (h->D - 2);
+    if (h->fam.family == FAM_GLM && (h->fam.off_lambda >= 0 || h->fam.gscale != SCALE_NONE)) return h->D + h->fam.Dx;
+    return h->D;
+}
+
+void b200nuts_destroy(B200Nuts* h) {
+    if (!h) return;
+    cudaFree(h->ctl); cudaFree(h->vecs); cudaFree(h->gtmp); cudaFree(h->scratch); cudaFree(h->keys);
+    cudaFree(h->partial); cudaFree(h->beta); cudaFree(h->sync);
+    delete h;
+}
+
+int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
+    if (!cfg || !out) { g_create_err = "null argument"; return B200NUTS_EINVAL; }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        g_create_err = "no CUDA device: the engine has no CPU fallback"; return B200NUTS_ECUDA;
+    }
+    B200Nuts* h = new B200Nuts();
+    h->cfg = *cfg;
+    std::string e = make_family(*cfg, h->fam, h->sites);
+    if (e.empty() && cfg->shard_count > 1) e = "row-sharded handles are not implemented yet";
+    if (!e.empty()) { g_create_err = e; delete h; return B200NUTS_EINVAL; }
+    h->C = cfg->num_chains; h->D = h->fam.D; h->Dp = (h->D + 3) & ~3;
+    make_tick_cfg(*cfg, h->fam, h->sites, 0, false, h->tick);
+    cudaGetDevice(&h->device);
+    cudaDeviceSetLimit(cudaLimitStackSize, 4096);      // per-chain state machine frames (tick.cuh)
+    cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
+    // regime
+    int regime = cfg->regime;
+    const bool glm = h->fam.family == FAM_GLM;
+    const bool stream_ok = glm && h->C <= kStreamCT && h->fam.Dx <= 64 && h->C <= h->num_sms;
+    if (regime == B200NUTS_REGIME_AUTO)
+        regime = (stream_ok && (long long)h->fam.N * h->fam.Dx >= (1LL << 20)) ? B200NUTS_REGIME_STREAM : B200NUTS_REGIME_WARP;
+    if (regime == B200NUTS_REGIME_STREAM && !stream_ok) {
+        g_create_err = "stream regime needs a GLM family with <= 8 chains and <= 64 columns"; delete h; return B200NUTS_EINVAL;
+    }
+    if (regime == B200NUTS_REGIME_GEMM) { g_create_err = "gemm regime is not implemented yet"; delete h; return B200NUTS_EINVAL; }
+    h->regime = regime;
+    auto fail = [&](const char* what, cudaError_t ce) {
+        g_create_err = std::string(what) + ": " + cudaGetErrorString(ce); b200nuts_destroy(h); return B200NUTS_ECUDA;
+    };
+    cudaError_t ce;
+    if ((ce = cudaMalloc(&h->ctl, sizeof(ChainCtl) * h->C)) != cudaSuccess) return fail("cudaMalloc ctl", ce);
+    if ((ce = cudaMalloc(&h->vecs, sizeof(float) * (size_t)V_COUNT * h->C * h->Dp)) != cudaSuccess) return fail("cudaMalloc vecs", ce);
+    if ((ce = cudaMalloc(&h->gtmp, sizeof(float) * (size_t)h->C * h->Dp)) != cudaSuccess) return fail("cudaMalloc gtmp", ce);
+    if ((ce = cudaMalloc(&h->keys, sizeof(uint32_t) * 2 * h->C)) != cudaSuccess) return fail("cudaMalloc keys", ce);
+    cudaMemset(h->vecs, 0, sizeof(float) * (size_t)V_COUNT * h->C * h->Dp);
+    cudaMemset(h->ctl, 0, sizeof(ChainCtl) * h->C);
+    if (glm && regime == B200NUTS_REGIME_WARP) {
+        const size_t stride = (size_t)h->fam.N + h->fam.Dx;
+        if ((ce = cudaMalloc(&h->scratch, sizeof(float) * stride * h->C)) != cudaSuccess) return fail("cudaMalloc scratch", ce);
+    }
+    if (glm && h->fam.likelihood == LIK_POISSON) {
+        double* d_acc = nullptr; double acc = 0.0;
+        if ((ce = cudaMalloc(&d_acc, 8)) != cudaSuccess) return fail("cudaMalloc", ce);
+        cudaMemset(d_acc, 0, 8);
+        k_lgamma_sum<<<296, 256>>>(h->fam.y, h->fam.N, d_acc);
+        ce = cudaMemcpy(&acc, d_acc, 8, cudaMemcpyDeviceToHost);
+        cudaFree(d_acc);
+        if (ce != cudaSuccess) return fail("lgamma sum", ce);
+        h->fam.nll_const = (float)acc;
+        h->launches += 1;
+    }
+    if (regime == B200NUTS_REGIME_STREAM) {
+        const int need = (h->fam.Dx + 7) / 8;
+        h->dpl = need <= 2 ? 2 : need <= 4 ? 4 : need <= 7 ? 7 : 8;
+        h->rho = choose_rho(h->fam.Dx);
+        h->tile_rows = (kMaxTileRows / (4 * h->rho)) * (4 * h->rho);
+        h->grid = h->num_sms;
+        int max_smem = 0;
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+        h->stages = 0;
+        for (int vs = 1; vs >= 0 && !h->stages; --vs)
+            for (int stg = 6; stg >= 2; --stg)
+                if (stream_smem_bytes(h->fam.Dx, h->Dp, stg, h->tile_rows, vs != 0) <= (size_t)max_smem) {
+                    h->stages = stg; h->vecs_in_smem = vs; break;
+                }
+        if (!h->stages) { g_create_err = "stream regime: shared memory budget exceeded"; b200nuts_destroy(h); return B200NUTS_EINVAL; }
+        h->smem = stream_smem_bytes(h->fam.Dx, h->Dp, h->stages, h->tile_rows, h->vecs_in_smem != 0);
+        if ((ce = cudaMalloc(&h->partial, sizeof(float) * (size_t)h->grid * kStreamCT * kGStride)) != cudaSuccess) return fail("cudaMalloc partial", ce);
+        if ((ce = cudaMalloc(&h->beta, sizeof(float) * kStreamCT * 64)) != cudaSuccess) return fail("cudaMalloc beta", ce);
+        if ((ce = cudaMalloc(&h->sync, sizeof(StreamSync))) != cudaSuccess) return fail("cudaMalloc sync", ce);
+        cudaMemset(h->beta, 0, sizeof(float) * kStreamCT * 64);
+        cudaMemset(h->partial, 0, sizeof(float) * (size_t)h->grid * kStreamCT * kGStride);
+    }
+    if ((ce = cudaDeviceSynchronize()) != cudaSuccess) return fail("create", ce);
+    *out = h;
+    return 0;
+}
+
+int b200nuts_init(B200Nuts* h, const uint32_t* keys, const float* z0, int32_t num_warmup, void* stream) {
+    if (!h || !keys || num_warmup < 0) return B200NUTS_EINVAL;
+    std::lock_guard<std::mutex> lk(h->mu);
+    cudaStream_t st = (cudaStream_t)stream;
+    std::string e = make_tick_cfg(h->cfg, h->fam, h->sites, num_warmup, z0 != nullptr, h->tick);
+    if (!e.empty()) { h->err = e; return B200NUTS_EINVAL; }
+    CK(cudaMemcpyAsync(h->keys, keys, sizeof(uint32_t) * 2 * h->C, cudaMemcpyHostToDevice, st));
+    const int blocks = (h->C + 3) / 4;
+    k_chain_begin<<<blocks, 128, 0, st>>>(h->tick, h->ctl, h->vecs, h->C, h->Dp, h->keys, z0);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    h->inited = true;
+    return 0;
+}
+
+int b200nuts_run(B200Nuts* h, const B200NutsRun* run, void* stream) {
+    if (!h || !run || run->thinning < 1 || run->upper < 0) return B200NUTS_EINVAL;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->inited) { h->err = "b200nuts_run called before b200nuts_init"; return B200NUTS_ESTATE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    h->tick.total_iters = run->upper;
+    h->tick.collect_start = run->collect_start; h->tick.thinning = run->thinning; h->tick.S = run->collection_size;
+    OutBufs out;
+    out.z = run->z; out.diverging = run->diverging; out.num_steps = run->num_steps; out.accept_prob = run->accept_prob;
+    out.mean_accept_prob = run->mean_accept_prob; out.pe = run->potential_energy; out.energy = run->energy;
+    out.step_size = run->step_size;
+    const int blocks = (h->C + 3) / 4;
+    k_chain_resume<<<blocks, 128, 0, st>>>(h->tick, h->ctl, h->vecs, h->C, h->Dp);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    if (h->regime == B200NUTS_REGIME_WARP) {
+        k_warp_run<<<blocks, 128, 0, st>>>(h->tick, h->fam, out, h->ctl, h->vecs, h->gtmp, h->scratch,
+                                           (long long)h->fam.N + h->fam.Dx, h->C, h->Dp);
+        CK(cudaGetLastError());
+        h->launches += 1;
+        return 0;
+    }
+    int rc = stream_launch(h, 0, out, nullptr, nullptr, nullptr, st);
+    if (rc) return rc;
+    return check_stream_abort(h, st);
+}
+
+int b200nuts_get_state(B200Nuts* h, B200NutsChainState* states, float* z, float* z_grad, float* inv_mass,
+                       float* mass_sqrt, float* wf_mean, float* wf_m2, void* stream) {
+    if (!h || !states) return B200NUTS_EINVAL;
+    std::lock_guard<std::mutex> lk(h->mu);
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<ChainCtl> ctl(h->C);
+    CK(cudaMemcpyAsync(ctl.data(), h->ctl, sizeof(ChainCtl) * h->C, cudaMemcpyDeviceToHost, st));
+    float* dst[6] = {z, z_grad, inv_mass, mass_sqrt, wf_mean, wf_m2};
+    const int fld[6] = {V_Z, V_G, V_IMM, V_SQRTM, V_WF_MEAN, V_WF_M2};
+    for (int k = 0; k < 6; ++k)
+        if (dst[k])
+            CK(cudaMemcpy2DAsync(dst[k], sizeof(float) * h->D, h->vecs + (size_t)fld[k] * h->C * h->Dp, sizeof(float) * h->Dp,
+                                 sizeof(float) * h->D, h->C, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int rc = 0;
+    for (int c = 0; c < h->C; ++c) {
+        ctl_to_public(ctl[c], states[c]);
+        if (ctl[c].init_failed) rc = B200NUTS_EINIT;
+    }
+    if (rc) h->err = "Cannot find valid initial parameters. Please check your model again.";
+    return rc;
+}
+
+int b200nuts_set_state(B200Nuts* h, const B200NutsChainState* states, const float* z, const float* z_grad,
+                       const float* inv_mass, const float* wf_mean, const float* wf_m2, int32_t num_warmup,
+                       void* stream) {
+    if (!h || !states || !z || !z_grad || !inv_mass) return B200NUTS_EINVAL;
+    std::lock_guard<std::mutex> lk(h->mu);
+    cudaStream_t st = (cudaStream_t)stream;
+    std::string e = make_tick_cfg(h->cfg, h->fam, h->sites, num_warmup, true, h->tick);
+    if (!e.empty()) { h->err = e; return B200NUTS_EINVAL; }
+    std::vector<ChainCtl> ctl(h->C);
+    for (int c = 0; c < h->C; ++c) public_to_ctl(states[c], ctl[c]);
+    std::vector<float> sqrtm((size_t)h->C * h->D);
+    for (size_t i = 0; i < sqrtm.size(); ++i) sqrtm[i] = 1.0f / sqrtf(inv_mass[i]);
+    CK(cudaMemcpyAsync(h->ctl, ctl.data(), sizeof(ChainCtl) * h->C, cudaMemcpyHostToDevice, st));
+    const float* src[6] = {z, z_grad, inv_mass, sqrtm.data(), wf_mean, wf_m2};
+    const int fld[6] = {V_Z, V_G, V_IMM, V_SQRTM, V_WF_MEAN, V_WF_M2};
+    for (int k = 0; k < 6; ++k)
+        if (src[k])
+            CK(cudaMemcpy2DAsync(h->vecs + (size_t)fld[k] * h->C * h->Dp, sizeof(float) * h->Dp, src[k], sizeof(float) * h->D,
+                                 sizeof(float) * h->D, h->C, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    h->inited = true;
+    return 0;
+}
+
+int b200nuts_potential_and_grad(B200Nuts* h, const float* z, float* U, float* g, void* stream) {
+    if (!h || !z || !U || !g) return B200NUTS_EINVAL;
+    std::lock_guard<std::mutex> lk(h->mu);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->regime == B200NUTS_REGIME_WARP) {
+        k_potential_warp<<<(h->C + 3) / 4, 128, 0, st>>>(h->fam, z, U, g, h->scratch, (long long)h->fam.N + h->fam.Dx, h->C);
+        CK(cudaGetLastError());
+        h->launches += 1;
+        return 0;
+    }
+    OutBufs none; memset(&none, 0, sizeof(none));
+    return stream_launch(h, 1, none, z, U, g, st);
+}
+
+int b200nuts_leapfrog(B200Nuts* h, const float* eps, const float* inv_mass, float* z, float* r, float* U, float* g,
+                      int32_t n_steps, void* stream) {
+    if (!h || !eps || !inv_mass || !z || !r || !U || !g || n_steps < 0) return B200NUTS_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = b200nuts_potential_and_grad(h, z, U, g, stream);
+    const int blocks = (h->C + 3) / 4;
+    for (int s = 0; s < n_steps && !rc; ++s) {
+        k_leap_pre<<<blocks, 128, 0, st>>>(h->C, h->D, eps, inv_mass, z, r, g);
+        rc = b200nuts_potential_and_grad(h, z, U, g, stream);
+        k_leap_post<<<blocks, 128, 0, st>>>(h->C, h->D, eps, r, g);
+        h->launches += 2;
+    }
+    if (!rc) CK(cudaGetLastError());
+    return rc;
+}
+
+int b200nuts_constrain(B200Nuts* h, const float* z, int64_t n, float* out, void* stream) {
+    if (!h || !z || !out || n < 0) return B200NUTS_EINVAL;
+    if (n == 0) return 0;
+    const int Dc = b200nuts_constrained_dim(h);
+    k_constrain<<<(unsigned)((n + 3) / 4), 128, 0, (cudaStream_t)stream>>>(h->fam, z, n, out, Dc);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+// ---- PRNG / det-math parity hooks: host in, host out -------------------------------------------
+static int hook_io(const void* in, size_t in_bytes, size_t out_bytes, void** d_in, void** d_out) {
+    *d_in = nullptr; *d_out = nullptr;
+    if (in_bytes && cudaMalloc(d_in, in_bytes) != cudaSuccess) return B200NUTS_ECUDA;
+    if (cudaMalloc(d_out, out_bytes) != cudaSuccess) { cudaFree(*d_in); return B200NUTS_ECUDA; }
+    if (in_bytes && cudaMemcpy(*d_in, in, in_bytes, cudaMemcpyHostToDevice) != cudaSuccess) return B200NUTS_ECUDA;
+    return 0;
+}
+static int hook_finish(void* host_out, size_t out_bytes, void* d_in, void* d_out) {
+    cudaError_t e = cudaMemcpy(host_out, d_out, out_bytes, cudaMemcpyDeviceToHost);
+    cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess) { g_create_err = cudaGetErrorString(e); return B200NUTS_ECUDA; }
+    return 0;
+}
+
+int b200nuts_prng_split(const uint32_t* keys, int64_t n_keys, int32_t num, uint32_t* out) {
+    if (!keys || !out || n_keys <= 0 || num <= 0) return B200NUTS_EINVAL;
+    void *di, *dout; const size_t ob = (size_t)n_keys * num * 8;
+    if (hook_io(keys, (size_t)n_keys * 8, ob, &di, &dout)) return B200NUTS_ECUDA;
+    const long long tot = n_keys * num;
+    k_prng_split<<<(unsigned)((tot + 255) / 256), 256>>>((const uint32_t*)di, n_keys, num, (uint32_t*)dout);
+    return hook_finish(out, ob, di, dout);
+}
+static int prng_draw(int kind, const uint32_t* key, int64_t n, float lo, float hi, void* out) {
+    if (!key || !out || n <= 0) return B200NUTS_EINVAL;
+    void *di, *dout;
+    if (hook_io(nullptr, 0, (size_t)n * 4, &di, &dout)) return B200NUTS_ECUDA;
+    k_prng_draw<<<(unsigned)((n + 255) / 256), 256>>>(kind, key[0], key[1], n, lo, hi, dout);
+    return hook_finish(out, (size_t)n * 4, di, dout);
+}
+int b200nuts_prng_bits(const uint32_t* key, int64_t n, uint32_t* out) { return prng_draw(0, key, n, 0, 1, out); }
+int b200nuts_prng_uniform(const uint32_t* key, int64_t n, float lo, float hi, float* out) { return prng_draw(1, key, n, lo, hi, out); }
+int b200nuts_prng_normal(const uint32_t* key, int64_t n, float* out) { return prng_draw(2, key, n, 0, 1, out); }
+int b200nuts_detmath(int32_t op, const float* x, int64_t n, float* out) {
+    if (!x || !out || n <= 0 || op < 0 || op > 4) return B200NUTS_EINVAL;
+    void *di, *dout;
+    if (hook_io(x, (size_t)n * 4, (size_t)n * 4, &di, &dout)) return B200NUTS_ECUDA;
+    k_detmath<<<(unsigned)((n + 255) / 256), 256>>>(op, (const float*)di, n, (float*)dout);
+    return hook_finish(out, (size_t)n * 4, di, dout);
+}
+
+}  // extern "C"

@@ -112,6 +112,7 @@ inline std::string make_tick_cfg(const B200NutsConfig& c, const FamilySpec& f, c
     t.md_warm = c.max_tree_depth_warmup > 0 ? c.max_tree_depth_warmup : 10;
     t.md_post = c.max_tree_depth > 0 ? c.max_tree_depth : 10;
     if (t.md_warm > kMaxDepthAlloc || t.md_post > kMaxDepthAlloc) return "max_tree_depth > 12 is not supported";
+    if (t.md_warm < 1 || t.md_post < 1) return "max_tree_depth must be >= 1";
     t.target_accept = c.target_accept_prob > 0 ? c.target_accept_prob : 0.8f;
     t.init_step_size = c.step_size > 0 ? c.step_size : 1.0f;
     t.adapt_step = c.adapt_step_size; t.adapt_mass = c.adapt_mass_matrix; t.regularize = c.regularize_mass_matrix;

@@ -31,7 +31,7 @@ struct FamilySpec {
     long long N; int32_t Dx;   // X [N, Dx] row-major, y [N]
     const float* X; const float* y;
     const float* aux0; const float* aux1;   // gaussian: mu, sigma; eight schools: sigma_j, y_j
-    const float* ylgam;        // poisson: lgamma(y + 1), precomputed at create()
+    float nll_const;           // poisson: sum_n lgamma(y_n + 1), precomputed at create()
     // GLM structure; offsets into z (-1 = site absent).  Sorted-site layouts:
     //   plain: coefs | horseshoe: lambdas, (prec_obs), tau, unscaled_betas | hierarchical: coefs, tau
     int32_t likelihood, off_lambda, off_tau, off_prec, off_u, gscale, g0, g1;
@@ -49,7 +49,7 @@ inline void lane_sync() {}
 #endif
 
 // ---- per-observation loss: value and d/d eta of the negative log-likelihood ------------------
-B2_HD void glm_loss(int lik, float eta, float y, float ylg, float& loss, float& dl) {
+B2_HD void glm_loss(int lik, float eta, float y, float& loss, float& dl) {
     if (lik == LIK_BERNOULLI) {          // binary_cross_entropy_with_logits (distributions/util.py:317-320)
         const float e = expf(-fabsf(eta));
         loss = fmaxf(eta, 0.0f) + log1pf(e) - eta * y;
@@ -57,7 +57,7 @@ B2_HD void glm_loss(int lik, float eta, float y, float ylg, float& loss, float& 
         dl = ((eta >= 0.0f) ? s : (1.0f - s)) - y;         // sigmoid(eta) - y
     } else if (lik == LIK_POISSON) {     // Poisson.log_prob (discrete.py:1388) with rate = exp(eta)
         const float r = expf(eta);
-        loss = r + ylg - y * eta;
+        loss = r - y * eta;                               // + lgamma(y+1): FamilySpec.nll_const
         dl = r - y;
     } else {                             // Normal: 0.5 * res^2 (precision applied in glm_finish)
         const float res = eta - y;
@@ -65,6 +65,28 @@ B2_HD void glm_loss(int lik, float eta, float y, float ylg, float& loss, float& 
         dl = res;
     }
 }
+
+#if defined(__CUDACC__)
+// Streaming-kernel variant: hardware ex2/lg2/rcp approximations (relative error ~1e-7, far inside
+// the rtol 1e-5 parity budget once summed over rows); no libm slow paths in the hot loop.
+__device__ __forceinline__ void glm_loss_fast(int lik, float eta, float y, float& loss, float& dl) {
+    if (lik == LIK_BERNOULLI) {
+        const float e = __expf(-fabsf(eta));
+        const float ope = 1.0f + e;
+        loss = (fmaxf(eta, 0.0f) - eta * y) + __logf(ope);
+        const float s = __fdividef(1.0f, ope);
+        dl = ((eta >= 0.0f) ? s : (1.0f - s)) - y;
+    } else if (lik == LIK_POISSON) {
+        const float r = __expf(eta);
+        loss = r - y * eta;
+        dl = r - y;
+    } else {
+        const float res = eta - y;
+        loss = 0.5f * res * res;
+        dl = res;
+    }
+}
+#endif
 
 B2_HD float glm_scale_at(const FamilySpec& f, const float* z, int j) {
     float s = 1.0f;
@@ -129,7 +151,7 @@ B2_HD void glm_finish(const FamilySpec& f, const float* z, float nll, const floa
         U = U + (prec - 3.0f * zp + 0.693147180559945309f);          // -[2 zp - prec - lgamma(3)] - zp
         if (lane_first() == 0) g[f.off_prec] = prec * nll - 0.5f * Nf + prec - 3.0f;
     } else {
-        U = U + nll;
+        U = U + (nll + f.nll_const);
     }
     u_out = U;
 }
@@ -189,7 +211,7 @@ B2_HD void potential_inwarp(const FamilySpec& f, const float* z, float* scratch,
         float eta = 0.0f;
         for (int j = 0; j < Dx; ++j) eta = fmaf(x[j], beta[j], eta);
         float loss, dl;
-        glm_loss(f.likelihood, eta, f.y[n], f.ylgam ? f.ylgam[n] : 0.0f, loss, dl);
+        glm_loss(f.likelihood, eta, f.y[n], loss, dl);
         resid[n] = dl;
         return loss;
     });

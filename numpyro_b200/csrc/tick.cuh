@@ -263,7 +263,7 @@ struct Tick {
         c.prop_pe = c.pe; c.prop_energy = c.energy0;
         c.max_depth = (c.i < cfg.num_warmup) ? cfg.md_warm : cfg.md_post;
         st(c.k_loop, k_tr);
-        if (c.depth < c.max_depth) begin_doubling(); else finish_transition();
+        begin_doubling();            // max_tree_depth >= 1 is validated on the host (keeps the call graph acyclic)
     }
 
     // one iteration of build_tree's while loop up to the first leapfrog (hmc_util.py:1159-1162, :920)
@@ -376,8 +376,8 @@ struct Tick {
             n = (int)ceilf(cfg.traj_len / c.eps);
             c.eps = cfg.traj_len / (float)n;
         }
+        if (!(n >= 1)) n = 1;         // keeps the call graph acyclic; ceil(L / eps) >= 1 for finite eps
         c.hmc_n = n; c.hmc_left = n;
-        if (n <= 0) { hmc_finish(c.pe); return; }
         leap_begin(cfg.D, c.eps, v(V_IMM), v(V_Z), v(V_R0), v(V_G), v(V_ZS), v(V_RS));
         c.phase = PH_HMC;
     }
@@ -392,11 +392,11 @@ struct Tick {
     }
     B2_HD void hmc_finish(float u_new) {
         const float e_old = c.energy0;
-        const float e_new = (c.hmc_n > 0) ? (u_new + kinetic(cfg.D, v(V_IMM), v(V_RS))) : e_old;
+        const float e_new = u_new + kinetic(cfg.D, v(V_IMM), v(V_RS));
         float delta = e_new - e_old;
         if (is_nan(delta)) delta = f_inf();
         const float acc = clip_max1(d_exp(-delta));
-        const bool take = (uniform01_at(mk(c.k_fin), 0) < acc) && (c.hmc_n > 0);
+        const bool take = uniform01_at(mk(c.k_fin), 0) < acc;
         if (take) { copy(V_ZP, V_ZS); copy(V_GP, V_GS); c.prop_pe = u_new; c.prop_energy = e_new; }
         else { copy(V_ZP, V_Z); copy(V_GP, V_G); c.prop_pe = c.pe; c.prop_energy = e_old; }
         c.t_div = (delta > 1000.0f) ? 1 : 0;

@@ -1,0 +1,195 @@
+"""Thin Python handle over the C ABI (include/b200nuts.h).
+
+PyTorch is used only as plumbing: it owns the device buffers (dataset, outputs) and the CUDA
+stream; every computation happens inside libb200nuts.so.  There is no CPU path -- constructing an
+``Engine`` without a GPU or without the built library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _capi
+
+_F32_FIELDS = ("accept_prob", "mean_accept_prob", "potential_energy", "energy", "step_size")
+_I32_FIELDS = ("diverging", "num_steps")
+ALL_FIELDS = ("z",) + _I32_FIELDS + _F32_FIELDS
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    """One handle = the chains that live on one GPU."""
+
+    def __init__(self, device="cuda:0", X=None, y=None, aux=None, **cfg):
+        if not torch.cuda.is_available():
+            raise EngineError("numpyro_b200 needs a CUDA device: the engine has no CPU fallback")
+        self.lib = _capi.load()
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        to = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float32).to(self.device).contiguous()
+        self.X, self.y, self.aux = to(X), to(y), to(aux)            # borrowed by the handle: keep alive
+        c = _capi.default_config(**cfg)
+        if self.X is not None:
+            c.X = self.X.data_ptr()
+            c.n_rows, c.n_cols = self.X.shape
+        if self.y is not None:
+            c.y = self.y.data_ptr()
+        if self.aux is not None:
+            c.aux = self.aux.data_ptr()
+        self.cfg = c
+        self.h = C.c_void_p()
+        rc = self.lib.b200nuts_create(C.byref(c), C.byref(self.h))
+        if rc != 0:
+            raise EngineError(f"b200nuts_create failed ({rc}): {self.lib.b200nuts_last_error(None).decode()}")
+        self.C = int(c.num_chains)
+        self.D = self.lib.b200nuts_dim(self.h)
+        self.Dc = self.lib.b200nuts_constrained_dim(self.h)
+        self.regime = self.lib.b200nuts_regime(self.h)
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            torch.cuda.synchronize(self.device)
+            self.lib.b200nuts_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise EngineError(f"{what} failed ({rc}): {self.lib.b200nuts_last_error(self.h).decode()}")
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ MCMCKernel.init
+    def init(self, keys, num_warmup: int, z0=None):
+        keys = np.ascontiguousarray(keys, np.uint32).reshape(self.C, 2)
+        self._z0 = None if z0 is None else torch.as_tensor(z0, dtype=torch.float32).to(self.device).contiguous().view(self.C, self.D)
+        self._check(self.lib.b200nuts_init(self.h, keys.ctypes.data_as(C.c_void_p), _ptr(self._z0), int(num_warmup),
+                                           self._stream()), "b200nuts_init")
+        self.num_warmup = int(num_warmup)
+
+    # ------------------------------------------------------------------ fori_collect
+    def run(self, upper: int, lower: int, thinning: int = 1, fields: Sequence[str] = ALL_FIELDS) -> Dict[str, torch.Tensor]:
+        S = max((upper - lower) // thinning, 0)
+        start = lower + (upper - lower) % thinning
+        out: Dict[str, torch.Tensor] = {}
+        run = _capi.Run(upper=int(upper), collect_start=int(start), thinning=int(thinning), collection_size=int(S))
+        for f in fields:
+            if f == "z":
+                t = torch.zeros((self.C, S, self.D), dtype=torch.float32, device=self.device)
+            elif f in _I32_FIELDS:
+                t = torch.zeros((self.C, S), dtype=torch.int32, device=self.device)
+            elif f in _F32_FIELDS:
+                t = torch.zeros((self.C, S), dtype=torch.float32, device=self.device)
+            else:
+                raise ValueError(f"unknown field {f!r}")
+            out[f] = t
+            setattr(run, f, t.data_ptr() if S > 0 else None)
+        self._check(self.lib.b200nuts_run(self.h, C.byref(run), self._stream()), "b200nuts_run")
+        return out
+
+    # ------------------------------------------------------------------ HMCState in / out
+    def state(self):
+        st = (_capi.ChainState * self.C)()
+        names = ("z", "z_grad", "inverse_mass_matrix", "mass_matrix_sqrt", "wf_mean", "wf_m2")
+        vec = {n: np.zeros((self.C, self.D), np.float32) for n in names}
+        rc = self.lib.b200nuts_get_state(self.h, C.cast(st, C.c_void_p), *[vec[n].ctypes.data_as(C.c_void_p) for n in names],
+                                         self._stream())
+        if rc == _capi.EINIT:
+            raise RuntimeError("Cannot find valid initial parameters. Please check your model again.")
+        self._check(rc, "b200nuts_get_state")
+        return st, vec
+
+    def set_state(self, st, vec, num_warmup: int):
+        arr = lambda n: None if vec.get(n) is None else np.ascontiguousarray(vec[n], np.float32).ctypes.data_as(C.c_void_p)
+        keep = {n: np.ascontiguousarray(v, np.float32) for n, v in vec.items() if v is not None}
+        ptr = lambda n: keep[n].ctypes.data_as(C.c_void_p) if n in keep else None
+        self._check(self.lib.b200nuts_set_state(self.h, C.cast(st, C.c_void_p), ptr("z"), ptr("z_grad"),
+                                                ptr("inverse_mass_matrix"), ptr("wf_mean"), ptr("wf_m2"),
+                                                int(num_warmup), self._stream()), "b200nuts_set_state")
+        self.num_warmup = int(num_warmup)
+
+    # ------------------------------------------------------------------ parity hooks
+    def potential_and_grad(self, z):
+        z = torch.as_tensor(z, dtype=torch.float32).to(self.device).contiguous().view(self.C, self.D)
+        U = torch.zeros(self.C, dtype=torch.float32, device=self.device)
+        g = torch.zeros((self.C, self.D), dtype=torch.float32, device=self.device)
+        self._check(self.lib.b200nuts_potential_and_grad(self.h, _ptr(z), _ptr(U), _ptr(g), self._stream()),
+                    "b200nuts_potential_and_grad")
+        return U, g
+
+    def leapfrog(self, eps, inv_mass, z, r, n_steps: int):
+        dev = lambda a, shape: torch.as_tensor(a, dtype=torch.float32).to(self.device).contiguous().view(*shape).clone()
+        eps, inv_mass = dev(eps, (self.C,)), dev(inv_mass, (self.C, self.D))
+        z, r = dev(z, (self.C, self.D)), dev(r, (self.C, self.D))
+        U = torch.zeros(self.C, dtype=torch.float32, device=self.device)
+        g = torch.zeros((self.C, self.D), dtype=torch.float32, device=self.device)
+        self._check(self.lib.b200nuts_leapfrog(self.h, _ptr(eps), _ptr(inv_mass), _ptr(z), _ptr(r), _ptr(U), _ptr(g),
+                                               int(n_steps), self._stream()), "b200nuts_leapfrog")
+        return z, r, U, g
+
+    def constrain(self, z: torch.Tensor) -> torch.Tensor:
+        z = z.contiguous().view(-1, self.D)
+        out = torch.empty((z.shape[0], self.Dc), dtype=torch.float32, device=self.device)
+        self._check(self.lib.b200nuts_constrain(self.h, _ptr(z), z.shape[0], _ptr(out), self._stream()), "b200nuts_constrain")
+        return out
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.b200nuts_launch_count(self.h))
+
+
+# ---------------------------------------------------------------------- PRNG / det-math hooks
+def prng_split(keys, num: int) -> np.ndarray:
+    keys = np.ascontiguousarray(keys, np.uint32).reshape(-1, 2)
+    out = np.zeros((keys.shape[0], num, 2), np.uint32)
+    rc = _capi.load().b200nuts_prng_split(keys.ctypes.data_as(C.c_void_p), keys.shape[0], num, out.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise EngineError(f"b200nuts_prng_split failed ({rc})")
+    return out
+
+
+def _draw(fn, key, n, *extra, dtype=np.float32):
+    key = np.ascontiguousarray(key, np.uint32).reshape(2)
+    out = np.zeros(n, dtype)
+    rc = fn(key.ctypes.data_as(C.c_void_p), n, *extra, out.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise EngineError(f"prng hook failed ({rc})")
+    return out
+
+
+def prng_bits(key, n):
+    return _draw(_capi.load().b200nuts_prng_bits, key, n, dtype=np.uint32)
+
+
+def prng_uniform(key, n, lo=0.0, hi=1.0):
+    return _draw(_capi.load().b200nuts_prng_uniform, key, n, C.c_float(lo), C.c_float(hi))
+
+
+def prng_normal(key, n):
+    return _draw(_capi.load().b200nuts_prng_normal, key, n)
+
+
+def detmath(op: int, x) -> np.ndarray:
+    x = np.ascontiguousarray(x, np.float32).ravel()
+    out = np.zeros_like(x)
+    rc = _capi.load().b200nuts_detmath(op, x.ctypes.data_as(C.c_void_p), x.shape[0], out.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise EngineError(f"b200nuts_detmath failed ({rc})")
+    return out

@@ -1,0 +1,398 @@
+"""numpyro's MCMC front end over the B200 engine.
+
+Mirrors the user-facing surface of numpyro/infer/mcmc.py (``MCMC`` :225-809, ``MCMCKernel``
+:33-159) and numpyro/infer/hmc.py (``HMC`` :533-822, ``NUTS`` :825-951, ``HMCState`` :31-48) for
+the hot path only: same constructor arguments, same ``run / warmup / get_samples /
+get_extra_fields / last_state / post_warmup_state / print_summary`` semantics and the same
+collection layout ``[num_chains, num_samples // thinning, ...]``.  The model argument is a
+declared family (numpyro_b200.families); arrays are NumPy on the host, every computation runs in
+the CUDA engine.  ``chain_method='parallel'`` shards chains over the GPUs visible to the process
+(or over torch.distributed ranks under torchrun) with no communication except the final gather;
+``'vectorized'`` keeps all chains on one GPU; ``'sequential'`` runs them one after the other.
+"""
+from __future__ import annotations
+
+import warnings
+from collections import namedtuple
+from concurrent.futures import ThreadPoolExecutor
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _capi, diagnostics, families, random as b2random
+from .engine import Engine
+
+HMCState = namedtuple("HMCState", ["i", "z", "z_grad", "potential_energy", "energy", "r", "trajectory_length",
+                                   "num_steps", "accept_prob", "mean_accept_prob", "diverging", "adapt_state", "rng_key"])
+HMCAdaptState = namedtuple("HMCAdaptState", ["step_size", "inverse_mass_matrix", "mass_matrix_sqrt",
+                                             "mass_matrix_sqrt_inv", "ss_state", "mm_state", "window_idx", "rng_key"])
+
+_STATE_FIELDS = {"potential_energy": "potential_energy", "energy": "energy", "num_steps": "num_steps",
+                 "accept_prob": "accept_prob", "mean_accept_prob": "mean_accept_prob", "diverging": "diverging",
+                 "adapt_state.step_size": "step_size"}
+
+
+class HMC:
+    """Hamiltonian Monte Carlo kernel (hmc.py:533-822) for a declared model family."""
+    _algo = _capi.ALGO_HMC
+
+    def __init__(self, model=None, potential_fn=None, kinetic_fn=None, step_size=1.0, inverse_mass_matrix=None,
+                 adapt_step_size=True, adapt_mass_matrix=True, dense_mass=False, target_accept_prob=0.8,
+                 num_steps=None, trajectory_length=2 * np.pi, init_strategy=None, find_heuristic_step_size=False,
+                 forward_mode_differentiation=False, regularize_mass_matrix=True, max_tree_depth=10, regime="auto"):
+        if potential_fn is not None or kinetic_fn is not None:
+            raise NotImplementedError("the engine fuses the potential of registered model families; "
+                                      "arbitrary potential_fn / kinetic_fn callables are not supported")
+        if not isinstance(model, families.Model):
+            raise TypeError("model must be a numpyro_b200.families.Model (a declared model family)")
+        if dense_mass or inverse_mass_matrix is not None:
+            raise NotImplementedError("dense / user-supplied mass matrices are not implemented yet (SURVEY.md 8(f) rank 1)")
+        if forward_mode_differentiation:
+            raise NotImplementedError("gradients are hand-derived; forward_mode_differentiation does not apply")
+        if init_strategy is not None:
+            raise NotImplementedError("only init_to_uniform(radius=2) (the default) or init_params are supported")
+        self._model = model
+        depth = max_tree_depth if isinstance(max_tree_depth, tuple) else (max_tree_depth, max_tree_depth)
+        self._cfg = dict(algo=self._algo, step_size=float(step_size), adapt_step_size=int(adapt_step_size),
+                         adapt_mass_matrix=int(adapt_mass_matrix), regularize_mass_matrix=int(regularize_mass_matrix),
+                         find_heuristic_step_size=int(find_heuristic_step_size), target_accept_prob=float(target_accept_prob),
+                         max_tree_depth_warmup=int(depth[0]), max_tree_depth=int(depth[1]),
+                         hmc_num_steps=int(num_steps or 0),
+                         trajectory_length=float(trajectory_length if num_steps is None else 0.0) or 2 * np.pi,
+                         regime={"auto": 0, "warp": 1, "stream": 2, "gemm": 3}[regime])
+        self._trajectory_length = None if num_steps is not None else trajectory_length
+
+    @property
+    def model(self):
+        return self._model
+
+    @property
+    def sample_field(self):
+        return "z"
+
+    @property
+    def default_fields(self):
+        return ("z", "diverging")
+
+    @property
+    def is_ensemble_kernel(self):
+        return False
+
+    def get_diagnostics_str(self, state):
+        return "{} steps of size {:.2e}. acc. prob={:.2f}".format(
+            np.ravel(state.num_steps)[0], np.ravel(state.adapt_state.step_size)[0], np.ravel(state.mean_accept_prob)[0])
+
+
+class NUTS(HMC):
+    """No-U-Turn sampler (hmc.py:825-951)."""
+    _algo = _capi.ALGO_NUTS
+
+    def __init__(self, model=None, potential_fn=None, kinetic_fn=None, step_size=1.0, inverse_mass_matrix=None,
+                 adapt_step_size=True, adapt_mass_matrix=True, dense_mass=False, target_accept_prob=0.8,
+                 trajectory_length=None, max_tree_depth=10, init_strategy=None, find_heuristic_step_size=False,
+                 forward_mode_differentiation=False, regularize_mass_matrix=True, regime="auto"):
+        super().__init__(model=model, potential_fn=potential_fn, kinetic_fn=kinetic_fn, step_size=step_size,
+                         inverse_mass_matrix=inverse_mass_matrix, adapt_step_size=adapt_step_size,
+                         adapt_mass_matrix=adapt_mass_matrix, dense_mass=dense_mass,
+                         target_accept_prob=target_accept_prob, num_steps=None, trajectory_length=2 * np.pi,
+                         init_strategy=init_strategy, find_heuristic_step_size=find_heuristic_step_size,
+                         forward_mode_differentiation=forward_mode_differentiation,
+                         regularize_mass_matrix=regularize_mass_matrix, max_tree_depth=max_tree_depth, regime=regime)
+        self._trajectory_length = None
+
+
+class _Shard:
+    """The chains [lo, hi) living on one device."""
+
+    def __init__(self, device, lo, hi):
+        self.device, self.lo, self.hi = device, lo, hi
+        self.engine: Optional[Engine] = None
+
+
+class MCMC:
+    """numpyro.infer.MCMC (mcmc.py:225-809) over the B200 engine."""
+
+    def __init__(self, sampler, *, num_warmup, num_samples, num_chains=1, thinning=1, postprocess_fn=None,
+                 chain_method="parallel", progress_bar=True, progress_rate=None, jit_model_args=False):
+        if not isinstance(sampler, HMC):
+            raise TypeError("sampler must be numpyro_b200.infer.NUTS or HMC")
+        if not isinstance(num_warmup, int) or num_warmup < 0:
+            raise ValueError("num_warmup must be a non-negative integer")
+        if thinning < 1:
+            raise ValueError("thinning must be a positive integer")
+        if chain_method not in ("parallel", "vectorized", "sequential"):
+            raise ValueError("Only supporting the following methods to draw chains: 'sequential', 'parallel', or 'vectorized'")
+        if postprocess_fn is not None:
+            raise NotImplementedError("postprocess_fn is derived from the declared family")
+        self.sampler, self.num_warmup, self.num_samples = sampler, num_warmup, num_samples
+        self.num_chains, self.thinning, self.chain_method = num_chains, thinning, chain_method
+        self.progress_bar = False          # the whole collection loop is device resident (util.py:411-416 path)
+        self._shards: List[_Shard] = []
+        self._bound = None
+        self._states = None
+        self._states_flat = None
+        self._last_state = None
+        self._warmup_state = None
+        self._collect_warmup = False
+        self._lower, self._upper = num_warmup, num_warmup + num_samples
+        self._dist = torch.distributed.is_available() and torch.distributed.is_initialized() and chain_method == "parallel"
+
+    # ------------------------------------------------------------------ plumbing
+    def _plan_shards(self):
+        C = self.num_chains
+        if self._dist:
+            W, r = torch.distributed.get_world_size(), torch.distributed.get_rank()
+            if C % W:
+                raise ValueError("num_chains must be divisible by the number of ranks")
+            per = C // W
+            return [_Shard(torch.device("cuda", torch.cuda.current_device()), r * per, (r + 1) * per)]
+        if self.chain_method == "sequential":
+            return [_Shard(torch.device("cuda", torch.cuda.current_device()), c, c + 1) for c in range(C)]
+        ndev = torch.cuda.device_count() if self.chain_method == "parallel" else 1
+        ndev = max(1, min(ndev, C))
+        if self.chain_method == "parallel" and ndev < min(C, 2) and C > 1:
+            warnings.warn("There are not enough devices to run parallel chains: the chains share one GPU "
+                          "(equivalent to chain_method='vectorized').", stacklevel=3)
+        first = torch.cuda.current_device() if ndev == 1 else 0
+        bounds = [C * k // ndev for k in range(ndev + 1)]
+        return [_Shard(torch.device("cuda", first + k), bounds[k], bounds[k + 1]) for k in range(ndev)]
+
+    def _ensure_engines(self, args, kwargs):
+        bound = self.sampler.model.bind(*args, **kwargs)
+        self._bound = bound
+        if self._shards:
+            for s in self._shards:
+                if s.engine is not None:
+                    s.engine.close()
+        self._shards = self._plan_shards()
+        for s in self._shards:
+            cfg = dict(self.sampler._cfg)
+            cfg.update(bound.cfg)
+            cfg["num_chains"] = s.hi - s.lo
+            s.engine = Engine(device=s.device, X=bound.X, y=bound.y, aux=bound.aux, **cfg)
+
+    def _for_each_shard(self, fn):
+        if len(self._shards) == 1 or self.chain_method == "sequential":
+            return [fn(s) for s in self._shards]
+        with ThreadPoolExecutor(len(self._shards)) as pool:
+            return list(pool.map(fn, self._shards))
+
+    # ------------------------------------------------------------------ run / warmup
+    def _chain_keys(self, rng_key):
+        rng_key = np.asarray(rng_key, np.uint32)
+        if rng_key.ndim == 2:
+            if rng_key.shape[0] != self.num_chains:
+                raise ValueError("a batch of keys must have num_chains rows")
+            return rng_key
+        return rng_key[None] if self.num_chains == 1 else b2random.split(rng_key, self.num_chains)   # mcmc.py:670-671
+
+    def warmup(self, rng_key, *args, extra_fields=(), collect_warmup=False, init_params=None, **kwargs):
+        """mcmc.py:589-633: run the adaptation phase only and keep its last state."""
+        self._warmup_state = None
+        self._collect_warmup = collect_warmup
+        self._lower, self._upper = (0 if collect_warmup else self.num_warmup), self.num_warmup
+        self._run(rng_key, args, kwargs, extra_fields, init_params, fresh=True)
+        self._warmup_state = self._last_state
+
+    def run(self, rng_key, *args, extra_fields=(), init_params=None, **kwargs):
+        """mcmc.py:635-729."""
+        if self._warmup_state is not None:
+            self._lower, self._upper = self.num_warmup, self.num_warmup + self.num_samples
+            self._run(rng_key, args, kwargs, extra_fields, init_params, fresh=False)
+        else:
+            self._lower, self._upper = self.num_warmup, self.num_warmup + self.num_samples
+            self._run(rng_key, args, kwargs, extra_fields, init_params, fresh=True)
+
+    def _run(self, rng_key, args, kwargs, extra_fields, init_params, fresh):
+        keys = self._chain_keys(rng_key)
+        if fresh or not self._shards:
+            self._ensure_engines(args, kwargs)
+        bound = self._bound
+        D = self._shards[0].engine.D
+        z0 = None
+        if init_params is not None:
+            z0 = self._flatten_init(init_params, bound, D)
+        fields = ["z", "diverging"]
+        unc_sites, remove = [], set()
+        for f in tuple(extra_fields):
+            if f.startswith("~z."):
+                remove.add(f[3:])
+            elif f.startswith("z."):
+                unc_sites.append(f[2:])
+            elif f in _STATE_FIELDS:
+                if _STATE_FIELDS[f] not in fields:
+                    fields.append(_STATE_FIELDS[f])
+            else:
+                raise ValueError(f"unsupported extra field {f!r}")
+
+        def work(s: _Shard):
+            e = s.engine
+            with torch.cuda.device(s.device):
+                if fresh:
+                    e.init(keys[s.lo:s.hi], self.num_warmup, None if z0 is None else z0[s.lo:s.hi])
+                else:
+                    st, vec = e.state()
+                    for k in range(e.C):                      # mcmc.py:677-679: replace the state's rng_key
+                        st[k].rng_key[0], st[k].rng_key[1] = int(keys[s.lo + k][0]), int(keys[s.lo + k][1])
+                    e.set_state(st, vec, self.num_warmup)
+                out = e.run(self._upper, self._lower, self.thinning, fields=fields)
+                con = e.constrain(out["z"]).view(e.C, -1, e.Dc)
+                st, vec = e.state()
+                host = {k: v.cpu().numpy() for k, v in out.items()}
+                host["_constrained"] = con.cpu().numpy()
+                return host, st, vec
+
+        results = self._for_each_shard(work)
+        host = {k: np.concatenate([r[0][k] for r in results], axis=0) for k in results[0][0]}
+        if self._dist:
+            host = self._all_gather(host)
+        states: Dict[str, object] = {}
+        zdict = {}
+        for s in bound.sites:
+            if s.name in remove:
+                continue
+            block = host["_constrained"][:, :, s.c_offset:s.c_offset + s.size]
+            zdict[s.name] = block.reshape(block.shape[:2] + tuple(s.shape))
+        states["z"] = zdict
+        states["diverging"] = host["diverging"].astype(bool)
+        for f in tuple(extra_fields):
+            if f in _STATE_FIELDS:
+                states[f] = host[_STATE_FIELDS[f]]
+        for name in unc_sites:
+            s = next(x for x in bound.latent_sites if x.name == name)
+            block = host["z"][:, :, s.z_offset:s.z_offset + s.size]
+            states["z." + name] = block.reshape(block.shape[:2] + tuple(s.shape))
+        self._states = states
+        self._states_flat = None
+        self._last_state = self._make_state([r[1] for r in results], [r[2] for r in results], bound)
+
+    def _all_gather(self, host):
+        dist = torch.distributed
+        out = {}
+        for k, v in host.items():
+            t = torch.from_numpy(np.ascontiguousarray(v)).cuda()
+            parts = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+            dist.all_gather(parts, t)                 # the only communication of the chain-sharded mode
+            out[k] = torch.cat(parts, dim=0).cpu().numpy()
+        return out
+
+    @staticmethod
+    def _flatten_init(init_params, bound, D):
+        if isinstance(init_params, dict):
+            first = np.asarray(next(iter(init_params.values())))
+            lat = bound.latent_sites
+            lead = first.shape[:first.ndim - len(next(s for s in lat if s.name == next(iter(init_params))).shape)]
+            n = int(np.prod(lead)) if lead else 1
+            z = np.zeros((n, D), np.float32)
+            for s in lat:
+                z[:, s.z_offset:s.z_offset + s.size] = np.asarray(init_params[s.name], np.float32).reshape(n, s.size)
+            return z
+        return np.asarray(init_params, np.float32).reshape(-1, D)
+
+    def _make_state(self, sts, vecs, bound):
+        cat = lambda name: np.concatenate([v[name] for v in vecs], axis=0)
+        st = [s[k] for s in sts for k in range(len(s))]
+        arr = lambda f, dt: np.array([getattr(s, f) for s in st], dt)
+        unflat = lambda a: {s.name: a[:, s.z_offset:s.z_offset + s.size].reshape((a.shape[0],) + tuple(s.shape))
+                            for s in bound.latent_sites}
+        squeeze = (lambda a: a[0]) if self.num_chains == 1 and not self._dist else (lambda a: a)
+        tree = lambda d: {k: squeeze(v) for k, v in d.items()}
+        imm, msq = cat("inverse_mass_matrix"), cat("mass_matrix_sqrt")
+        key = tuple(sorted(s.name for s in bound.latent_sites))        # one-block structured mass matrix (hmc.py:759-769)
+        adapt = HMCAdaptState(
+            squeeze(arr("step_size", np.float32)), {key: squeeze(imm)}, {key: squeeze(msq)}, {key: squeeze(1.0 / msq)},
+            (squeeze(arr("ss_x_t", np.float32)), squeeze(arr("ss_x_avg", np.float32)), squeeze(arr("ss_g_avg", np.float32)),
+             squeeze(arr("ss_t", np.int32)), squeeze(arr("ss_prox", np.float32))),
+            {key: (squeeze(cat("wf_mean")), squeeze(cat("wf_m2")), squeeze(arr("mm_n", np.int32)))},
+            squeeze(arr("window_idx", np.int32)),
+            squeeze(np.array([[s.adapt_rng_key[0], s.adapt_rng_key[1]] for s in st], np.uint32)))
+        return HMCState(squeeze(arr("i", np.int32)), tree(unflat(cat("z"))), tree(unflat(cat("z_grad"))),
+                        squeeze(arr("potential_energy", np.float32)), squeeze(arr("energy", np.float32)), None,
+                        self.sampler._trajectory_length, squeeze(arr("num_steps", np.int32)),
+                        squeeze(arr("accept_prob", np.float32)), squeeze(arr("mean_accept_prob", np.float32)),
+                        squeeze(arr("diverging", np.int32).astype(bool)), adapt,
+                        squeeze(np.array([[s.rng_key[0], s.rng_key[1]] for s in st], np.uint32)))
+
+    # ------------------------------------------------------------------ results
+    @property
+    def last_state(self):
+        return self._last_state
+
+    @property
+    def post_warmup_state(self):
+        return self._warmup_state
+
+    @post_warmup_state.setter
+    def post_warmup_state(self, state):
+        """mcmc.py:558-587: continue sampling from a previous (post warm-up) state."""
+        self._warmup_state = state
+        if state is not None and self._shards:
+            self._push_state(state)
+
+    def _push_state(self, state: HMCState):
+        bound = self._bound
+        C = self.num_chains
+        lead = lambda a: np.asarray(a).reshape((C,) + np.asarray(a).shape[(0 if C == 1 and np.asarray(a).ndim == 0 else (1 if C > 1 else 0)):])
+        def flat(tree):
+            out = np.zeros((C, self._shards[0].engine.D), np.float32)
+            for s in bound.latent_sites:
+                out[:, s.z_offset:s.z_offset + s.size] = np.asarray(tree[s.name], np.float32).reshape(C, s.size)
+            return out
+        z, g = flat(state.z), flat(state.z_grad)
+        a = state.adapt_state
+        one = lambda d: np.asarray(next(iter(d.values())) if isinstance(d, dict) else d, np.float32).reshape(C, -1)
+        imm = one(a.inverse_mass_matrix)
+        mm = next(iter(a.mm_state.values())) if isinstance(a.mm_state, dict) else a.mm_state
+        sc = lambda v, dt: np.asarray(v, dt).reshape(C)
+        keys = np.asarray(state.rng_key, np.uint32).reshape(C, 2)
+        akeys = np.asarray(a.rng_key, np.uint32).reshape(C, 2)
+        for s in self._shards:
+            n = s.hi - s.lo
+            st = (_capi.ChainState * n)()
+            for k in range(n):
+                c = s.lo + k
+                st[k].i = int(sc(state.i, np.int32)[c]); st[k].rng_key[0], st[k].rng_key[1] = int(keys[c][0]), int(keys[c][1])
+                st[k].potential_energy = float(sc(state.potential_energy, np.float32)[c]); st[k].energy = float(sc(state.energy, np.float32)[c])
+                st[k].num_steps = int(sc(state.num_steps, np.int32)[c]); st[k].accept_prob = float(sc(state.accept_prob, np.float32)[c])
+                st[k].mean_accept_prob = float(sc(state.mean_accept_prob, np.float32)[c]); st[k].diverging = int(sc(state.diverging, np.int32)[c])
+                st[k].step_size = float(sc(a.step_size, np.float32)[c])
+                st[k].ss_x_t, st[k].ss_x_avg, st[k].ss_g_avg = (float(sc(a.ss_state[j], np.float32)[c]) for j in range(3))
+                st[k].ss_t = int(sc(a.ss_state[3], np.int32)[c]); st[k].ss_prox = float(sc(a.ss_state[4], np.float32)[c])
+                st[k].mm_n = int(sc(mm[2], np.int32)[c]); st[k].window_idx = int(sc(a.window_idx, np.int32)[c])
+                st[k].adapt_rng_key[0], st[k].adapt_rng_key[1] = int(akeys[c][0]), int(akeys[c][1])
+            vec = {"z": z[s.lo:s.hi], "z_grad": g[s.lo:s.hi], "inverse_mass_matrix": imm[s.lo:s.hi],
+                   "wf_mean": np.asarray(mm[0], np.float32).reshape(C, -1)[s.lo:s.hi],
+                   "wf_m2": np.asarray(mm[1], np.float32).reshape(C, -1)[s.lo:s.hi]}
+            with torch.cuda.device(s.device):
+                s.engine.set_state(st, vec, self.num_warmup)
+
+    def get_samples(self, group_by_chain=False):
+        """mcmc.py:549-556."""
+        if self._states is None:
+            raise RuntimeError("run() has not been called")
+        z = self._states["z"]
+        if group_by_chain:
+            return dict(z)
+        return {k: v.reshape((-1,) + v.shape[2:]) for k, v in z.items()}
+
+    def get_extra_fields(self, group_by_chain=False):
+        if self._states is None:
+            raise RuntimeError("run() has not been called")
+        out = {k: v for k, v in self._states.items() if k != "z"}
+        if group_by_chain:
+            return out
+        return {k: v.reshape((-1,) + v.shape[2:]) for k, v in out.items()}
+
+    def print_summary(self, prob=0.9, exclude_deterministic=True):
+        """mcmc.py:769-797 (table of mean / std / n_eff / r_hat + number of divergences)."""
+        det = {s.name for s in self._bound.sites if s.deterministic}
+        sites = {k: v for k, v in self._states["z"].items() if not (exclude_deterministic and k in det)}
+        summ = diagnostics.summary(sites, group_by_chain=True)
+        print("\n{:>16} {:>9} {:>9} {:>9} {:>9}".format("", "mean", "std", "n_eff", "r_hat"))
+        for name, s in summ.items():
+            mean, std, neff, rhat = (np.atleast_1d(s[k]).ravel() for k in ("mean", "std", "n_eff", "r_hat"))
+            for j in range(mean.shape[0]):
+                label = name if mean.shape[0] == 1 else f"{name}[{j}]"
+                print("{:>16} {:>9.2f} {:>9.2f} {:>9.2f} {:>9.2f}".format(label, mean[j], std[j], neff[j], rhat[j]))
+        print("\nNumber of divergences: {}".format(int(np.sum(self._states["diverging"]))))

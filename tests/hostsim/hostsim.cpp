@@ -35,9 +35,9 @@ int hostsim_create(const B200NutsConfig* cfg, HostSim** out) {
     if (h->fam.family == FAM_GLM) {
         h->scratch.assign((size_t)(h->fam.N + h->fam.Dx), 0.0f);
         if (h->fam.likelihood == LIK_POISSON) {
-            h->ylgam.resize(h->fam.N);
-            for (long long n = 0; n < h->fam.N; ++n) h->ylgam[n] = lgammaf(h->fam.y[n] + 1.0f);
-            h->fam.ylgam = h->ylgam.data();
+            double acc = 0.0;
+            for (long long n = 0; n < h->fam.N; ++n) acc += lgamma((double)h->fam.y[n] + 1.0);
+            h->fam.nll_const = (float)acc;
         }
     }
     *out = h;
