@@ -103,6 +103,8 @@ EXPORTS = {
     "b200nuts_prng_normal": (C.c_int, [vp, i64, vp]),
     "b200nuts_detmath": (C.c_int, [i32, vp, i64, vp]),
     "b200nuts_launch_count": (i64, [vp]),
+    "b200nuts_pass_count": (i64, [vp]),
+    "b200nuts_debug_clocks": (C.c_int, [vp, vp]),
 }
 
 _lib = None

@@ -25,7 +25,8 @@ struct B200Nuts {
     // R2
     float* partial = nullptr; float* beta = nullptr; StreamSync* sync = nullptr;
     int grid = 0, rho = 1, stages = 4, tile_rows = 192, dpl = 0, vecs_in_smem = 0; size_t smem = 0;
-    long long launches = 0;
+    long long launches = 0, passes = 0;
+    unsigned long long dbg[8] = {0};
     std::string err;
     std::mutex mu;
 };
@@ -209,6 +210,8 @@ static int check_stream_abort(B200Nuts* h, cudaStream_t st) {
     StreamSync s;
     CK(cudaMemcpyAsync(&s, h->sync, sizeof(s), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    h->passes += (long long)s.passes;
+    for (int i = 0; i < 8; ++i) h->dbg[i] = s.dbg[i];
     if (s.abort_flag) { h->err = "stream engine aborted: inter-pass exchange timed out"; return B200NUTS_ECUDA; }
     return 0;
 }
@@ -219,6 +222,12 @@ const char* b200nuts_last_error(const B200Nuts* h) { return h ? h->err.c_str() :
 int b200nuts_dim(const B200Nuts* h) { return h ? h->D : B200NUTS_EINVAL; }
 int b200nuts_regime(const B200Nuts* h) { return h ? h->regime : B200NUTS_EINVAL; }
 int64_t b200nuts_launch_count(const B200Nuts* h) { return h ? h->launches : 0; }
+int64_t b200nuts_pass_count(const B200Nuts* h) { return h ? h->passes : 0; }
+int b200nuts_debug_clocks(const B200Nuts* h, uint64_t* out8) {
+    if (!h || !out8) return B200NUTS_EINVAL;
+    for (int i = 0; i < 8; ++i) out8[i] = h->dbg[i];
+    return 0;
+}
 
 int b200nuts_constrained_dim(const B200Nuts* h) {
     if (!h) return B200NUTS_EINVAL;

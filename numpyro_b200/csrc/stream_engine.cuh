@@ -36,7 +36,9 @@ constexpr int kMaxStages = 6;
 constexpr int kTilePad = 64;              // zeroed floats after each X stage (strided over-reads stay finite)
 constexpr int kGStride = 72;             // floats per (cta, chain) partial: gbeta[<=64], nll, pad
 
-struct StreamSync { unsigned int arrive, ready, done, abort_flag; unsigned long long passes; };
+// dbg: clock64 totals on CTA 0 -- [0] wait for betas, [1] sweep + publish partial, [2] wait for all partials,
+// [3] cross-CTA reduction, [4] finish + tick + publish beta, [5] total loop
+struct StreamSync { unsigned int arrive, ready, done, abort_flag; unsigned long long passes; unsigned long long dbg[8]; };
 
 struct StreamParams {
     TickCfg cfg; FamilySpec fam; OutBufs out;
@@ -112,7 +114,7 @@ B2_HD size_t stream_smem_bytes(int D, int Dp, int stages, int kTileRows, bool ve
     b += (size_t)stages * kTileRows * 4;                           // y ring
     b += 2 * kMaxStages * 8;                                       // mbarriers
     b += (size_t)12 * kStreamCT * kGStride * 4;                    // cross-warp reduction + tick scratch
-    b += 2 * 64 * 4 + 64;                                          // gred, coef, flags
+    b += 2 * 64 * 4 + 64 + 64;                                     // gred, coef, flags, debug timers
     b += ((sizeof(ChainCtl) + 15) / 16) * 16;
     if (vecs_in_smem) b += (size_t)V_COUNT * Dp * 4;
     return b + 128;
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
     s.gred = (float*)q; q += 64 * 4;
     s.coef = (float*)q; q += 64 * 4;
     s.flags = (int*)q; q += 64;
+    unsigned long long* tdbg = (unsigned long long*)q; q += 64;
     s.ctl = (ChainCtl*)q; q += ((sizeof(ChainCtl) + 15) / 16) * 16;
     s.cvecs = (float*)q;
 
@@ -156,6 +159,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         for (int i = 0; i < kStages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], kStreamWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s.flags[0] = 0;                              // stop flag for the producer
+        for (int i = 0; i < 8; ++i) tdbg[i] = 0ull;
     }
     ChainVecs cv;
     if (is_tick) {
@@ -237,12 +241,17 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         }
     }
 
+    const bool dbg = (cta == 0 && ctid == 0);
+    long long t_prev = clock64(), t_red = 0;
+    const long long t_begin = t_prev;
+#define B2_DBG_LAP(k) do { if (dbg) { const long long t_now = clock64(); tdbg[k] += (unsigned long long)(t_now - t_prev); t_prev = t_now; } } while (0)
     while (true) {
         // ---- wait for every chain's beta of this pass
         if (ctid == 0) {
             ok = spin_ge(&p.sync->ready, (unsigned)p.C * (pass + 1u), p.sync, p.spin_limit);
             s.flags[1] = ok ? 1 : 0;
             s.flags[2] = (int)ld_acquire(&p.sync->done);
+            B2_DBG_LAP(0);
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kStreamWarps * 32) : "memory");
         if (!s.flags[1] || s.flags[2] >= p.C) break;
@@ -312,6 +321,77 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
             }
         };
 
+        // Two independent warp steps written side by side so the scheduler can overlap the
+        // shuffle / MUFU latency chain of one with the FFMA2 blocks of the other.
+        auto step2 = [&](const float* xa, float ya, bool va, const float* xb, float yb, bool vb) {
+            float x[2][DPL];
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) { x[0][i] = xa[8 * i]; x[1][i] = xb[8 * i]; }
+            unsigned long long L2[2][kStreamCT / 2];
+#pragma unroll
+            for (int c = 0; c < kStreamCT / 2; ++c) { L2[0][c] = 0ull; L2[1][c] = 0ull; }
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) {
+                const unsigned long long xx0 = pack2(x[0][i], x[0][i]), xx1 = pack2(x[1][i], x[1][i]);
+#pragma unroll
+                for (int c = 0; c < kStreamCT / 2; ++c) { ffma2(L2[0][c], xx0, bet[i][c]); ffma2(L2[1][c], xx1, bet[i][c]); }
+            }
+            float L[2][kStreamCT];
+#pragma unroll
+            for (int c = 0; c < kStreamCT / 2; ++c) {
+                unpack2(L2[0][c], L[0][2 * c], L[0][2 * c + 1]);
+                unpack2(L2[1][c], L[1][2 * c], L[1][2 * c + 1]);
+            }
+            float M4[2][4], M2[2][2], eta[2];
+            const bool hi = (j & 4) != 0, mid = (j & 2) != 0, lo = (j & 1) != 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int q2 = 0; q2 < 2; ++q2) {
+                    const float send = hi ? L[q2][k] : L[q2][k + 4];
+                    const float keep = hi ? L[q2][k + 4] : L[q2][k];
+                    M4[q2][k] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 4);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+#pragma unroll
+                for (int q2 = 0; q2 < 2; ++q2) {
+                    const float send = mid ? M4[q2][k] : M4[q2][k + 2];
+                    const float keep = mid ? M4[q2][k + 2] : M4[q2][k];
+                    M2[q2][k] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 2);
+                }
+            }
+#pragma unroll
+            for (int q2 = 0; q2 < 2; ++q2) {
+                const float send = lo ? M2[q2][0] : M2[q2][1];
+                const float keep = lo ? M2[q2][1] : M2[q2][0];
+                eta[q2] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 1);
+            }
+            float loss0, dl0, loss1, dl1;
+            glm_loss_fast(p.fam.likelihood, eta[0], ya, loss0, dl0);
+            glm_loss_fast(p.fam.likelihood, eta[1], yb, loss1, dl1);
+            if (!va) { loss0 = 0.0f; dl0 = 0.0f; }
+            if (!vb) { loss1 = 0.0f; dl1 = 0.0f; }
+            nll_acc += loss0;
+            nll_acc += loss1;
+            float r[2][kStreamCT];
+#pragma unroll
+            for (int c = 0; c < kStreamCT; ++c) {
+                r[0][c] = __shfl_sync(0xFFFFFFFFu, dl0, (lane & 24) | c);
+                r[1][c] = __shfl_sync(0xFFFFFFFFu, dl1, (lane & 24) | c);
+            }
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) {
+                const unsigned long long xx0 = pack2(x[0][i], x[0][i]), xx1 = pack2(x[1][i], x[1][i]);
+#pragma unroll
+                for (int c = 0; c < kStreamCT / 2; ++c) {
+                    ffma2(acc[i][c], xx0, pack2(r[0][2 * c], r[0][2 * c + 1]));
+                    ffma2(acc[i][c], xx1, pack2(r[1][2 * c], r[1][2 * c + 1]));
+                }
+            }
+        };
+
         // ---- sweep this CTA's tiles
         for (int t = 0; t < n_tiles; ++t, ++cons_it) {
             const int st = cons_it % kStages; const uint32_t ph = (cons_it / kStages) & 1u;
@@ -323,11 +403,17 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
             // global step index (t * steps + u) == cw (mod 11): perfectly balanced over the pass
             const int steps = kTileRows / 4;
             const int u0 = (cw + kStreamWarps - (int)(((long long)t * steps) % kStreamWarps)) % kStreamWarps;
-            for (int u = u0; u < steps; u += kStreamWarps) {
+            for (int u = u0; u < steps; u += 2 * kStreamWarps) {
                 const int blk = (rho == 1) ? u : (int)__umulhi((unsigned)u, rho_magic), sidx = u - blk * rho;   // u / rho
                 const int row = blk * 4 * rho + sidx + rho * rsub;
                 if (blk * 4 * rho >= rows) break;                 // warp-uniform
-                step(tile + row * D + j, yt[row], row < rows, false);
+                const int ub = u + kStreamWarps;
+                const int blkb = (rho == 1) ? ub : (int)__umulhi((unsigned)ub, rho_magic), sidxb = ub - blkb * rho;
+                const int rowb = blkb * 4 * rho + sidxb + rho * rsub;
+                if (ub < steps && blkb * 4 * rho < rows)
+                    step2(tile + row * D + j, yt[row], row < rows, tile + rowb * D + j, yt[rowb], rowb < rows);
+                else
+                    step(tile + row * D + j, yt[row], row < rows, false);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&s.empty[st]);
@@ -367,28 +453,40 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         }
         __threadfence();
         asm volatile("bar.sync 1, %0;" ::"n"(kStreamWarps * 32) : "memory");
-        if (ctid == 0) red_release_add(&p.sync->arrive, 1u);
+        if (ctid == 0) { red_release_add(&p.sync->arrive, 1u); B2_DBG_LAP(1); }
 
         // ---- chain owner: sum the partials in fixed order, finish the potential, tick the chain
         if (is_tick) {
             if (ctid == 0) {
                 ok = spin_ge(&p.sync->arrive, (unsigned)G * (pass + 1u), p.sync, p.spin_limit);
                 s.flags[1] = ok ? 1 : 0;
+                B2_DBG_LAP(2);
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kStreamWarps * 32) : "memory");
             if (s.flags[1]) {
-                // 4 segments x 65 outputs, each thread adds its segment's CTAs in ascending order
-                const int o = ctid % 65, seg = ctid / 65;         // seg 0..5 (only 0..3 used)
-                float a = 0.0f;
-                if (seg < 4) {
-                    const int g0 = G * seg / 4, g1 = G * (seg + 1) / 4;
-                    for (int g = g0; g < g1; ++g) a += __ldcg(p.partial + ((size_t)g * kStreamCT + cta) * kGStride + o);
+                // 5 segments x 65 outputs; each thread adds its segment's CTAs in ascending order.
+                // Loads are issued 8 at a time (independent, L2 latency overlapped), adds stay ordered.
+                const int o = ctid % 65, seg = ctid / 65;         // seg 0..5 (only 0..4 used)
+                if (seg < 5) {
+                    float a = 0.0f;
+                    const int g0 = G * seg / 5, g1 = G * (seg + 1) / 5;
+                    const float* src = p.partial + (size_t)cta * kGStride + o;
+                    for (int g = g0; g < g1; g += 8) {
+                        float v[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            v[k] = (g + k < g1) ? __ldcg(src + (size_t)(g + k) * (kStreamCT * kGStride)) : 0.0f;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) a += v[k];
+                    }
                     s.red[seg * kGStride + o] = a;
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kStreamWarps * 32) : "memory");
                 if (cw == 0) {
+                    B2_DBG_LAP(3);
                     for (int d = lane; d < 65; d += 32)
-                        s.gred[d] = ((s.red[d] + s.red[kGStride + d]) + s.red[2 * kGStride + d]) + s.red[3 * kGStride + d];
+                        s.gred[d] = (((s.red[d] + s.red[kGStride + d]) + s.red[2 * kGStride + d]) + s.red[3 * kGStride + d]) +
+                                    s.red[4 * kGStride + d];
                     __syncwarp();
                     const float nll = s.gred[64];
                     float* gz = s.red + 8 * kGStride;             // scratch for the gradient wrt z (<= Dp floats)
@@ -424,6 +522,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                         if (finished) atomicAdd(&p.sync->done, 1u);
                         __threadfence();
                         red_release_add(&p.sync->ready, 1u);
+                        B2_DBG_LAP(4);
                     }
                 }
             }
@@ -443,7 +542,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         }
         if (ctid == 0 && p.mode == 0) p.ctl[cta] = *s.ctl;
     }
-    if (cta == 0 && ctid == 0) p.sync->passes = pass;
+    if (cta == 0 && ctid == 0) {
+        p.sync->passes = pass;
+        tdbg[5] = (unsigned long long)(clock64() - t_begin);
+        for (int i = 0; i < 8; ++i) p.sync->dbg[i] = tdbg[i];
+    }
+    (void)t_red;
 }
 
 }  // namespace b2

@@ -147,12 +147,23 @@ class Engine:
     def constrain(self, z: torch.Tensor) -> torch.Tensor:
         z = z.contiguous().view(-1, self.D)
         out = torch.empty((z.shape[0], self.Dc), dtype=torch.float32, device=self.device)
+        if z.shape[0] == 0:
+            return out
         self._check(self.lib.b200nuts_constrain(self.h, _ptr(z), z.shape[0], _ptr(out), self._stream()), "b200nuts_constrain")
         return out
 
     @property
     def launch_count(self) -> int:
         return int(self.lib.b200nuts_launch_count(self.h))
+
+    @property
+    def pass_count(self) -> int:
+        return int(self.lib.b200nuts_pass_count(self.h))
+
+    def debug_clocks(self) -> np.ndarray:
+        out = np.zeros(8, np.uint64)
+        self._check(self.lib.b200nuts_debug_clocks(self.h, out.ctypes.data_as(C.c_void_p)), "b200nuts_debug_clocks")
+        return out
 
 
 # ---------------------------------------------------------------------- PRNG / det-math hooks

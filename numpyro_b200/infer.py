@@ -244,6 +244,8 @@ class MCMC:
                 return host, st, vec
 
         results = self._for_each_shard(work)
+        #: gradient evaluations (leapfrogs) spent so far by every local chain, warm-up included
+        self.total_grad_evals = int(sum(int(st[k].total_leapfrogs) for _, st, _ in results for k in range(len(st))))
         host = {k: np.concatenate([r[0][k] for r in results], axis=0) for k in results[0][0]}
         if self._dist:
             host = self._all_gather(host)

@@ -212,6 +212,30 @@ class GLM(Family):
             gz[off:off + sz] = -g[n]
         return -lp, gz
 
+    def potential_and_grad_f32(self, z):
+        """Plain-GLM potential in float32 with BLAS matvecs: the arithmetic a CPU run of the
+        reference performs (fp32 ``jnp.dot(data, coefs)`` forward + transpose product backward).
+        Used only as the timed CPU baseline of bench.py; parity tests use the fp64 path."""
+        assert not self.local and not self.gscale and self.likelihood in ("bernoulli", "poisson")
+        if not hasattr(self, "_X32"):
+            self._X32 = np.ascontiguousarray(self.X, F)
+            self._y32 = np.ascontiguousarray(self.y, F)
+            self._lg32 = F(0.0) if self._lgam is None else F(np.sum(self._lgam))
+        u = np.asarray(z, F)
+        eta = self._X32 @ u
+        with np.errstate(all="ignore"):
+            if self.likelihood == "bernoulli":
+                e = np.exp(-np.abs(eta))
+                nll = np.sum(np.maximum(eta, 0) + np.log1p(e) - eta * self._y32, dtype=np.float64)
+                dl = F(1.0) / (F(1.0) + np.exp(-eta)) - self._y32
+            else:
+                r = np.exp(eta)
+                nll = np.sum(r - self._y32 * eta, dtype=np.float64) + self._lg32
+                dl = r - self._y32
+        g = u + self._X32.T @ dl
+        U = nll + 0.5 * float(u @ u) + self.D * LOG_SQRT_2PI
+        return F(U), g.astype(F)
+
     def constrain(self, z):
         z = np.asarray(z, F)
         p = self._split(z)

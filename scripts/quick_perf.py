@@ -40,3 +40,6 @@ ns = out["num_steps"].cpu().numpy()
 print("sample 40 iters: %.1f ms, leapfrogs %d (per chain %s) -> %.0f grad-evals/s; us/pass(max chain) %.2f; HBM-roofline frac %.3f" % (
     ms, ns.sum(), ns.sum(1), ns.sum() / ms * 1e3, ms * 1e3 / ns.sum(1).max(), (ns.sum(1).max() * 127822640 / (ms * 1e-3)) / 6545.6e9))
 print("divergences", int(out["diverging"].sum()))
+dbg = e.debug_clocks().astype(np.float64)
+names = ["wait_beta", "sweep+publish", "wait_partials", "reduce", "finish+tick+publish", "total"]
+print("CTA0 clock breakdown per pass:", {n: round(dbg[i] / max(e.pass_count and ns.sum(1).max(), 1), 0) for i, n in enumerate(names)})
