@@ -141,20 +141,21 @@ class MCMC:
     # ------------------------------------------------------------------ plumbing
     def _plan_shards(self):
         C = self.num_chains
+        cur = torch.cuda.current_device() if torch.cuda.is_available() else 0
         if self._dist:
             W, r = torch.distributed.get_world_size(), torch.distributed.get_rank()
             if C % W:
                 raise ValueError("num_chains must be divisible by the number of ranks")
             per = C // W
-            return [_Shard(torch.device("cuda", torch.cuda.current_device()), r * per, (r + 1) * per)]
+            return [_Shard(torch.device("cuda", cur), r * per, (r + 1) * per)]
         if self.chain_method == "sequential":
-            return [_Shard(torch.device("cuda", torch.cuda.current_device()), c, c + 1) for c in range(C)]
+            return [_Shard(torch.device("cuda", cur), c, c + 1) for c in range(C)]
         ndev = torch.cuda.device_count() if self.chain_method == "parallel" else 1
         ndev = max(1, min(ndev, C))
         if self.chain_method == "parallel" and ndev < min(C, 2) and C > 1:
             warnings.warn("There are not enough devices to run parallel chains: the chains share one GPU "
                           "(equivalent to chain_method='vectorized').", stacklevel=3)
-        first = torch.cuda.current_device() if ndev == 1 else 0
+        first = cur if ndev == 1 else 0
         bounds = [C * k // ndev for k in range(ndev + 1)]
         return [_Shard(torch.device("cuda", first + k), bounds[k], bounds[k + 1]) for k in range(ndev)]
 
@@ -272,8 +273,10 @@ class MCMC:
     def _all_gather(self, host):
         dist = torch.distributed
         out = {}
+        on_gpu = dist.get_backend() == "nccl"
         for k, v in host.items():
-            t = torch.from_numpy(np.ascontiguousarray(v)).cuda()
+            t = torch.from_numpy(np.ascontiguousarray(v))
+            t = t.cuda() if on_gpu else t
             parts = [torch.empty_like(t) for _ in range(dist.get_world_size())]
             dist.all_gather(parts, t)                 # the only communication of the chain-sharded mode
             out[k] = torch.cat(parts, dim=0).cpu().numpy()
