@@ -24,7 +24,7 @@ struct B200Nuts {
     uint32_t* keys = nullptr;
     // R2
     float* partial = nullptr; float* beta = nullptr; StreamSync* sync = nullptr;
-    int grid = 0, rho = 1, stages = 4, tile_rows = 192, dpl = 0, vecs_in_smem = 0; size_t smem = 0;
+    int grid = 0, stages = 4, vecs_in_smem = 0; size_t smem = 0;
     long long launches = 0, passes = 0;
     unsigned long long dbg[8] = {0};
     std::string err;
@@ -171,7 +171,7 @@ __global__ void k_detmath(int op, const float* x, long long n, float* out) {
 }
 
 // ------------------------------------------------------------------------------------------------
-static int choose_rho(int D) {
+[[maybe_unused]] static int choose_rho(int D) {
     static const int cand[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 48};
     for (int r : cand) {
         bool seen[4] = {false, false, false, false}; bool okk = true;
@@ -189,17 +189,14 @@ static int stream_launch(B200Nuts* h, int mode, const OutBufs& out, const float*
     StreamParams p; memset(&p, 0, sizeof(p));
     p.cfg = h->tick; p.cfg.D = h->D; p.fam = h->fam; p.out = out; p.C = h->C; p.Dp = h->Dp; p.mode = mode;
     p.ctl = h->ctl; p.vecs = h->vecs; p.partial = h->partial; p.beta = h->beta; p.sync = h->sync;
-    p.z_in = z_in; p.u_out = u_out; p.g_out = g_out; p.rho = h->rho; p.stages = h->stages; p.tile_rows = h->tile_rows;
+    p.z_in = z_in; p.u_out = u_out; p.g_out = g_out; p.stages = h->stages;
     p.vecs_in_smem = h->vecs_in_smem; p.spin_limit = 6000000000LL;
     CK(cudaMemsetAsync(h->sync, 0, sizeof(StreamSync), st));
     void* args[] = {&p};
-    const void* fn = nullptr;
-    switch (h->dpl) {
-    case 2: fn = (const void*)stream_engine_kernel<2>; break;
-    case 4: fn = (const void*)stream_engine_kernel<4>; break;
-    case 7: fn = (const void*)stream_engine_kernel<7>; break;
-    default: fn = (const void*)stream_engine_kernel<8>; break;
-    }
+    const int need = (h->fam.Dx + 7) / 8;
+    const void* fn = need <= 1 ? (const void*)stream_engine_kernel<1> : need <= 2 ? (const void*)stream_engine_kernel<2>
+                   : need <= 4 ? (const void*)stream_engine_kernel<4> : need <= 7 ? (const void*)stream_engine_kernel<7>
+                                                                                : (const void*)stream_engine_kernel<8>;
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     CK(cudaLaunchCooperativeKernel(fn, dim3(h->grid), dim3(kStreamThreads), args, h->smem, st));
     h->launches += 1;
@@ -297,21 +294,17 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
         h->launches += 1;
     }
     if (regime == B200NUTS_REGIME_STREAM) {
-        const int need = (h->fam.Dx + 7) / 8;
-        h->dpl = need <= 2 ? 2 : need <= 4 ? 4 : need <= 7 ? 7 : 8;
-        h->rho = choose_rho(h->fam.Dx);
-        h->tile_rows = (kMaxTileRows / (4 * h->rho)) * (4 * h->rho);
         h->grid = h->num_sms;
         int max_smem = 0;
         cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
         h->stages = 0;
         for (int vs = 1; vs >= 0 && !h->stages; --vs)
-            for (int stg = 6; stg >= 2; --stg)
-                if (stream_smem_bytes(h->fam.Dx, h->Dp, stg, h->tile_rows, vs != 0) <= (size_t)max_smem) {
+            for (int stg = kMaxStages; stg >= 8; --stg)      // 7 tiles are being processed at any time
+                if (stream_smem_bytes(h->fam.Dx, h->Dp, stg, vs != 0) <= (size_t)max_smem) {
                     h->stages = stg; h->vecs_in_smem = vs; break;
                 }
         if (!h->stages) { g_create_err = "stream regime: shared memory budget exceeded"; b200nuts_destroy(h); return B200NUTS_EINVAL; }
-        h->smem = stream_smem_bytes(h->fam.Dx, h->Dp, h->stages, h->tile_rows, h->vecs_in_smem != 0);
+        h->smem = stream_smem_bytes(h->fam.Dx, h->Dp, h->stages, h->vecs_in_smem != 0);
         if ((ce = cudaMalloc(&h->partial, sizeof(float) * (size_t)h->grid * kStreamCT * kGStride)) != cudaSuccess) return fail("cudaMalloc partial", ce);
         if ((ce = cudaMalloc(&h->beta, sizeof(float) * kStreamCT * 64)) != cudaSuccess) return fail("cudaMalloc beta", ce);
         if ((ce = cudaMalloc(&h->sync, sizeof(StreamSync))) != cudaSuccess) return fail("cudaMalloc sync", ce);
