@@ -150,7 +150,7 @@ int64_t b200nuts_launch_count(const B200Nuts* h);
 /* streaming regime: sweeps over X executed so far by b200nuts_run (one sweep serves one gradient of every chain) */
 int64_t b200nuts_pass_count(const B200Nuts* h);
 /* streaming regime: clock64 totals of the last run on CTA 0 (see StreamSync.dbg in stream_engine.cuh) */
-int b200nuts_debug_clocks(const B200Nuts* h, uint64_t* out8);
+int b200nuts_debug_clocks(const B200Nuts* h, uint64_t* out16);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,7 @@
 // their FMAs explicitly).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 #include <mutex>
@@ -24,9 +25,10 @@ struct B200Nuts {
     uint32_t* keys = nullptr;
     // R2
     float* partial = nullptr; float* beta = nullptr; StreamSync* sync = nullptr;
+    float* img = nullptr; long long n_tiles = 0; int pad_rows = 0, ks = 0;   // engine-owned tile image of (X, y)
     int grid = 0, stages = 4, vecs_in_smem = 0; size_t smem = 0;
     long long launches = 0, passes = 0;
-    unsigned long long dbg[8] = {0};
+    unsigned long long dbg[16] = {0};
     std::string err;
     std::mutex mu;
 };
@@ -171,17 +173,25 @@ __global__ void k_detmath(int op, const float* x, long long n, float* out) {
 }
 
 // ------------------------------------------------------------------------------------------------
-[[maybe_unused]] static int choose_rho(int D) {
-    static const int cand[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 48};
-    for (int r : cand) {
-        bool seen[4] = {false, false, false, false}; bool okk = true;
-        for (int k = 0; k < 4 && okk; ++k) {
-            const int off = (int)(((long long)D * r * k) % 32);
-            if (off % 8 != 0 || seen[off / 8]) okk = false; else seen[off / 8] = true;
-        }
-        if (okk) return r;
+template <int KS>
+static const void* stream_kernel_lik(int lik) {
+    return lik == LIK_BERNOULLI ? (const void*)stream_engine_kernel<KS, LIK_BERNOULLI>
+         : lik == LIK_POISSON   ? (const void*)stream_engine_kernel<KS, LIK_POISSON>
+                                : (const void*)stream_engine_kernel<KS, LIK_NORMAL>;
+}
+static const void* stream_kernel_for(int ks, int lik) {
+#ifdef B2_STREAM_FAST_BUILD        // development builds: the covtype instance only
+    return (ks == 7 && lik == LIK_BERNOULLI) ? (const void*)stream_engine_kernel<7, LIK_BERNOULLI> : nullptr;
+#else
+    switch (ks) {
+    case 1: return stream_kernel_lik<1>(lik);
+    case 2: return stream_kernel_lik<2>(lik);
+    case 4: return stream_kernel_lik<4>(lik);
+    case 7: return stream_kernel_lik<7>(lik);
+    case 8: return stream_kernel_lik<8>(lik);
+    default: return nullptr;
     }
-    return 1;
+#endif
 }
 
 static int stream_launch(B200Nuts* h, int mode, const OutBufs& out, const float* z_in, float* u_out, float* g_out,
@@ -191,14 +201,25 @@ static int stream_launch(B200Nuts* h, int mode, const OutBufs& out, const float*
     p.ctl = h->ctl; p.vecs = h->vecs; p.partial = h->partial; p.beta = h->beta; p.sync = h->sync;
     p.z_in = z_in; p.u_out = u_out; p.g_out = g_out; p.stages = h->stages;
     p.vecs_in_smem = h->vecs_in_smem; p.spin_limit = 6000000000LL;
+    p.img = h->img; p.n_tiles = h->n_tiles; p.pad_rows = h->pad_rows;
+    { const char* e = getenv("B200NUTS_DEBUG_SWEEP"); p.dbg_sweep = e ? atoi(e) : 0; }
     CK(cudaMemsetAsync(h->sync, 0, sizeof(StreamSync), st));
     void* args[] = {&p};
-    const int need = (h->fam.Dx + 7) / 8;
-    const void* fn = need <= 1 ? (const void*)stream_engine_kernel<1> : need <= 2 ? (const void*)stream_engine_kernel<2>
-                   : need <= 4 ? (const void*)stream_engine_kernel<4> : need <= 7 ? (const void*)stream_engine_kernel<7>
-                                                                                : (const void*)stream_engine_kernel<8>;
+    const void* fn = stream_kernel_for(h->ks, h->fam.likelihood);
+    if (!fn) { h->err = "stream regime: no kernel instance for this shape"; return B200NUTS_EINVAL; }
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    CK(cudaLaunchCooperativeKernel(fn, dim3(h->grid), dim3(kStreamThreads), args, h->smem, st));
+    {
+        cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(h->grid), dim3(kStreamThreads), args, h->smem, st);
+        if (le != cudaSuccess) {
+            cudaFuncAttributes fa; memset(&fa, 0, sizeof(fa)); cudaFuncGetAttributes(&fa, fn);
+            int occ = -1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kStreamThreads, h->smem);
+            char buf[256];
+            snprintf(buf, sizeof(buf), " [regs %d, maxThreadsPerBlock %d, static smem %zu, dynamic smem %zu, threads %d, blocks/SM %d]",
+                     fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, h->smem, kStreamThreads, occ);
+            h->err = std::string("cudaLaunchCooperativeKernel: ") + cudaGetErrorString(le) + buf;
+            return B200NUTS_ECUDA;
+        }
+    }
     h->launches += 1;
     return 0;
 }
@@ -208,7 +229,7 @@ static int check_stream_abort(B200Nuts* h, cudaStream_t st) {
     CK(cudaMemcpyAsync(&s, h->sync, sizeof(s), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     h->passes += (long long)s.passes;
-    for (int i = 0; i < 8; ++i) h->dbg[i] = s.dbg[i];
+    for (int i = 0; i < 16; ++i) h->dbg[i] = s.dbg[i];
     if (s.abort_flag) { h->err = "stream engine aborted: inter-pass exchange timed out"; return B200NUTS_ECUDA; }
     return 0;
 }
@@ -220,9 +241,9 @@ int b200nuts_dim(const B200Nuts* h) { return h ? h->D : B200NUTS_EINVAL; }
 int b200nuts_regime(const B200Nuts* h) { return h ? h->regime : B200NUTS_EINVAL; }
 int64_t b200nuts_launch_count(const B200Nuts* h) { return h ? h->launches : 0; }
 int64_t b200nuts_pass_count(const B200Nuts* h) { return h ? h->passes : 0; }
-int b200nuts_debug_clocks(const B200Nuts* h, uint64_t* out8) {
-    if (!h || !out8) return B200NUTS_EINVAL;
-    for (int i = 0; i < 8; ++i) out8[i] = h->dbg[i];
+int b200nuts_debug_clocks(const B200Nuts* h, uint64_t* out16) {
+    if (!h || !out16) return B200NUTS_EINVAL;
+    for (int i = 0; i < 16; ++i) out16[i] = h->dbg[i];
     return 0;
 }
 
@@ -236,7 +257,7 @@ int b200nuts_constrained_dim(const B200Nuts* h) {
 void b200nuts_destroy(B200Nuts* h) {
     if (!h) return;
     cudaFree(h->ctl); cudaFree(h->vecs); cudaFree(h->gtmp); cudaFree(h->scratch); cudaFree(h->keys);
-    cudaFree(h->partial); cudaFree(h->beta); cudaFree(h->sync);
+    cudaFree(h->partial); cudaFree(h->beta); cudaFree(h->sync); cudaFree(h->img);
     delete h;
 }
 
@@ -297,14 +318,23 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
         h->grid = h->num_sms;
         int max_smem = 0;
         cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+        h->ks = stream_ks_for(h->fam.Dx);
         h->stages = 0;
         for (int vs = 1; vs >= 0 && !h->stages; --vs)
-            for (int stg = kMaxStages; stg >= 8; --stg)      // 7 tiles are being processed at any time
-                if (stream_smem_bytes(h->fam.Dx, h->Dp, stg, vs != 0) <= (size_t)max_smem) {
+            for (int stg = kMaxStages; stg >= 2; --stg)      // slots per consumer warp: one in use, the others in flight
+                if (stream_smem_bytes(h->ks, h->Dp, stg, vs != 0) <= (size_t)max_smem) {
                     h->stages = stg; h->vecs_in_smem = vs; break;
                 }
         if (!h->stages) { g_create_err = "stream regime: shared memory budget exceeded"; b200nuts_destroy(h); return B200NUTS_EINVAL; }
-        h->smem = stream_smem_bytes(h->fam.Dx, h->Dp, h->stages, h->vecs_in_smem != 0);
+        h->smem = stream_smem_bytes(h->ks, h->Dp, h->stages, h->vecs_in_smem != 0);
+        // engine-owned tile image of (X, y): one contiguous block per 32 rows (stream_engine.cuh)
+        h->n_tiles = (h->fam.N + kTileRows - 1) / kTileRows;
+        h->pad_rows = (int)(h->n_tiles * kTileRows - h->fam.N);
+        const size_t img_floats = (size_t)h->n_tiles * stream_tile_floats(h->ks);
+        if ((ce = cudaMalloc(&h->img, sizeof(float) * img_floats)) != cudaSuccess) return fail("cudaMalloc tile image", ce);
+        k_stream_repack<<<h->num_sms * 8, 256>>>(h->fam.X, h->fam.y, h->fam.N, h->fam.Dx, stream_pitch(h->ks), h->n_tiles, h->img);
+        if ((ce = cudaGetLastError()) != cudaSuccess) return fail("repack", ce);
+        h->launches += 1;
         if ((ce = cudaMalloc(&h->partial, sizeof(float) * (size_t)h->grid * kStreamCT * kGStride)) != cudaSuccess) return fail("cudaMalloc partial", ce);
         if ((ce = cudaMalloc(&h->beta, sizeof(float) * kStreamCT * 64)) != cudaSuccess) return fail("cudaMalloc beta", ce);
         if ((ce = cudaMalloc(&h->sync, sizeof(StreamSync))) != cudaSuccess) return fail("cudaMalloc sync", ce);

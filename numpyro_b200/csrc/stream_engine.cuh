@@ -9,21 +9,35 @@
 // (tick.cuh): chain c is owned by the tick warp of CTA c, with its ~10 KB of tree state resident in
 // that CTA's shared memory for the whole launch.
 //
-// CTA = 16 warps: warp 0 producer, warps 1..14 consumers (7 pairs), warp 15 tick.
-// Data movement: X is consumed in its natural [N, D] row-major fp32 layout.  The producer streams
-// contiguous 64-row tiles (13.8 KB at D = 54) into a <=12-deep shared-memory ring with 1-D bulk
-// async copies (cp.async.bulk + mbarrier complete_tx); it free-runs across passes (X is the same
-// every pass), so the ring keeps refilling during the inter-pass exchange.
-// Compute mapping (tile t belongs to consumer pair t mod 7, each warp takes 32 of its 64 rows):
-//   forward : half-warp h owns chains 4h..4h+3, lane l owns rows l and l+16; x comes as 8-byte
-//             loads down the lane's own rows (conflict-free when D/2 is odd), beta as 16-byte
-//             broadcast loads from shared memory; 8 logits per lane, no cross-lane reduction;
-//   link    : each lane evaluates its 8 (row, chain) losses/residuals, residuals go to a 1 KB
-//             per-warp buffer;
-//   backward: half-warp h again owns chains 4h..4h+3, lane q owns 4 columns; per row one pair of
-//             8-byte x loads, one 16-byte residual load and 8 packed FMAs into register accumulators
-//             that live for the whole pass.
-// FMAs are issued as packed fma.rn.f32x2 (SASS FFMA2).
+// Data layout.  b200nuts_create repacks the caller's X [N, D] / y [N] once into an engine-owned
+// *tile image* in HBM.  Tile i = rows 16i .. 16i+15 and their 16 responses, one contiguous 16-byte
+// aligned block moved by ONE 1-D bulk async copy (cp.async.bulk + mbarrier complete_tx).  Inside a
+// tile rows r and r+8 are interleaved ("pair rows"): the four floats
+//     { X[r][c], X[r+8][c], X[r][c+1], X[r+8][c+1] }            (r < 8, c even)
+// are adjacent.  That quad IS the A fragment of the forward mma.sync (rows g / g+8, k = t / t+4) and
+// its two halves ARE B fragments of the backward one (k = t / t+4 rows, n = column), so every
+// fragment is filled by a single 128-bit shared-memory load with no register shuffling.  Columns are
+// padded to P = 8*odd floats and 16-byte chunks are XOR-swizzled by bit 1 of the pair row, which
+// makes both access patterns bank-conflict free.
+//
+// CTA = 14 warps: warps 0..12 consumers, warp 13 tick.  Tile t of a CTA's slice belongs to consumer
+// warp t mod 13 (static assignment: the summation order is fixed, results are bit-reproducible).
+// Every consumer warp runs its own private ring of `stages` slots and refills a slot itself the
+// moment it has finished reading it (one elected lane: expect_tx + bulk copy) -- measured on B200, a
+// single issuing thread needs ~680 cycles per copy round trip and caps a CTA at ~3 TB/s chip-wide, 15
+// independent issuers do not.  The tile sequence of a warp simply wraps around at the end of a pass
+// (X is the same every pass), so the first `stages` tiles of the next pass are already in flight
+// while the chains exchange gradients.
+// Per tile (mma.sync m16n8k8, TF32 operands split hi/lo, fp32 accumulate -- fp32-level accuracy):
+//   forward : logits[16 rows][8 chains] = X_t beta, 3 products (lo*hi, hi*lo, hi*hi) in independent
+//             accumulator chains; beta lives in B fragments in registers for the whole pass;
+//   link    : each lane owns 4 (row, chain) pairs: loss + residual (ex2/lg2/rcp);
+//   shuffle : residuals move from C-fragment to A-fragment layout (8 shuffles), split hi/lo and
+//             *stacked*: A = [r_hi ; r_lo]^T (16 x 8 rows);
+//   backward: gbeta^T[chain][col] += A X_t, X as the B operand (hi then lo part): rows 0..7 of the
+//             result collect r_hi x, rows 8..15 the r_lo x correction; 8 columns per MMA.  A chunk of 16
+//             columns accumulates over the tile's 2 k-steps on the tensor core, then joins the
+//             per-pass fp32 accumulators with FADDs.
 // Inter-pass exchange (deterministic, no float atomics): per-CTA partials -> global; chain c's
 // CTA sums the partials in fixed order, its tick warp finishes the potential (priors, Jacobians),
 // ticks the chain and publishes the next beta_c; two monotone counters replace grid.sync.
@@ -35,18 +49,31 @@
 namespace b2 {
 
 constexpr int kStreamCT = 8;             // chains per pass
-constexpr int kConsWarps = 14;           // consumer warps = 7 pairs
-constexpr int kPairs = kConsWarps / 2;
-constexpr int kStreamThreads = 32 * (kConsWarps + 2);
-constexpr int kTileRows = 64;            // rows per ring slot (two 32-row units)
-constexpr int kMaxStages = 12;
+constexpr int kConsWarps = 13;           // consumer warps
+constexpr int kStreamThreads = 32 * (kConsWarps + 1);
+constexpr int kTileRows = 16;            // rows per ring slot = one consumer warp's unit of work
+constexpr int kMaxStages = 4;            // tile slots per consumer warp (4: tiles are consumed in pairs)
 constexpr int kGStride = 72;             // floats per (cta, chain) partial: gbeta[<=64], nll, pad
+constexpr int kRedWarps = (kConsWarps + 1) / 2;   // rows of the two-stage CTA reduction scratch
+constexpr int kXRedFloats = 5 * kGStride + 192;   // owner CTA: 5 segment sums + gradient scratch for the tick
 constexpr int kBarTop = 1, kBarCons = 2, kBarTick = 3;
-constexpr int kConsThreads = kConsWarps * 32, kTopThreads = (kConsWarps + 1) * 32;
+constexpr int kConsThreads = kConsWarps * 32, kTopThreads = kStreamThreads;
 
-// dbg: clock64 totals on CTA 0 -- [0] wait for betas, [1] sweep + publish partial, [2] wait for all partials,
-// [3] cross-CTA reduction, [4] finish + tick + publish beta, [5] total loop
-struct StreamSync { unsigned int arrive, ready, done, abort_flag; unsigned long long passes; unsigned long long dbg[8]; };
+B2_HD constexpr int stream_pitch(int KS) { return (KS % 2 == 0) ? 8 * KS + 8 : 8 * KS; }     // 8 * odd
+// float offset of element (row r, column c) of a tile, r in [0, 16), c in [0, P)
+B2_HD int stream_tile_index(int P, int r, int c) {
+    const int pr = r & 7, hi = (r >> 3) & 1;
+    const int chunk = (c >> 1) ^ (((pr >> 1) & 1) << 1);
+    return pr * 2 * P + 4 * chunk + 2 * (c & 1) + hi;
+}
+B2_HD int stream_tile_y_index(int P, int r) { return kTileRows * P + (r & 7) * 2 + ((r >> 3) & 1); }
+B2_HD constexpr int stream_tile_floats(int KS) { return kTileRows * stream_pitch(KS) + kTileRows; }
+B2_HD constexpr int stream_ks_for(int D) { return D <= 8 ? 1 : D <= 16 ? 2 : D <= 32 ? 4 : D <= 56 ? 7 : 8; }
+
+// dbg: clock64 totals on CTA 0 -- [0] wait for betas (incl. the owners' ticks), [1] sweep, [2] CTA reduction +
+// publish partial, [3] wait for all partials, [4] cross-CTA reduction, [5] total loop, [6] tick warp busy,
+// [7] beta -> fragments, [8] tick: finish potential, [9] tick: state machine, [10] tick: publish beta
+struct StreamSync { unsigned int arrive, ready, done, abort_flag; unsigned long long passes; unsigned long long dbg[16]; };
 
 struct StreamParams {
     TickCfg cfg; FamilySpec fam; OutBufs out;
@@ -56,8 +83,12 @@ struct StreamParams {
     float* beta;                         // [kStreamCT][64]
     StreamSync* sync;
     const float* z_in; float* u_out; float* g_out;    // mode 1
-    int stages;                          // depth of the shared-memory ring
+    const float* img;                    // tile image of (X, y), see above
+    long long n_tiles;                   // tiles in the image
+    int pad_rows;                        // zero rows appended to fill the last tile
+    int stages;                          // slots in every consumer warp's private ring
     int vecs_in_smem;
+    int dbg_sweep;                       // timing experiments only: 1 = copies without compute, 2 = compute without copies
     long long spin_limit;
 };
 
@@ -89,13 +120,6 @@ B2_D unsigned int ld_acquire(const unsigned int* p) {
 B2_D void red_release_add(unsigned int* p, unsigned int v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-B2_D unsigned long long pack2(float lo, float hi) {
-    unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
-}
-B2_D void unpack2(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-B2_D void ffma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
-}
 // tf32 split: hi keeps the top 19 bits (exactly what the tensor core consumes), lo = x - hi (exact in fp32;
 // its own low bits are dropped by the MMA: relative error 2^-22 of x).
 B2_D void tf32_split(uint32_t& hi, uint32_t& lo) {
@@ -103,13 +127,54 @@ B2_D void tf32_split(uint32_t& hi, uint32_t& lo) {
     lo = __float_as_uint(__uint_as_float(hi) - __uint_as_float(h));
     hi = h;
 }
-B2_D void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+B2_D void split4(const float (&x)[4], uint32_t (&hi)[4], uint32_t (&lo)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { hi[i] = __float_as_uint(x[i]); tf32_split(hi[i], lo[i]); }
 }
+// (not volatile: pure functions of their operands, the compiler may interleave independent chains)
+B2_D void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+B2_D void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// two fp32 -> packed bf16x2 (round to nearest even): first -> bits [15:0] (the lower k index of an MMA fragment)
+B2_D uint32_t pack_bf16(float first, float second) {
+    uint32_t d; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(second), "f"(first)); return d;
+}
+// lo part of the tf32 split: x - trunc_tf32(x), exact in fp32
+B2_D float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 template <int ID, int N> B2_D void bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
 template <int ID, int N> B2_D void bar_arrive() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
+B2_D float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+B2_D float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+B2_D float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// Per-observation loss and d loss / d eta with the hardware ex2/lg2/rcp approximations (relative
+// error ~1e-7 per term, far inside the rtol 1e-5 parity budget once summed over rows).  Same
+// formulas as glm_loss (families.cuh): distributions/util.py:317-320, discrete.py:1388.
+template <int LIK>
+B2_D void link_fn(float eta, float y, float& loss, float& dl) {
+    if (LIK == LIK_BERNOULLI) {
+        const float e = ex2_approx(fabsf(eta) * -1.4426950408889634f);       // exp(-|eta|), in (0, 1]
+        const float ope = 1.0f + e;
+        loss = __fmaf_rn(lg2_approx(ope), 0.6931471805599453f, __fmaf_rn(-eta, y, fmaxf(eta, 0.0f)));
+        const float s = rcp_approx(ope);                                     // sigmoid(|eta|)
+        dl = ((eta >= 0.0f) ? s : (1.0f - s)) - y;
+    } else if (LIK == LIK_POISSON) {
+        const float r = ex2_approx(eta * 1.4426950408889634f);
+        loss = __fmaf_rn(-y, eta, r);
+        dl = r - y;
+    } else {
+        const float res = eta - y;
+        loss = 0.5f * res * res;
+        dl = res;
+    }
+}
 
 // Spin until *ctr >= target.  Gives up (and raises the abort flag for everybody) after spin_limit
 // clocks so that a protocol bug can never wedge the GPU.
@@ -124,71 +189,125 @@ B2_D bool spin_ge(const unsigned int* ctr, unsigned int target, StreamSync* sy, 
 
 B2_HD size_t stream_fixed_smem(int Dp, bool vecs_in_smem) {
     size_t b = 0;
-    b += 2 * kMaxStages * 8;                                       // mbarriers
+    b += (size_t)kConsWarps * kMaxStages * 8;                      // mbarriers
     b += 64 * kStreamCT * 4;                                       // beta, [d][chain]
-    b += (size_t)kConsWarps * 32 * kStreamCT * 4;                  // residual buffers, [warp][row][chain]
-    b += (size_t)kConsWarps * kStreamCT * kGStride * 4;            // cross-warp reduction + tick scratch
-    b += 64 * 4 + 64 * 4 + 64 + 64;                                // gred(+nll), tail tile header, flags, timers
-    b += 16 * 64 * 4 + 64;                                         // tail group (<= 3 valid rows of a zeroed 16 x 64 block) + y
+    b += (size_t)kRedWarps * 16 * 32 * 4;                          // CTA reduction scratch, [warp][value][lane]
+    b += (size_t)kXRedFloats * 4;                                  // cross-CTA reduction + tick scratch
+    b += 64 * 4 + 64 * 4 + 64 + 128;                               // gred(+nll), flags, timers
     b += ((sizeof(ChainCtl) + 15) / 16) * 16;
     if (vecs_in_smem) b += (size_t)V_COUNT * Dp * 4;
     return b + 128;
 }
-B2_HD size_t stream_smem_bytes(int D, int Dp, int stages, bool vecs_in_smem) {
-    return stream_fixed_smem(Dp, vecs_in_smem) + (size_t)stages * ((size_t)kTileRows * D * 4 + kTileRows * 4);
+B2_HD size_t stream_smem_bytes(int KS, int Dp, int stages, bool vecs_in_smem) {
+    return stream_fixed_smem(Dp, vecs_in_smem) + (size_t)kConsWarps * stages * stream_tile_floats(KS) * 4;
 }
 
-// KS = ceil(D / 8): k-steps of the forward MMA (compile time so every fragment stays in registers).
-template <int KS>
-__global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const StreamParams p) {
+// One-time repack of the caller's (X, y) into the tile image (see the header comment).
+__global__ void k_stream_repack(const float* __restrict__ X, const float* __restrict__ y, long long N, int D, int P,
+                                long long n_tiles, float* __restrict__ img) {
+    const long long tile_floats = (long long)kTileRows * P + kTileRows;
+    const long long per_tile = (long long)kTileRows * (P + 1);          // (row, column) pairs incl. the y "column" P
+    const long long total = n_tiles * per_tile;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long tile = i / per_tile; const int o = (int)(i - tile * per_tile);
+        const int r = o / (P + 1), c = o - r * (P + 1);
+        const long long row = tile * kTileRows + r;
+        float v = 0.0f;
+        if (c < P) {
+            if (row < N && c < D) v = X[row * D + c];
+            img[tile * tile_floats + stream_tile_index(P, r, c)] = v;
+        } else {
+            if (row < N) v = y[row];
+            img[tile * tile_floats + stream_tile_y_index(P, r)] = v;
+        }
+    }
+}
+
+// beta_c = s(z) * u for the next sweep (zero when the chain is done), published to global memory
+B2_D void stream_publish_beta(const StreamParams& p, int cta, const float* zsrc, bool active) {
+    const int lane = threadIdx.x & 31;
+    float* bout = p.beta + (size_t)cta * 64;
+    for (int d = lane; d < 64; d += 32) {
+        float b = 0.0f;
+        if (active && d < p.fam.Dx) b = glm_scale_at(p.fam, zsrc, d) * zsrc[p.fam.off_u + d];
+        __stcg(bout + d, b);
+    }
+    __syncwarp();
+}
+
+// The tick warp's work between two sweeps, for the chain owned by this CTA: finish the potential from the
+// reduced likelihood sums, advance the NUTS state machine, publish the next beta.  Deliberately not inlined:
+// it is the same code for every kernel instance.  Returns true when the chain needs no further gradient.
+__device__ __noinline__ bool stream_tick_step(const StreamParams& p, ChainCtl* sctl, ChainVecs cv, const float* gred,
+                                              float* gz, float nll, int cta, unsigned long long* tdbg) {
+    const int lane = threadIdx.x & 31;
+    const bool dbg = (cta == 0 && lane == 0);
+    long long t0 = dbg ? clock64() : 0ll;
+#define B2_TICK_LAP(k) do { __syncwarp(); if (dbg) { const long long t1 = clock64(); tdbg[k] += (unsigned long long)(t1 - t0); t0 = t1; } } while (0)
+    float u;
+    if (p.mode == 1) {
+        const float* zin = p.z_in + (size_t)cta * p.cfg.D;
+        glm_finish(p.fam, zin, nll, gred, u, gz);
+        __syncwarp();
+        if (lane == 0) p.u_out[cta] = u;
+        for (int d = lane; d < p.cfg.D; d += 32) p.g_out[(size_t)cta * p.cfg.D + d] = gz[d];
+        return true;
+    }
+    if (sctl->phase == PH_DONE) return false;
+    ChainCtl c = *sctl;
+    __syncwarp();
+    glm_finish(p.fam, cv.v(V_ZS), nll, gred, u, gz);
+    B2_TICK_LAP(8);
+    Tick tk{p.cfg, c, cv, p.out, cta, p.C};
+    tk.advance(u, gz);
+    __syncwarp();
+    if (lane == 0) *sctl = c;
+    const bool finished = (c.phase == PH_DONE);
+    B2_TICK_LAP(9);
+    stream_publish_beta(p, cta, cv.v(V_ZS), !finished);
+    B2_TICK_LAP(10);
+#undef B2_TICK_LAP
+    return finished;
+}
+
+struct StreamOne { static constexpr int value = 1; };
+struct StreamTwo { static constexpr int value = 2; };
+
+// KS = columns / 8 of the padded tile (compile time so every fragment stays in registers), LIK = likelihood.
+template <int KS, int LIK>
+__global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const __grid_constant__ StreamParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int D = p.fam.Dx;                        // columns of X (coefficients)
+    constexpr int P = stream_pitch(KS);            // row pitch of a tile, floats
+    constexpr int TILE_FLOATS = stream_tile_floats(KS);
+    constexpr int NCH = KS / 2;                    // backward: 16-column chunks (two 8-column MMAs per 128-bit load)
+    constexpr bool ODD = (KS & 1) != 0;            // ... + one 8-column chunk (64-bit loads) when KS is odd
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x, cta = blockIdx.x;
     const int nst = p.stages;
 
     // ---- carve shared memory
     unsigned char* q = smem_raw;
-    float* tiles = (float*)q; q += (size_t)nst * kTileRows * D * 4;
-    float* ytiles = (float*)q; q += (size_t)nst * kTileRows * 4;
-    uint64_t* full = (uint64_t*)q; q += kMaxStages * 8;
-    uint64_t* empty = (uint64_t*)q; q += kMaxStages * 8;
+    float* tiles = (float*)q; q += (size_t)kConsWarps * nst * TILE_FLOATS * 4;
+    uint64_t* full = (uint64_t*)q; q += (size_t)kConsWarps * kMaxStages * 8;
     float* bs = (float*)q; q += 64 * kStreamCT * 4;
-    float* rbuf_all = (float*)q; q += (size_t)kConsWarps * 32 * kStreamCT * 4;
-    float* red = (float*)q; q += (size_t)kConsWarps * kStreamCT * kGStride * 4;
+    float* red = (float*)q; q += (size_t)kRedWarps * 16 * 32 * 4;
+    float* xred = (float*)q; q += (size_t)kXRedFloats * 4;
     float* gred = (float*)q; q += 64 * 4 + 64 * 4;
     int* flags = (int*)q; q += 64;
-    unsigned long long* tdbg = (unsigned long long*)q; q += 64;
-    float* tail = (float*)q; q += 16 * 64 * 4 + 64;            // rows N - N%4 .. N-1 in a zeroed 16-row group, then their y
+    unsigned long long* tdbg = (unsigned long long*)q; q += 128;
     ChainCtl* sctl = (ChainCtl*)q; q += ((sizeof(ChainCtl) + 15) / 16) * 16;
     float* cvecs = (float*)q;
-    const int tile_floats = kTileRows * D;
 
-    // ---- this CTA's slice of rows, in units of 4 rows so every tile start is 16-byte aligned
-    const long long N = p.fam.N;
-    const long long Q = N / 4;
-    const long long q0 = Q * cta / G, q1 = Q * (cta + 1) / G;
-    const long long row0 = 4 * q0, row1 = 4 * q1;
-    const int n_tiles = (int)((row1 - row0 + kTileRows - 1) / kTileRows);
+    // ---- this CTA's slice of tiles
+    const long long t_begin_tile = p.n_tiles * cta / G, t_end_tile = p.n_tiles * (cta + 1) / G;
+    const int n_tiles = (int)(t_end_tile - t_begin_tile);
     const bool is_tick = cta < p.C;
-    const int n_tail = (cta == G - 1) ? (int)(N % 4) : 0;
 
-    // ---- one-time setup: zero the ring (stale words must be finite), init barriers
-    for (int i = tid; i < nst * (tile_floats + kTileRows); i += blockDim.x) tiles[i] = 0.0f;
-    for (int i = tid; i < kConsWarps * kStreamCT * kGStride; i += blockDim.x) red[i] = 0.0f;
-    for (int i = tid; i < 16 * 64 + 16; i += blockDim.x) {
-        float v = 0.0f;
-        if (n_tail > 0) {
-            if (i < 16 * 64) { const int r = i / D, d = i - r * D; if (i < n_tail * D) v = p.fam.X[(4 * Q + r) * D + d]; }
-            else if (i - 16 * 64 < n_tail) v = p.fam.y[4 * Q + (i - 16 * 64)];
-        }
-        tail[i] = v;
-    }
+    // ---- one-time setup: init barriers, stage the chain
     if (tid == 0) {
-        for (int i = 0; i < nst; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2); }
+        for (int i = 0; i < kConsWarps * kMaxStages; ++i) mbar_init(&full[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        flags[0] = 0;                                // stop flag for the producer
-        for (int i = 0; i < 8; ++i) tdbg[i] = 0ull;
+        for (int i = 0; i < 16; ++i) tdbg[i] = 0ull;
     }
     ChainVecs cv; cv.base = nullptr; cv.field_stride = 0;
     if (is_tick) {
@@ -204,58 +323,19 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
-    // =============================================================== producer warp
-    if (warp == 0) {
-        if (lane == 0 && n_tiles > 0) {
-            uint32_t it = 0;
-            while (true) {
-                for (int t = 0; t < n_tiles; ++t, ++it) {
-                    const int st = it % nst; const uint32_t ph = (it / nst) & 1u;
-                    if (it >= (uint32_t)nst) {
-                        // wait for both consumer warps of the slot's previous tile; leave early when told to stop
-                        while (!mbar_try_wait(&empty[st], ph ^ 1u)) {
-                            if (*(volatile int*)&flags[0]) goto producer_done;
-                        }
-                    }
-                    if (*(volatile int*)&flags[0]) goto producer_done;
-                    const long long r = row0 + (long long)t * kTileRows;
-                    const int rows = (int)((row1 - r < kTileRows) ? (row1 - r) : kTileRows);
-                    const uint32_t xb = (uint32_t)rows * (uint32_t)D * 4u, yb = (uint32_t)rows * 4u;
-                    mbar_expect_tx(&full[st], xb + yb);
-                    bulk_g2s(tiles + (size_t)st * tile_floats, p.fam.X + r * D, xb, &full[st]);
-                    bulk_g2s(ytiles + (size_t)st * kTileRows, p.fam.y + r, yb, &full[st]);
-                }
-            }
-        producer_done:
-            {   // drain: every issued copy must have landed before the CTA may exit
-                const uint32_t issued = it;
-                const uint32_t first = issued > (uint32_t)nst ? issued - nst : 0u;
-                for (uint32_t k = first; k < issued; ++k) mbar_wait(&full[k % nst], (k / nst) & 1u);
-            }
-        }
-        return;
-    }
-
     StreamSync* sy = p.sync;
     unsigned int pass = 0;
 
     // =============================================================== tick warp
-    if (warp == kConsWarps + 1) {
+    if (warp == kConsWarps) {
         const bool dbg = (cta == 0 && lane == 0);
-        long long t_prev = clock64();
-        auto publish_beta = [&](const float* zsrc, bool active) {
-            float* bout = p.beta + (size_t)cta * 64;
-            for (int d = lane; d < 64; d += 32) {
-                float b = 0.0f;
-                if (active && d < D) b = glm_scale_at(p.fam, zsrc, d) * zsrc[p.fam.off_u + d];
-                __stcg(bout + d, b);
-            }
-            __syncwarp();
-        };
+        float loss0, dl0;
+        link_fn<LIK>(0.0f, 0.0f, loss0, dl0);        // what every zero pad row adds to a chain's nll
+        const float pad_nll = (float)p.pad_rows * loss0;
         if (is_tick) {                               // prologue: the first beta
             const float* zsrc = (p.mode == 0) ? cv.v(V_ZS) : (p.z_in + (size_t)cta * p.cfg.D);
             const bool active = (p.mode == 1) || (sctl->phase != PH_DONE);
-            publish_beta(zsrc, active);
+            stream_publish_beta(p, cta, zsrc, active);
             if (lane == 0) {
                 if (p.mode == 0 && sctl->phase == PH_DONE) atomicAdd(&sy->done, 1u);
                 __threadfence();
@@ -266,42 +346,22 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
             bar_sync<kBarTop, kTopThreads>();
             if (!flags[1] || flags[2] >= p.C) break;
             if (is_tick) {
-                bar_sync<kBarTick, kTopThreads>();   // segment sums are in `red`
-                if (dbg) t_prev = clock64();
+                bar_sync<kBarTick, kTopThreads>();   // segment sums are in `xred`
                 if (flags[3]) {
+                    const long long t_a = dbg ? clock64() : 0ll;
                     for (int d = lane; d < 65; d += 32)
-                        gred[d] = (((red[d] + red[kGStride + d]) + red[2 * kGStride + d]) + red[3 * kGStride + d]) +
-                                  red[4 * kGStride + d];
+                        gred[d] = (((xred[d] + xred[kGStride + d]) + xred[2 * kGStride + d]) + xred[3 * kGStride + d]) +
+                                  xred[4 * kGStride + d];
                     __syncwarp();
-                    const float nll = gred[64];
-                    float* gz = red + 8 * kGStride;  // scratch for the gradient wrt z (<= Dp floats)
-                    float u;
-                    bool finished = false;
-                    if (p.mode == 1) {
-                        const float* zin = p.z_in + (size_t)cta * p.cfg.D;
-                        glm_finish(p.fam, zin, nll, gred, u, gz);
-                        __syncwarp();
-                        if (lane == 0) p.u_out[cta] = u;
-                        for (int d = lane; d < p.cfg.D; d += 32) p.g_out[(size_t)cta * p.cfg.D + d] = gz[d];
-                        finished = true;
-                    } else if (sctl->phase != PH_DONE) {
-                        ChainCtl c = *sctl;
-                        __syncwarp();
-                        glm_finish(p.fam, cv.v(V_ZS), nll, gred, u, gz);
-                        __syncwarp();
-                        Tick tk{p.cfg, c, cv, p.out, cta, p.C};
-                        tk.advance(u, gz);
-                        __syncwarp();
-                        if (lane == 0) *sctl = c;
-                        finished = (c.phase == PH_DONE);
-                        publish_beta(cv.v(V_ZS), !finished);
-                    }
+                    const float nll = gred[64] - pad_nll;
+                    float* gz = xred + 5 * kGStride; // scratch for the gradient wrt z (<= Dp floats)
+                    const bool finished = stream_tick_step(p, sctl, cv, gred, gz, nll, cta, tdbg);
                     __syncwarp();
                     if (lane == 0) {
                         if (finished) atomicAdd(&sy->done, 1u);
                         __threadfence();
                         red_release_add(&sy->ready, 1u);
-                        if (dbg) tdbg[4] += (unsigned long long)(clock64() - t_prev);
+                        if (dbg) tdbg[6] += (unsigned long long)(clock64() - t_a);
                     }
                 }
             }
@@ -312,93 +372,148 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
     }
 
     // =============================================================== consumer warps
-    const int cw = warp - 1;                         // 0..13
-    const int ctid = tid - 32;                       // 0..447
-    const int pair = cw >> 1, half = cw & 1;         // tile owner pair, which 32 rows of the tile
+    const int cw = warp;                             // 0..12
+    const int ctid = tid;                            // 0..415
     const int g = lane >> 2, t = lane & 3;           // mma.sync fragment coordinates (groupID, threadID_in_group)
-    constexpr int MT = (KS + 1) / 2;                 // 16-column tiles of the backward product
-    uint32_t bhi[KS][2], blo[KS][2];                 // beta as B fragments of the forward MMA, tf32 hi / lo parts
-    float gacc[MT][4];                               // gbeta in C-fragment layout: d = 16mt + g (+8), chain 2t (+1)
-    float nll[2];                                    // loss of chains 2t, 2t+1 over this lane's rows
-    uint32_t tiles_done = 0;                         // running tile counter of this CTA (ring position)
+    // float offsets inside a tile (stream_tile_index): forward lane (g, t) reads pair row g, columns
+    // 8kk + 2t, +1; backward lane (g, t) reads pair row 4ks + t, columns 16j + 2g, +1 (or 16*NCH + g)
+    const int off_f = g * 2 * P + 4 * (t ^ (((g >> 1) & 1) << 1));
+    const int off_b = t * 2 * P + 4 * (g ^ (((t >> 1) & 1) << 1));
+    const int off_b1 = t * 2 * P + 4 * (8 * NCH + ((g >> 1) ^ (((t >> 1) & 1) << 1))) + 2 * (g & 1);
+    const int src_ks0 = (t << 2) | (g >> 1), src_ks1 = ((4 + t) << 2) | (g >> 1);   // shuffle sources, see unit()
+    uint32_t bhi[KS][2], bbf[KS][2];                 // beta as B fragments of the forward MMAs: tf32 (raw fp32 bits; the
+                                                     // tensor core reads the top 19) and bf16x2 {hi part, lo part}
+    float gacc[KS][4];                               // gbeta^T in C-fragment layout: chain g, columns bwd_col(nt, 2t / 2t+1);
+                                                     // [0], [1] = r_hi part, [2], [3] = r_lo part
+    float nll[2] = {0.0f, 0.0f};                     // loss of chains 2t, 2t+1 over this lane's rows
+
+    // ---- this warp's private ring: its tiles are w, w + 13, w + 26, ... of the CTA's slice, over and over
+    const int n_mine = (n_tiles > cw) ? (n_tiles - cw + kConsWarps - 1) / kConsWarps : 0;
+    float* my_tiles = tiles + (size_t)cw * nst * TILE_FLOATS;
+    uint64_t* my_full = full + cw * kMaxStages;
+    const float* my_src = p.img + (t_begin_tile + cw) * TILE_FLOATS;
+    auto issue = [&](int slot, int j) {              // one lane: tile j of this warp -> slot
+        mbar_expect_tx(&my_full[slot], TILE_FLOATS * 4u);
+        bulk_g2s(my_tiles + (size_t)slot * TILE_FLOATS, my_src + (size_t)j * kConsWarps * TILE_FLOATS, TILE_FLOATS * 4u, &my_full[slot]);
+    };
+    int slot = 0; uint32_t parity = 0;               // ring position of the next tile to consume
+    if (lane == 0 && n_mine > 0)
+        for (int s = 0; s < nst; ++s) issue(s, s % n_mine);
+    const bool pairs = (nst == 4);                   // consume two tiles at a time (two independent instruction streams)
 
     const bool dbg = (cta == 0 && ctid == 0);
     long long t_prev = clock64();
     const long long t_begin = t_prev;
 #define B2_DBG_LAP(k) do { if (dbg) { const long long t_now = clock64(); tdbg[k] += (unsigned long long)(t_now - t_prev); t_prev = t_now; } } while (0)
 
-    // One 32-row unit = two 16-row groups.  Per group: forward MMA (logits), link function in the
-    // C-fragment layout (4 (row, chain) pairs per lane, no reduction), residuals shuffled into B-fragment
-    // layout, backward MMA (gbeta).  All products are 3xTF32 (hi*hi + hi*lo + lo*hi, fp32 accumulate).
-    // Row permutations inside a group are chosen so every LDS.32 is bank-conflict free at D = 54:
-    // forward fragment rows (g, g+8) <-> data rows (2g, 2g+1); backward k index (t, t+4) <-> rows (4t+2ks, +1).
-    auto unit = [&](const float* xt, const float* yt, int nvalid) {
-#pragma unroll 1
-        for (int grp = 0; grp < 2; ++grp) {
-            if (16 * grp >= nvalid) break;
-            const float* xg = xt + 16 * grp * D;
-            const float* yg = yt + 16 * grp;
-            const int nv = nvalid - 16 * grp;
-            // ---- forward
-            const float* xa = xg + (2 * g) * D + t;
-            const float* xb = xa + D;
-            float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    // column of X behind n index `n` of backward N-tile `nt`
+    auto bwd_col = [&](int nt, int n) { return (ODD && nt == KS - 1) ? 16 * NCH + n : 16 * (nt >> 1) + 2 * n + (nt & 1); };
+
+    // NG 16-row tiles at once (NG = 1 or 2; with 2 the two tiles' instruction streams are independent and
+    // interleave).  Products are split-precision: x = xh + xl (xh = the 19 bits a TF32 MMA reads), likewise beta
+    // and r.  hi*hi runs as TF32 MMAs; the three small cross terms run as BF16 MMAs (k = 16), which is exact
+    // enough because each is already ~2^-11 of the main term (total relative error ~1e-6, fp32 accumulate).
+    auto unit = [&](auto ng_tag, const float* xa, const float* xb) {
+        constexpr int NG = decltype(ng_tag)::value;
+        constexpr int NC = (NG == 2) ? 1 : 2;        // accumulator chains per MMA kind and tile
+        const float* xt[2] = {xa, xb};
+        // ---- forward: logits
+        float acc[NG][2 * NC][4];
 #pragma unroll
-            for (int kk = 0; kk < KS; ++kk) {
-                uint32_t a[4], al[4];
-                a[0] = __float_as_uint(xa[8 * kk]); a[1] = __float_as_uint(xb[8 * kk]);
-                a[2] = __float_as_uint(xa[8 * kk + 4]); a[3] = __float_as_uint(xb[8 * kk + 4]);
+        for (int gi = 0; gi < NG; ++gi)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) tf32_split(a[i], al[i]);
-                mma_tf32(c, al, bhi[kk][0], bhi[kk][1]);
-                mma_tf32(c, a, blo[kk][0], blo[kk][1]);
-                mma_tf32(c, a, bhi[kk][0], bhi[kk][1]);
+            for (int k = 0; k < 2 * NC; ++k) { acc[gi][k][0] = 0.0f; acc[gi][k][1] = 0.0f; acc[gi][k][2] = 0.0f; acc[gi][k][3] = 0.0f; }
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk) {
+#pragma unroll
+            for (int gi = 0; gi < NG; ++gi) {
+                // (row g, col c), (row g+8, c), (row g, c+1), (row g+8, c+1) with c = 8kk + 2t
+                const float4 v = *reinterpret_cast<const float4*>(xt[gi] + off_f + 16 * kk);
+                const uint32_t ar[4] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
+                mma_tf32(acc[gi][kk % NC], ar, bhi[kk][0], bhi[kk][1]);                      // xh * bh
+                // k = (2t, 2t+1): xl at columns (c, c+1);  k = (2t+8, 2t+9): x at columns (c, c+1)
+                const uint32_t ab[4] = {pack_bf16(tf32_lo(v.x), tf32_lo(v.z)), pack_bf16(tf32_lo(v.y), tf32_lo(v.w)),
+                                        pack_bf16(v.x, v.z), pack_bf16(v.y, v.w)};
+                mma_bf16(acc[gi][NC + kk % NC], ab, bbf[kk][0], bbf[kk][1]);                // xl * bh + x * bl
             }
-            // ---- link: c0 (row 2g, chain 2t), c1 (2g, 2t+1), c2 (2g+1, 2t), c3 (2g+1, 2t+1)
-            float dl[4];
-            {
-                const float ya = yg[2 * g], yb = yg[2 * g + 1];
-                const bool va = (2 * g) < nv, vb = (2 * g + 1) < nv;
-                float ls[4];
-                glm_loss_fast(p.fam.likelihood, c[0], ya, ls[0], dl[0]);
-                glm_loss_fast(p.fam.likelihood, c[1], ya, ls[1], dl[1]);
-                glm_loss_fast(p.fam.likelihood, c[2], yb, ls[2], dl[2]);
-                glm_loss_fast(p.fam.likelihood, c[3], yb, ls[3], dl[3]);
-                if (!va) { ls[0] = 0.0f; ls[1] = 0.0f; dl[0] = 0.0f; dl[1] = 0.0f; }
-                if (!vb) { ls[2] = 0.0f; ls[3] = 0.0f; dl[2] = 0.0f; dl[3] = 0.0f; }
-                nll[0] += ls[0]; nll[1] += ls[1]; nll[0] += ls[2]; nll[1] += ls[3];
+        }
+        // ---- link: c0 (row g, chain 2t), c1 (g, 2t+1), c2 (g+8, 2t), c3 (g+8, 2t+1)
+        float dl[NG][4];
+#pragma unroll
+        for (int gi = 0; gi < NG; ++gi) {
+            const float2 yy = *reinterpret_cast<const float2*>(xt[gi] + kTileRows * P + 2 * g);    // y[row g], y[row g+8]
+            float ls[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float eta = acc[gi][0][i] + acc[gi][NC][i];
+                if (NC == 2) eta = (acc[gi][1][i] + acc[gi][3][i]) + eta;
+                link_fn<LIK>(eta, (i < 2) ? yy.x : yy.y, ls[i], dl[gi][i]);
             }
-            // ---- residuals -> B fragments of the backward MMA: b0 = r[row 4t+2ks][chain g], b1 = r[row 4t+2ks+1][chain g]
-            uint32_t rh[2][2], rl[2][2];
+            nll[0] += ls[0] + ls[2]; nll[1] += ls[1] + ls[3];
+        }
+        // ---- residuals -> A fragments.  k-step ks covers pair rows 4ks..4ks+3; lane (g, t) needs
+        //      r[row 4ks+t][chain g] and r[row 4ks+t+8][chain g], held by lane (4ks+t, g>>1) of the C layout.
+        //      TF32: stacked A = [r_hi ; r_lo]^T: a0 = r_hi(low row), a1 = r_lo(low), a2 = r_hi(high), a3 = r_lo(high)
+        //      BF16 (k = 16 = both k-steps): a0 = {r(ks0 low), r(ks0 high)}, a2 = {r(ks1 low), r(ks1 high)}, a1 = a3 = 0
+        uint32_t ra[NG][2][4], rb[NG][4];
+#pragma unroll
+        for (int gi = 0; gi < NG; ++gi) {
+            rb[gi][1] = 0u; rb[gi][3] = 0u;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-                const int src = ((2 * t + ks) << 2) | (g >> 1);
-                const float e0 = __shfl_sync(0xFFFFFFFFu, dl[0], src), e1 = __shfl_sync(0xFFFFFFFFu, dl[1], src);
-                const float o0 = __shfl_sync(0xFFFFFFFFu, dl[2], src), o1 = __shfl_sync(0xFFFFFFFFu, dl[3], src);
-                rh[ks][0] = __float_as_uint((g & 1) ? e1 : e0);
-                rh[ks][1] = __float_as_uint((g & 1) ? o1 : o0);
-                tf32_split(rh[ks][0], rl[ks][0]);
-                tf32_split(rh[ks][1], rl[ks][1]);
+                const int src = ks ? src_ks1 : src_ks0;
+                const float e0 = __shfl_sync(0xFFFFFFFFu, dl[gi][0], src), e1 = __shfl_sync(0xFFFFFFFFu, dl[gi][1], src);
+                const float o0 = __shfl_sync(0xFFFFFFFFu, dl[gi][2], src), o1 = __shfl_sync(0xFFFFFFFFu, dl[gi][3], src);
+                const float lo_row = (g & 1) ? e1 : e0, hi_row = (g & 1) ? o1 : o0;
+                ra[gi][ks][0] = __float_as_uint(lo_row); ra[gi][ks][1] = __float_as_uint(tf32_lo(lo_row));
+                ra[gi][ks][2] = __float_as_uint(hi_row); ra[gi][ks][3] = __float_as_uint(tf32_lo(hi_row));
+                rb[gi][2 * ks] = pack_bf16(lo_row, hi_row);
             }
-            // ---- backward: gbeta[16mt + m][chain] += sum_rows x[row][16mt + m] * r[row][chain]
+        }
+        // ---- backward: gbeta^T[chain][col] += sum_rows r[row][chain] * x[row][col], 16 columns (2 MMAs wide) at a time
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                float gt[4] = {0.0f, 0.0f, 0.0f, 0.0f};       // fresh accumulator per group: few tensor-core adds, then fp32 FADD
+        for (int j = 0; j < NCH; ++j) {
+            float ga[NG][2][4];
+#pragma unroll
+            for (int gi = 0; gi < NG; ++gi) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) { ga[gi][k][0] = 0.0f; ga[gi][k][1] = 0.0f; ga[gi][k][2] = 0.0f; ga[gi][k][3] = 0.0f; }
+                float xl[2][4];
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) {
-                    const float* x0 = xg + (4 * t + 2 * ks) * D + 16 * mt + g;
-                    const float* x1 = x0 + D;
-                    uint32_t a[4], al[4];
-                    a[0] = __float_as_uint(x0[0]); a[1] = __float_as_uint(x0[8]);
-                    a[2] = __float_as_uint(x1[0]); a[3] = __float_as_uint(x1[8]);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) tf32_split(a[i], al[i]);
-                    mma_tf32(gt, al, rh[ks][0], rh[ks][1]);
-                    mma_tf32(gt, a, rl[ks][0], rl[ks][1]);
-                    mma_tf32(gt, a, rh[ks][0], rh[ks][1]);
+                    // col c = 16j+2g: rows (4ks+t, +8); col c+1: rows (4ks+t, +8)
+                    const float4 v = *reinterpret_cast<const float4*>(xt[gi] + off_b + ks * 8 * P + 32 * j);
+                    mma_tf32(ga[gi][0], ra[gi][ks], __float_as_uint(v.x), __float_as_uint(v.y));   // [r_hi ; r_lo] * xh
+                    mma_tf32(ga[gi][1], ra[gi][ks], __float_as_uint(v.z), __float_as_uint(v.w));
+                    xl[ks][0] = tf32_lo(v.x); xl[ks][1] = tf32_lo(v.y); xl[ks][2] = tf32_lo(v.z); xl[ks][3] = tf32_lo(v.w);
                 }
+                mma_bf16(ga[gi][0], rb[gi], pack_bf16(xl[0][0], xl[0][1]), pack_bf16(xl[1][0], xl[1][1]));   // r * xl, 16 rows
+                mma_bf16(ga[gi][1], rb[gi], pack_bf16(xl[0][2], xl[0][3]), pack_bf16(xl[1][2], xl[1][3]));
+            }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) gacc[mt][i] += gt[i];
+            for (int i = 0; i < 4; ++i) {
+                if (NG == 2) { gacc[2 * j][i] += ga[0][0][i] + ga[NG - 1][0][i]; gacc[2 * j + 1][i] += ga[0][1][i] + ga[NG - 1][1][i]; }
+                else { gacc[2 * j][i] += ga[0][0][i]; gacc[2 * j + 1][i] += ga[0][1][i]; }
+            }
+        }
+        if (ODD) {
+            float ga[NG][4];
+#pragma unroll
+            for (int gi = 0; gi < NG; ++gi) {
+                ga[gi][0] = 0.0f; ga[gi][1] = 0.0f; ga[gi][2] = 0.0f; ga[gi][3] = 0.0f;
+                float xl[2][2];
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const float2 v = *reinterpret_cast<const float2*>(xt[gi] + off_b1 + ks * 8 * P);
+                    mma_tf32(ga[gi], ra[gi][ks], __float_as_uint(v.x), __float_as_uint(v.y));
+                    xl[ks][0] = tf32_lo(v.x); xl[ks][1] = tf32_lo(v.y);
+                }
+                mma_bf16(ga[gi], rb[gi], pack_bf16(xl[0][0], xl[0][1]), pack_bf16(xl[1][0], xl[1][1]));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (NG == 2) gacc[KS - 1][i] += ga[0][i] + ga[NG - 1][i];
+                else gacc[KS - 1][i] += ga[0][i];
             }
         }
     };
@@ -419,39 +534,53 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         }
         bar_sync<kBarCons, kConsThreads>();
 #pragma unroll
-        for (int kk = 0; kk < KS; ++kk) {                                   // beta -> B fragments (k = d, n = chain)
-            bhi[kk][0] = __float_as_uint(bs[(8 * kk + t) * kStreamCT + g]);
-            bhi[kk][1] = __float_as_uint(bs[(8 * kk + t + 4) * kStreamCT + g]);
-            tf32_split(bhi[kk][0], blo[kk][0]);
-            tf32_split(bhi[kk][1], blo[kk][1]);
+        for (int kk = 0; kk < KS; ++kk) {                                   // beta -> B fragments (k = column, n = chain)
+            const float b0 = bs[(8 * kk + 2 * t) * kStreamCT + g], b1 = bs[(8 * kk + 2 * t + 1) * kStreamCT + g];
+            bhi[kk][0] = __float_as_uint(b0); bhi[kk][1] = __float_as_uint(b1);
+            bbf[kk][0] = pack_bf16(b0 - tf32_lo(b0), b1 - tf32_lo(b1));     // pairs with xl (k = 2t, 2t+1)
+            bbf[kk][1] = pack_bf16(tf32_lo(b0), tf32_lo(b1));               // pairs with x  (k = 2t+8, 2t+9)
         }
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) { gacc[mt][0] = 0.0f; gacc[mt][1] = 0.0f; gacc[mt][2] = 0.0f; gacc[mt][3] = 0.0f; }
+        for (int nt = 0; nt < KS; ++nt) { gacc[nt][0] = 0.0f; gacc[nt][1] = 0.0f; gacc[nt][2] = 0.0f; gacc[nt][3] = 0.0f; }
         nll[0] = 0.0f; nll[1] = 0.0f;
+        if (ctid == 0) B2_DBG_LAP(7);
 
-        // ---- sweep: tile t of this pass belongs to pair t mod 7; this warp takes rows [32*half, 32*half+32)
-        for (int t = pair; t < n_tiles; t += kPairs) {
-            const uint32_t gi = tiles_done + (uint32_t)t;
-            const int st = gi % nst; const uint32_t ph = (gi / nst) & 1u;
-            mbar_wait(&full[st], ph);
-            const long long r0 = row0 + (long long)t * kTileRows;
-            const int rows = (int)((row1 - r0 < kTileRows) ? (row1 - r0) : kTileRows);
-            const int nvalid = rows - 32 * half;
-            if (nvalid > 0) unit(tiles + (size_t)st * tile_floats + 32 * half * D, ytiles + (size_t)st * kTileRows + 32 * half, nvalid);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[st]);
-        }
-        tiles_done += (uint32_t)n_tiles;
-        if (n_tail > 0 && cw == 0) unit(tail, tail + 16 * 64, n_tail);      // last N % 4 rows (staged at start)
-
-        // ---- reduce: lanes -> warp -> CTA, then publish the partial
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int d = 16 * mt + g + ((i & 2) ? 8 : 0), chain = 2 * t + (i & 1);
-                if (d < D) red[((size_t)cw * kStreamCT + chain) * kGStride + d] = gacc[mt][i];
+        // ---- sweep: consume this warp's tiles in order (two at a time when the ring has 4 slots); a finished
+        //      slot is refilled at once with the tile `nst` positions further down the (cyclic) sequence
+        {
+            int j = 0, jn = nst % (n_mine > 0 ? n_mine : 1);                // jn = (j + nst) mod n_mine
+            while (j < n_mine) {
+                const int s0 = slot; const uint32_t p0 = parity;
+                if (++slot == nst) { slot = 0; parity ^= 1u; }
+                if (pairs && j + 1 < n_mine) {
+                    const int s1 = slot; const uint32_t p1 = parity;
+                    if (++slot == nst) { slot = 0; parity ^= 1u; }
+                    if (p.dbg_sweep != 2) { mbar_wait(&my_full[s0], p0); mbar_wait(&my_full[s1], p1); }
+                    if (p.dbg_sweep != 1) unit(StreamTwo{}, my_tiles + (size_t)s0 * TILE_FLOATS, my_tiles + (size_t)s1 * TILE_FLOATS);
+                    __syncwarp();
+                    if (lane == 0 && p.dbg_sweep != 2) {
+                        issue(s0, jn); if (++jn == n_mine) jn = 0;
+                        issue(s1, jn); if (++jn == n_mine) jn = 0;
+                    }
+                    j += 2;
+                } else {
+                    if (p.dbg_sweep != 2) mbar_wait(&my_full[s0], p0);
+                    if (p.dbg_sweep != 1) unit(StreamOne{}, my_tiles + (size_t)s0 * TILE_FLOATS, nullptr);
+                    __syncwarp();
+                    if (lane == 0 && p.dbg_sweep != 2) { issue(s0, jn); if (++jn == n_mine) jn = 0; }
+                    j += 1;
+                }
             }
+        }
+        if (ctid == 0) B2_DBG_LAP(1);
+
+        // ---- reduce warps -> CTA in two stages through a [7][16][32] scratch (value-major, lane-minor: no bank
+        //      conflicts), then publish the partial.  Fixed order => bit-reproducible.
+        float val[16];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            val[2 * nt] = (nt < KS) ? gacc[nt < KS ? nt : 0][0] + gacc[nt < KS ? nt : 0][2] : 0.0f;
+            val[2 * nt + 1] = (nt < KS) ? gacc[nt < KS ? nt : 0][1] + gacc[nt < KS ? nt : 0][3] : 0.0f;
         }
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -459,28 +588,58 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
             nll[k] += __shfl_xor_sync(0xFFFFFFFFu, nll[k], 8);
             nll[k] += __shfl_xor_sync(0xFFFFFFFFu, nll[k], 16);
         }
-        if (g == 0) {
-            red[((size_t)cw * kStreamCT + 2 * t) * kGStride + 64] = nll[0];
-            red[((size_t)cw * kStreamCT + 2 * t + 1) * kGStride + 64] = nll[1];
+        constexpr int NV = (KS < 8) ? 2 * KS + 2 : 16;   // values per lane; KS == 8 has no spare slot: nll rides separately
+        if (KS < 8) { val[2 * KS] = nll[0]; val[2 * KS + 1] = nll[1]; }
+        if (cw >= kRedWarps) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) red[((cw - kRedWarps) * 16 + k) * 32 + lane] = val[k];
+            if (KS == 8 && g == 0) { gred[128 + (cw - kRedWarps) * 8 + 2 * t] = nll[0]; gred[128 + (cw - kRedWarps) * 8 + 2 * t + 1] = nll[1]; }
+        }
+        bar_sync<kBarCons, kConsThreads>();
+        if (cw + kRedWarps < kConsWarps) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) val[k] += red[(cw * 16 + k) * 32 + lane];
+            if (KS == 8) { nll[0] += gred[128 + cw * 8 + 2 * t]; nll[1] += gred[128 + cw * 8 + 2 * t + 1]; }
+        }
+        bar_sync<kBarCons, kConsThreads>();
+        if (cw < kRedWarps) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) red[(cw * 16 + k) * 32 + lane] = val[k];
+            if (KS == 8 && g == 0) { gred[128 + cw * 8 + 2 * t] = nll[0]; gred[128 + cw * 8 + 2 * t + 1] = nll[1]; }
         }
         bar_sync<kBarCons, kConsThreads>();
         for (int o = ctid; o < kStreamCT * 65; o += kConsThreads) {
             const int c = o / 65, d = o - c * 65;
             float a = 0.0f;
+            if (d < 8 * KS) {                    // (chain c, column d) lives in lane (g = c, t = n >> 1), value 2 nt + (n & 1)
+                int nt, n;
+                if (ODD && d >= 16 * NCH) { nt = KS - 1; n = d - 16 * NCH; }
+                else { nt = 2 * (d >> 4) + (d & 1); n = (d & 15) >> 1; }
+                const int src = (2 * nt + (n & 1)) * 32 + (c << 2) + (n >> 1);
 #pragma unroll
-            for (int w = 0; w < kConsWarps; ++w) a += red[((size_t)w * kStreamCT + c) * kGStride + d];
+                for (int w = 0; w < kRedWarps; ++w) a += red[w * 16 * 32 + src];
+            } else if (d == 64) {                // nll of chain c = 2t + e: lane t, value 2 KS + e
+                if (KS < 8) {
+                    const int src = (2 * KS + (c & 1)) * 32 + (c >> 1);
+#pragma unroll
+                    for (int w = 0; w < kRedWarps; ++w) a += red[w * 16 * 32 + src];
+                } else {
+#pragma unroll
+                    for (int w = 0; w < kRedWarps; ++w) a += gred[128 + w * 8 + c];
+                }
+            }
             __stcg(p.partial + ((size_t)cta * kStreamCT + c) * kGStride + d, a);
         }
         __threadfence();
         bar_sync<kBarCons, kConsThreads>();
-        if (ctid == 0) { red_release_add(&sy->arrive, 1u); B2_DBG_LAP(1); }
+        if (ctid == 0) { red_release_add(&sy->arrive, 1u); B2_DBG_LAP(2); }
 
         // ---- chain owner: sum the partials of all CTAs in fixed order, hand over to the tick warp
         if (is_tick) {
             if (ctid == 0) {
                 const bool ok = spin_ge(&sy->arrive, (unsigned)G * (pass + 1u), sy, p.spin_limit);
                 flags[3] = ok ? 1 : 0;
-                B2_DBG_LAP(2);
+                B2_DBG_LAP(3);
             }
             bar_sync<kBarCons, kConsThreads>();
             if (flags[3]) {
@@ -491,26 +650,30 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                     float a = 0.0f;
                     const int g0 = G * seg / 5, g1 = G * (seg + 1) / 5;
                     const float* src = p.partial + (size_t)cta * kGStride + o;
-                    for (int g = g0; g < g1; g += 16) {
+                    for (int gg = g0; gg < g1; gg += 16) {
                         float v[16];
 #pragma unroll
                         for (int k = 0; k < 16; ++k)
-                            v[k] = (g + k < g1) ? __ldcg(src + (size_t)(g + k) * (kStreamCT * kGStride)) : 0.0f;
+                            v[k] = (gg + k < g1) ? __ldcg(src + (size_t)(gg + k) * (kStreamCT * kGStride)) : 0.0f;
 #pragma unroll
                         for (int k = 0; k < 16; ++k) a += v[k];
                     }
-                    red[seg * kGStride + o] = a;
+                    xred[seg * kGStride + o] = a;
                 }
             }
             __threadfence_block();
             bar_arrive<kBarTick, kTopThreads>();     // tick warp takes over; consumers go wait for the next beta
-            if (ctid == 0) B2_DBG_LAP(3);
+            if (ctid == 0) B2_DBG_LAP(4);
         }
         ++pass;
     }
 
-    // ---- shutdown: stop the producer, write the chain state back
-    if (ctid == 0) { *(volatile int*)&flags[0] = 1; }
+    // ---- shutdown: drain this warp's outstanding copies, write the chain state back
+    if (n_mine > 0 && p.dbg_sweep != 2)
+        for (int s = 0; s < nst; ++s) {
+            mbar_wait(&my_full[slot], parity);
+            if (++slot == nst) { slot = 0; parity ^= 1u; }
+        }
     bar_sync<kBarCons, kConsThreads>();
     if (is_tick && p.vecs_in_smem && p.mode == 0) {
         // the tick warp left the loop through the same top barrier, so the vectors are final
@@ -522,7 +685,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
     if (cta == 0 && ctid == 0) {
         sy->passes = pass;
         tdbg[5] = (unsigned long long)(clock64() - t_begin);
-        for (int i = 0; i < 8; ++i) sy->dbg[i] = tdbg[i];
+        for (int i = 0; i < 16; ++i) sy->dbg[i] = tdbg[i];
     }
 #undef B2_DBG_LAP
 }

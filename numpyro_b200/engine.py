@@ -161,7 +161,7 @@ class Engine:
         return int(self.lib.b200nuts_pass_count(self.h))
 
     def debug_clocks(self) -> np.ndarray:
-        out = np.zeros(8, np.uint64)
+        out = np.zeros(16, np.uint64)
         self._check(self.lib.b200nuts_debug_clocks(self.h, out.ctypes.data_as(C.c_void_p)), "b200nuts_debug_clocks")
         return out
 

@@ -41,5 +41,5 @@ print("sample 40 iters: %.1f ms, leapfrogs %d (per chain %s) -> %.0f grad-evals/
     ms, ns.sum(), ns.sum(1), ns.sum() / ms * 1e3, ms * 1e3 / ns.sum(1).max(), (ns.sum(1).max() * 127822640 / (ms * 1e-3)) / 6545.6e9))
 print("divergences", int(out["diverging"].sum()))
 dbg = e.debug_clocks().astype(np.float64)
-names = ["wait_beta", "sweep+publish", "wait_partials", "reduce", "finish+tick+publish", "total"]
+names = ["wait_beta", "sweep", "cta_reduce+publish", "wait_partials", "xcta_reduce", "total", "tick_busy", "beta_frags", "tick_finish", "tick_advance", "tick_publish"]
 print("CTA0 clock breakdown per pass:", {n: round(dbg[i] / max(e.pass_count and ns.sum(1).max(), 1), 0) for i, n in enumerate(names)})

@@ -1,0 +1,28 @@
+"""Timing experiment: per-pass time of the streaming engine with B200NUTS_DEBUG_SWEEP = 0 / 1 (copies only) / 2 (compute only)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from numpyro_b200 import _capi, engine as eng
+from oracle import prng
+F = np.float32
+N, D, C = 581012, 54, 8
+rng = np.random.default_rng(1)
+X = rng.standard_normal(size=(N, D), dtype=F)
+beta = (rng.normal(size=D) * 0.3).astype(F)
+y = (rng.uniform(size=N) < 1 / (1 + np.exp(-(X @ beta)))).astype(F)
+names = ["wait_beta", "sweep", "cta_reduce+publish", "wait_partials", "xcta_reduce", "total", "tick_busy", "beta_frags",
+         "tick_finish", "tick_advance", "tick_publish"]
+for mode in (0, 1, 2):
+    os.environ["B200NUTS_DEBUG_SWEEP"] = str(mode)
+    e = eng.Engine(family=_capi.FAMILY_GLM, num_chains=C, X=X, y=y, max_tree_depth=6, max_tree_depth_warmup=6)
+    e.init(prng.split(prng.key(1), C), 20)
+    e.run(20, 20, fields=())
+    torch.cuda.synchronize()
+    p0 = e.pass_count
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(); e.run(60, 20, fields=("num_steps",)); t1.record(); torch.cuda.synchronize()
+    passes = e.pass_count - p0
+    dbg = e.debug_clocks().astype(np.float64)
+    print("mode", mode, "passes", passes, "us/pass %.2f" % (t0.elapsed_time(t1) * 1e3 / passes),
+          {n: round(dbg[i] / passes) for i, n in enumerate(names)})
+    e.close()
