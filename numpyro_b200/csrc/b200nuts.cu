@@ -203,6 +203,7 @@ static int stream_launch(B200Nuts* h, int mode, const OutBufs& out, const float*
     p.vecs_in_smem = h->vecs_in_smem; p.spin_limit = 6000000000LL;
     p.img = h->img; p.n_tiles = h->n_tiles; p.pad_rows = h->pad_rows;
     { const char* e = getenv("B200NUTS_DEBUG_SWEEP"); p.dbg_sweep = e ? atoi(e) : 0; }
+    { const char* e = getenv("B200NUTS_DEBUG_WARPS"); p.dbg_warps = e ? atoi(e) : 1000; }
     CK(cudaMemsetAsync(h->sync, 0, sizeof(StreamSync), st));
     void* args[] = {&p};
     const void* fn = stream_kernel_for(h->ks, h->fam.likelihood);
@@ -230,6 +231,13 @@ static int check_stream_abort(B200Nuts* h, cudaStream_t st) {
     CK(cudaStreamSynchronize(st));
     h->passes += (long long)s.passes;
     for (int i = 0; i < 16; ++i) h->dbg[i] = s.dbg[i];
+    if (getenv("B200NUTS_DEBUG_TICK")) {
+        for (int c = 0; c < h->C; ++c)
+            fprintf(stderr, "[b200nuts] owner %d: passes %llu tick avg %.0f max %llu | per pass: finish %.0f advance %.0f publish %.0f gredsum %.0f release %.0f\n", c, s.passes,
+                    s.passes ? (double)s.tick_sum[c] / (double)s.passes : 0.0, s.tick_max[c],
+                    (double)s.tick_lap[c][0] / s.passes, (double)s.tick_lap[c][1] / s.passes, (double)s.tick_lap[c][2] / s.passes,
+                    (double)s.tick_lap[c][3] / s.passes, (double)s.tick_slow[c] / s.passes);
+    }
     if (s.abort_flag) { h->err = "stream engine aborted: inter-pass exchange timed out"; return B200NUTS_ECUDA; }
     return 0;
 }
@@ -336,9 +344,9 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
         if ((ce = cudaGetLastError()) != cudaSuccess) return fail("repack", ce);
         h->launches += 1;
         if ((ce = cudaMalloc(&h->partial, sizeof(float) * (size_t)h->grid * kStreamCT * kGStride)) != cudaSuccess) return fail("cudaMalloc partial", ce);
-        if ((ce = cudaMalloc(&h->beta, sizeof(float) * kStreamCT * 64)) != cudaSuccess) return fail("cudaMalloc beta", ce);
+        if ((ce = cudaMalloc(&h->beta, sizeof(float) * 8 * kStreamCT * 16)) != cudaSuccess) return fail("cudaMalloc beta", ce);
         if ((ce = cudaMalloc(&h->sync, sizeof(StreamSync))) != cudaSuccess) return fail("cudaMalloc sync", ce);
-        cudaMemset(h->beta, 0, sizeof(float) * kStreamCT * 64);
+        cudaMemset(h->beta, 0, sizeof(float) * 8 * kStreamCT * 16);
         cudaMemset(h->partial, 0, sizeof(float) * (size_t)h->grid * kStreamCT * kGStride);
     }
     if ((ce = cudaDeviceSynchronize()) != cudaSuccess) return fail("create", ce);

@@ -20,8 +20,8 @@
 // padded to P = 8*odd floats and 16-byte chunks are XOR-swizzled by bit 1 of the pair row, which
 // makes both access patterns bank-conflict free.
 //
-// CTA = 14 warps: warps 0..12 consumers, warp 13 tick.  Tile t of a CTA's slice belongs to consumer
-// warp t mod 13 (static assignment: the summation order is fixed, results are bit-reproducible).
+// CTA = 16 warps: warps 0..14 consumers, warp 15 tick.  Tile t of a CTA's slice belongs to consumer
+// warp t mod 15 (static assignment: the summation order is fixed, results are bit-reproducible).
 // Every consumer warp runs its own private ring of `stages` slots and refills a slot itself the
 // moment it has finished reading it (one elected lane: expect_tx + bulk copy) -- measured on B200, a
 // single issuing thread needs ~680 cycles per copy round trip and caps a CTA at ~3 TB/s chip-wide, 15
@@ -49,13 +49,14 @@
 namespace b2 {
 
 constexpr int kStreamCT = 8;             // chains per pass
-constexpr int kConsWarps = 13;           // consumer warps
+constexpr int kConsWarps = 15;           // consumer warps
 constexpr int kStreamThreads = 32 * (kConsWarps + 1);
 constexpr int kTileRows = 16;            // rows per ring slot = one consumer warp's unit of work
 constexpr int kMaxStages = 4;            // tile slots per consumer warp (4: tiles are consumed in pairs)
 constexpr int kGStride = 72;             // floats per (cta, chain) partial: gbeta[<=64], nll, pad
 constexpr int kRedWarps = (kConsWarps + 1) / 2;   // rows of the two-stage CTA reduction scratch
-constexpr int kXRedFloats = 5 * kGStride + 192;   // owner CTA: 5 segment sums + gradient scratch for the tick
+constexpr int kXSeg = 7;                 // segments of the cross-CTA reduction (7 x 65 threads)
+constexpr int kXRedFloats = kXSeg * kGStride + 192;   // owner CTA: segment sums + gradient scratch for the tick
 constexpr int kBarTop = 1, kBarCons = 2, kBarTick = 3;
 constexpr int kConsThreads = kConsWarps * 32, kTopThreads = kStreamThreads;
 
@@ -73,14 +74,15 @@ B2_HD constexpr int stream_ks_for(int D) { return D <= 8 ? 1 : D <= 16 ? 2 : D <
 // dbg: clock64 totals on CTA 0 -- [0] wait for betas (incl. the owners' ticks), [1] sweep, [2] CTA reduction +
 // publish partial, [3] wait for all partials, [4] cross-CTA reduction, [5] total loop, [6] tick warp busy,
 // [7] beta -> fragments, [8] tick: finish potential, [9] tick: state machine, [10] tick: publish beta
-struct StreamSync { unsigned int arrive, ready, done, abort_flag; unsigned long long passes; unsigned long long dbg[16]; };
+struct StreamSync { unsigned int arrive, ready, done, abort_flag; unsigned long long passes; unsigned long long dbg[16];
+                    unsigned long long tick_sum[kStreamCT], tick_max[kStreamCT], tick_slow[kStreamCT], tick_lap[kStreamCT][4]; };   // per owner CTA: tick cycles
 
 struct StreamParams {
     TickCfg cfg; FamilySpec fam; OutBufs out;
     int C, Dp, mode;                     // mode 0: run chains, 1: evaluate potential at z_in
     ChainCtl* ctl; float* vecs;          // [C], [V_COUNT][C][Dp]
     float* partial;                      // [grid][kStreamCT][kGStride]
-    float* beta;                         // [kStreamCT][64]
+    float* beta;                         // [8 k-steps][kStreamCT][4][4]: every chain's beta as ready-made MMA fragments
     StreamSync* sync;
     const float* z_in; float* u_out; float* g_out;    // mode 1
     const float* img;                    // tile image of (X, y), see above
@@ -89,6 +91,7 @@ struct StreamParams {
     int stages;                          // slots in every consumer warp's private ring
     int vecs_in_smem;
     int dbg_sweep;                       // timing experiments only: 1 = copies without compute, 2 = compute without copies
+    int dbg_warps;                       // ... only the first dbg_warps consumer warps compute
     long long spin_limit;
 };
 
@@ -148,6 +151,20 @@ B2_D uint32_t pack_bf16(float first, float second) {
 }
 // lo part of the tf32 split: x - trunc_tf32(x), exact in fp32
 B2_D float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// packed fp32 pairs (Blackwell add/sub.f32x2 = one issue slot for two lanes of work)
+B2_D unsigned long long pack2f(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+B2_D void unpack2f(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+B2_D void tf32_lo2(float x0, float x1, float& l0, float& l1) {
+    const float h0 = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pack2f(x0, x1)), "l"(pack2f(h0, h1)));
+    unpack2f(d, l0, l1);
+}
+B2_D void add2f(float& a0, float& a1, float b0, float b1) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pack2f(a0, a1)), "l"(pack2f(b0, b1)));
+    unpack2f(d, a0, a1);
+}
 template <int ID, int N> B2_D void bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
 template <int ID, int N> B2_D void bar_arrive() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
 B2_D float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -190,7 +207,6 @@ B2_D bool spin_ge(const unsigned int* ctr, unsigned int target, StreamSync* sy, 
 B2_HD size_t stream_fixed_smem(int Dp, bool vecs_in_smem) {
     size_t b = 0;
     b += (size_t)kConsWarps * kMaxStages * 8;                      // mbarriers
-    b += 64 * kStreamCT * 4;                                       // beta, [d][chain]
     b += (size_t)kRedWarps * 16 * 32 * 4;                          // CTA reduction scratch, [warp][value][lane]
     b += (size_t)kXRedFloats * 4;                                  // cross-CTA reduction + tick scratch
     b += 64 * 4 + 64 * 4 + 64 + 128;                               // gred(+nll), flags, timers
@@ -223,14 +239,24 @@ __global__ void k_stream_repack(const float* __restrict__ X, const float* __rest
     }
 }
 
-// beta_c = s(z) * u for the next sweep (zero when the chain is done), published to global memory
+// beta_c = s(z) * u for the next sweep (zero when the chain is done), published to global memory as the B
+// fragments the consumers need: for k-step kk and lane (g = chain, t) the four words
+//   { beta[8kk+2t], beta[8kk+2t+1] (raw fp32: the TF32 MMA reads the top 19 bits),
+//     bf16x2(beta_hi[8kk+2t], beta_hi[8kk+2t+1]), bf16x2(beta_lo[..], beta_lo[..]) }      (see unit() below)
 B2_D void stream_publish_beta(const StreamParams& p, int cta, const float* zsrc, bool active) {
     const int lane = threadIdx.x & 31;
-    float* bout = p.beta + (size_t)cta * 64;
-    for (int d = lane; d < 64; d += 32) {
-        float b = 0.0f;
-        if (active && d < p.fam.Dx) b = glm_scale_at(p.fam, zsrc, d) * zsrc[p.fam.off_u + d];
-        __stcg(bout + d, b);
+    {
+        const int kk = lane >> 2, t = lane & 3;          // 8 k-steps x 4 = 32 lanes
+        const int d0 = 8 * kk + 2 * t;
+        float b0 = 0.0f, b1 = 0.0f;
+        if (active && d0 < p.fam.Dx) b0 = glm_scale_at(p.fam, zsrc, d0) * zsrc[p.fam.off_u + d0];
+        if (active && d0 + 1 < p.fam.Dx) b1 = glm_scale_at(p.fam, zsrc, d0 + 1) * zsrc[p.fam.off_u + d0 + 1];
+        const float l0 = tf32_lo(b0), l1 = tf32_lo(b1);
+        float4 w;
+        w.x = b0; w.y = b1;
+        w.z = __uint_as_float(pack_bf16(b0 - l0, b1 - l1));
+        w.w = __uint_as_float(pack_bf16(l0, l1));
+        __stcg(reinterpret_cast<float4*>(p.beta) + (kk * kStreamCT + cta) * 4 + t, w);
     }
     __syncwarp();
 }
@@ -238,10 +264,10 @@ B2_D void stream_publish_beta(const StreamParams& p, int cta, const float* zsrc,
 // The tick warp's work between two sweeps, for the chain owned by this CTA: finish the potential from the
 // reduced likelihood sums, advance the NUTS state machine, publish the next beta.  Deliberately not inlined:
 // it is the same code for every kernel instance.  Returns true when the chain needs no further gradient.
-__device__ __noinline__ bool stream_tick_step(const StreamParams& p, ChainCtl* sctl, ChainVecs cv, const float* gred,
+__device__ __forceinline__ bool stream_tick_step(const StreamParams& p, ChainCtl* sctl, ChainVecs cv, const float* gred,
                                               float* gz, float nll, int cta, unsigned long long* tdbg) {
     const int lane = threadIdx.x & 31;
-    const bool dbg = (cta == 0 && lane == 0);
+    const bool dbg = (lane == 0);
     long long t0 = dbg ? clock64() : 0ll;
 #define B2_TICK_LAP(k) do { __syncwarp(); if (dbg) { const long long t1 = clock64(); tdbg[k] += (unsigned long long)(t1 - t0); t0 = t1; } } while (0)
     float u;
@@ -289,7 +315,6 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
     unsigned char* q = smem_raw;
     float* tiles = (float*)q; q += (size_t)kConsWarps * nst * TILE_FLOATS * 4;
     uint64_t* full = (uint64_t*)q; q += (size_t)kConsWarps * kMaxStages * 8;
-    float* bs = (float*)q; q += 64 * kStreamCT * 4;
     float* red = (float*)q; q += (size_t)kRedWarps * 16 * 32 * 4;
     float* xred = (float*)q; q += (size_t)kXRedFloats * 4;
     float* gred = (float*)q; q += 64 * 4 + 64 * 4;
@@ -329,6 +354,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
     // =============================================================== tick warp
     if (warp == kConsWarps) {
         const bool dbg = (cta == 0 && lane == 0);
+        unsigned long long tk_sum = 0ull, tk_max = 0ull, tk_slow = 0ull;
+        unsigned long long* tlap = tdbg + 8;          // [0..2] finish / advance / publish, [3] gred sum, [4] release
         float loss0, dl0;
         link_fn<LIK>(0.0f, 0.0f, loss0, dl0);        // what every zero pad row adds to a chain's nll
         const float pad_nll = (float)p.pad_rows * loss0;
@@ -338,8 +365,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
             stream_publish_beta(p, cta, zsrc, active);
             if (lane == 0) {
                 if (p.mode == 0 && sctl->phase == PH_DONE) atomicAdd(&sy->done, 1u);
-                __threadfence();
-                red_release_add(&sy->ready, 1u);
+                red_release_add(&sy->ready, 1u);     // release: cumulative over the warp's stores ordered by __syncwarp
             }
         }
         while (true) {
@@ -348,26 +374,38 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
             if (is_tick) {
                 bar_sync<kBarTick, kTopThreads>();   // segment sums are in `xred`
                 if (flags[3]) {
-                    const long long t_a = dbg ? clock64() : 0ll;
-                    for (int d = lane; d < 65; d += 32)
-                        gred[d] = (((xred[d] + xred[kGStride + d]) + xred[2 * kGStride + d]) + xred[3 * kGStride + d]) +
-                                  xred[4 * kGStride + d];
+                    const long long t_a = clock64();
+                    for (int d = lane; d < 65; d += 32) {
+                        float a = xred[d];
+#pragma unroll
+                        for (int sgm = 1; sgm < kXSeg; ++sgm) a += xred[sgm * kGStride + d];
+                        gred[d] = a;
+                    }
                     __syncwarp();
                     const float nll = gred[64] - pad_nll;
-                    float* gz = xred + 5 * kGStride; // scratch for the gradient wrt z (<= Dp floats)
+                    if (lane == 0) tlap[3] += (unsigned long long)(clock64() - t_a);
+                    float* gz = xred + kXSeg * kGStride; // scratch for the gradient wrt z (<= Dp floats)
                     const bool finished = stream_tick_step(p, sctl, cv, gred, gz, nll, cta, tdbg);
                     __syncwarp();
                     if (lane == 0) {
+                        const long long t_r = clock64();
                         if (finished) atomicAdd(&sy->done, 1u);
-                        __threadfence();
                         red_release_add(&sy->ready, 1u);
-                        if (dbg) tdbg[6] += (unsigned long long)(clock64() - t_a);
+                        tlap[4] += (unsigned long long)(clock64() - t_r);
+                        const unsigned long long dt = (unsigned long long)(clock64() - t_a);
+                        tk_sum += dt; if (dt > tk_max) tk_max = dt; if (dt > 12000ull) tk_slow += 1ull;
+                        if (dbg) tdbg[6] += dt;
                     }
                 }
             }
             ++pass;
         }
         if (is_tick && lane == 0 && p.mode == 0) p.ctl[cta] = *sctl;
+        if (is_tick && lane == 0) {
+            sy->tick_sum[cta] = tk_sum; sy->tick_max[cta] = tk_max; sy->tick_slow[cta] = tk_slow;
+            for (int k = 0; k < 4; ++k) sy->tick_lap[cta][k] = tlap[k < 3 ? k : 3];
+            sy->tick_slow[cta] = tlap[4];
+        }
         return;
     }
 
@@ -432,8 +470,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                 const uint32_t ar[4] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
                 mma_tf32(acc[gi][kk % NC], ar, bhi[kk][0], bhi[kk][1]);                      // xh * bh
                 // k = (2t, 2t+1): xl at columns (c, c+1);  k = (2t+8, 2t+9): x at columns (c, c+1)
-                const uint32_t ab[4] = {pack_bf16(tf32_lo(v.x), tf32_lo(v.z)), pack_bf16(tf32_lo(v.y), tf32_lo(v.w)),
-                                        pack_bf16(v.x, v.z), pack_bf16(v.y, v.w)};
+                float lx, ly, lz, lw;
+                tf32_lo2(v.x, v.y, lx, ly); tf32_lo2(v.z, v.w, lz, lw);
+                const uint32_t ab[4] = {pack_bf16(lx, lz), pack_bf16(ly, lw), pack_bf16(v.x, v.z), pack_bf16(v.y, v.w)};
                 mma_bf16(acc[gi][NC + kk % NC], ab, bbf[kk][0], bbf[kk][1]);                // xl * bh + x * bl
             }
         }
@@ -485,16 +524,18 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                     const float4 v = *reinterpret_cast<const float4*>(xt[gi] + off_b + ks * 8 * P + 32 * j);
                     mma_tf32(ga[gi][0], ra[gi][ks], __float_as_uint(v.x), __float_as_uint(v.y));   // [r_hi ; r_lo] * xh
                     mma_tf32(ga[gi][1], ra[gi][ks], __float_as_uint(v.z), __float_as_uint(v.w));
-                    xl[ks][0] = tf32_lo(v.x); xl[ks][1] = tf32_lo(v.y); xl[ks][2] = tf32_lo(v.z); xl[ks][3] = tf32_lo(v.w);
+                    tf32_lo2(v.x, v.y, xl[ks][0], xl[ks][1]); tf32_lo2(v.z, v.w, xl[ks][2], xl[ks][3]);
                 }
                 mma_bf16(ga[gi][0], rb[gi], pack_bf16(xl[0][0], xl[0][1]), pack_bf16(xl[1][0], xl[1][1]));   // r * xl, 16 rows
                 mma_bf16(ga[gi][1], rb[gi], pack_bf16(xl[0][2], xl[0][3]), pack_bf16(xl[1][2], xl[1][3]));
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (NG == 2) { gacc[2 * j][i] += ga[0][0][i] + ga[NG - 1][0][i]; gacc[2 * j + 1][i] += ga[0][1][i] + ga[NG - 1][1][i]; }
-                else { gacc[2 * j][i] += ga[0][0][i]; gacc[2 * j + 1][i] += ga[0][1][i]; }
-            }
+            for (int gi = 0; gi < NG; ++gi)
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    add2f(gacc[2 * j + k][0], gacc[2 * j + k][1], ga[gi][k][0], ga[gi][k][1]);
+                    add2f(gacc[2 * j + k][2], gacc[2 * j + k][3], ga[gi][k][2], ga[gi][k][3]);
+                }
         }
         if (ODD) {
             float ga[NG][4];
@@ -506,14 +547,14 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                 for (int ks = 0; ks < 2; ++ks) {
                     const float2 v = *reinterpret_cast<const float2*>(xt[gi] + off_b1 + ks * 8 * P);
                     mma_tf32(ga[gi], ra[gi][ks], __float_as_uint(v.x), __float_as_uint(v.y));
-                    xl[ks][0] = tf32_lo(v.x); xl[ks][1] = tf32_lo(v.y);
+                    tf32_lo2(v.x, v.y, xl[ks][0], xl[ks][1]);
                 }
                 mma_bf16(ga[gi], rb[gi], pack_bf16(xl[0][0], xl[0][1]), pack_bf16(xl[1][0], xl[1][1]));
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (NG == 2) gacc[KS - 1][i] += ga[0][i] + ga[NG - 1][i];
-                else gacc[KS - 1][i] += ga[0][i];
+            for (int gi = 0; gi < NG; ++gi) {
+                add2f(gacc[KS - 1][0], gacc[KS - 1][1], ga[gi][0], ga[gi][1]);
+                add2f(gacc[KS - 1][2], gacc[KS - 1][3], ga[gi][2], ga[gi][3]);
             }
         }
     };
@@ -528,17 +569,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         }
         bar_sync<kBarTop, kTopThreads>();
         if (!flags[1] || flags[2] >= p.C) break;
-        for (int i = ctid; i < 64 * kStreamCT; i += kConsThreads) {        // beta -> shared, [d][chain]
-            const int d = i >> 3, c = i & 7;
-            bs[i] = (c < p.C) ? __ldcg(p.beta + c * 64 + d) : 0.0f;
-        }
-        bar_sync<kBarCons, kConsThreads>();
 #pragma unroll
-        for (int kk = 0; kk < KS; ++kk) {                                   // beta -> B fragments (k = column, n = chain)
-            const float b0 = bs[(8 * kk + 2 * t) * kStreamCT + g], b1 = bs[(8 * kk + 2 * t + 1) * kStreamCT + g];
-            bhi[kk][0] = __float_as_uint(b0); bhi[kk][1] = __float_as_uint(b1);
-            bbf[kk][0] = pack_bf16(b0 - tf32_lo(b0), b1 - tf32_lo(b1));     // pairs with xl (k = 2t, 2t+1)
-            bbf[kk][1] = pack_bf16(tf32_lo(b0), tf32_lo(b1));               // pairs with x  (k = 2t+8, 2t+9)
+        for (int kk = 0; kk < KS; ++kk) {                                   // beta -> B fragments, straight from L2
+            const float4 w = __ldcg(reinterpret_cast<const float4*>(p.beta) + (kk * kStreamCT + g) * 4 + t);
+            bhi[kk][0] = __float_as_uint(w.x); bhi[kk][1] = __float_as_uint(w.y);
+            bbf[kk][0] = __float_as_uint(w.z); bbf[kk][1] = __float_as_uint(w.w);
         }
 #pragma unroll
         for (int nt = 0; nt < KS; ++nt) { gacc[nt][0] = 0.0f; gacc[nt][1] = 0.0f; gacc[nt][2] = 0.0f; gacc[nt][3] = 0.0f; }
@@ -556,7 +591,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                     const int s1 = slot; const uint32_t p1 = parity;
                     if (++slot == nst) { slot = 0; parity ^= 1u; }
                     if (p.dbg_sweep != 2) { mbar_wait(&my_full[s0], p0); mbar_wait(&my_full[s1], p1); }
-                    if (p.dbg_sweep != 1) unit(StreamTwo{}, my_tiles + (size_t)s0 * TILE_FLOATS, my_tiles + (size_t)s1 * TILE_FLOATS);
+                    if (p.dbg_sweep != 1 && cw < p.dbg_warps) unit(StreamTwo{}, my_tiles + (size_t)s0 * TILE_FLOATS, my_tiles + (size_t)s1 * TILE_FLOATS);
                     __syncwarp();
                     if (lane == 0 && p.dbg_sweep != 2) {
                         issue(s0, jn); if (++jn == n_mine) jn = 0;
@@ -565,7 +600,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                     j += 2;
                 } else {
                     if (p.dbg_sweep != 2) mbar_wait(&my_full[s0], p0);
-                    if (p.dbg_sweep != 1) unit(StreamOne{}, my_tiles + (size_t)s0 * TILE_FLOATS, nullptr);
+                    if (p.dbg_sweep != 1 && cw < p.dbg_warps) unit(StreamOne{}, my_tiles + (size_t)s0 * TILE_FLOATS, nullptr);
                     __syncwarp();
                     if (lane == 0 && p.dbg_sweep != 2) { issue(s0, jn); if (++jn == n_mine) jn = 0; }
                     j += 1;
@@ -630,8 +665,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
             }
             __stcg(p.partial + ((size_t)cta * kStreamCT + c) * kGStride + d, a);
         }
-        __threadfence();
-        bar_sync<kBarCons, kConsThreads>();
+        bar_sync<kBarCons, kConsThreads>();          // orders every thread's partial stores before the release below
         if (ctid == 0) { red_release_add(&sy->arrive, 1u); B2_DBG_LAP(2); }
 
         // ---- chain owner: sum the partials of all CTAs in fixed order, hand over to the tick warp
@@ -643,20 +677,20 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
             }
             bar_sync<kBarCons, kConsThreads>();
             if (flags[3]) {
-                // 5 segments x 65 outputs; each thread adds its segment's CTAs in ascending order.
-                // Loads are issued 16 at a time (independent, L2 latency overlapped), adds stay ordered.
-                const int o = ctid % 65, seg = ctid / 65;         // seg 0..6 (only 0..4 used)
-                if (seg < 5) {
+                // kXSeg segments x 65 outputs; each thread adds its segment's CTAs in ascending order.
+                // All loads of a segment are issued together (independent, L2 latency overlapped), adds stay ordered.
+                const int o = ctid % 65, seg = ctid / 65;
+                if (seg < kXSeg) {
                     float a = 0.0f;
-                    const int g0 = G * seg / 5, g1 = G * (seg + 1) / 5;
+                    const int g0 = G * seg / kXSeg, g1 = G * (seg + 1) / kXSeg;
                     const float* src = p.partial + (size_t)cta * kGStride + o;
-                    for (int gg = g0; gg < g1; gg += 16) {
-                        float v[16];
+                    for (int gg = g0; gg < g1; gg += 24) {
+                        float v[24];
 #pragma unroll
-                        for (int k = 0; k < 16; ++k)
+                        for (int k = 0; k < 24; ++k)
                             v[k] = (gg + k < g1) ? __ldcg(src + (size_t)(gg + k) * (kStreamCT * kGStride)) : 0.0f;
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) a += v[k];
+                        for (int k = 0; k < 24; ++k) a += v[k];
                     }
                     xred[seg * kGStride + o] = a;
                 }

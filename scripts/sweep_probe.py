@@ -12,8 +12,13 @@ beta = (rng.normal(size=D) * 0.3).astype(F)
 y = (rng.uniform(size=N) < 1 / (1 + np.exp(-(X @ beta)))).astype(F)
 names = ["wait_beta", "sweep", "cta_reduce+publish", "wait_partials", "xcta_reduce", "total", "tick_busy", "beta_frags",
          "tick_finish", "tick_advance", "tick_publish"]
-for mode in (0, 1, 2):
+configs = [(0, 1000, 0), (1, 1000, 0), (2, 1000, 0)]
+if len(sys.argv) > 1:
+    configs = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
+for mode, warps, skip in configs:
     os.environ["B200NUTS_DEBUG_SWEEP"] = str(mode)
+    os.environ["B200NUTS_DEBUG_WARPS"] = str(warps)
+    os.environ["B200NUTS_DEBUG_SKIP"] = str(skip)
     e = eng.Engine(family=_capi.FAMILY_GLM, num_chains=C, X=X, y=y, max_tree_depth=6, max_tree_depth_warmup=6)
     e.init(prng.split(prng.key(1), C), 20)
     e.run(20, 20, fields=())
@@ -23,6 +28,6 @@ for mode in (0, 1, 2):
     t0.record(); e.run(60, 20, fields=("num_steps",)); t1.record(); torch.cuda.synchronize()
     passes = e.pass_count - p0
     dbg = e.debug_clocks().astype(np.float64)
-    print("mode", mode, "passes", passes, "us/pass %.2f" % (t0.elapsed_time(t1) * 1e3 / passes),
+    print("mode", mode, "warps", warps, "skip", skip, "passes", passes, "us/pass %.2f" % (t0.elapsed_time(t1) * 1e3 / passes),
           {n: round(dbg[i] / passes) for i, n in enumerate(names)})
     e.close()
