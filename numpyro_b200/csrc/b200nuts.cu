@@ -11,6 +11,8 @@
 #include <string>
 #include <vector>
 #include <mutex>
+#include <chrono>
+#include <thread>
 #include "engine.cuh"
 #include "stream_engine.cuh"
 
@@ -24,11 +26,12 @@ struct B200Nuts {
     ChainCtl* ctl = nullptr; float* vecs = nullptr; float* gtmp = nullptr; float* scratch = nullptr;
     uint32_t* keys = nullptr;
     // R2
-    float* partial = nullptr; float* beta = nullptr; StreamSync* sync = nullptr;
+    float2* partial = nullptr; uint4* beta = nullptr; StreamSync* sync = nullptr;
     float* img = nullptr; long long n_tiles = 0; int pad_rows = 0, ks = 0;   // engine-owned tile image of (X, y)
     int grid = 0, stages = 4, vecs_in_smem = 0; size_t smem = 0;
     long long launches = 0, passes = 0;
     unsigned long long dbg[16] = {0};
+    unsigned int* trace_host = nullptr; unsigned int* trace_dev = nullptr;     // B200NUTS_TRACE: host-mapped progress words
     std::string err;
     std::mutex mu;
 };
@@ -180,8 +183,8 @@ static const void* stream_kernel_lik(int lik) {
                                 : (const void*)stream_engine_kernel<KS, LIK_NORMAL>;
 }
 static const void* stream_kernel_for(int ks, int lik) {
-#ifdef B2_STREAM_FAST_BUILD        // development builds: the covtype instance only
-    return (ks == 7 && lik == LIK_BERNOULLI) ? (const void*)stream_engine_kernel<7, LIK_BERNOULLI> : nullptr;
+#ifdef B2_STREAM_FAST_KS           // development builds: one instance only (B200NUTS_FAST_KS=<ks> python -m numpyro_b200.build)
+    return (ks == B2_STREAM_FAST_KS && lik == LIK_BERNOULLI) ? (const void*)stream_engine_kernel<B2_STREAM_FAST_KS, LIK_BERNOULLI> : nullptr;
 #else
     switch (ks) {
     case 1: return stream_kernel_lik<1>(lik);
@@ -200,11 +203,22 @@ static int stream_launch(B200Nuts* h, int mode, const OutBufs& out, const float*
     p.cfg = h->tick; p.cfg.D = h->D; p.fam = h->fam; p.out = out; p.C = h->C; p.Dp = h->Dp; p.mode = mode;
     p.ctl = h->ctl; p.vecs = h->vecs; p.partial = h->partial; p.beta = h->beta; p.sync = h->sync;
     p.z_in = z_in; p.u_out = u_out; p.g_out = g_out; p.stages = h->stages;
-    p.vecs_in_smem = h->vecs_in_smem; p.spin_limit = 6000000000LL;
+    p.vecs_in_smem = h->vecs_in_smem; p.spin_limit = 2000000000LL;      // ~1 s: every wait in the engine is bounded
+    { const char* e = getenv("B200NUTS_SPIN_LIMIT"); if (e) p.spin_limit = atoll(e); }
+    { const char* e = getenv("B200NUTS_NO_PREFETCH"); p.no_prefetch = e ? atoi(e) : 0; }
+    if (getenv("B200NUTS_TRACE") && !h->trace_host) {
+        if (cudaHostAlloc((void**)&h->trace_host, sizeof(unsigned int) * 32 * h->grid, cudaHostAllocMapped) == cudaSuccess)
+            cudaHostGetDevicePointer((void**)&h->trace_dev, h->trace_host, 0);
+    }
+    if (h->trace_host) memset(h->trace_host, 0, sizeof(unsigned int) * 32 * h->grid);
+    p.trace = h->trace_dev;
     p.img = h->img; p.n_tiles = h->n_tiles; p.pad_rows = h->pad_rows;
     { const char* e = getenv("B200NUTS_DEBUG_SWEEP"); p.dbg_sweep = e ? atoi(e) : 0; }
     { const char* e = getenv("B200NUTS_DEBUG_WARPS"); p.dbg_warps = e ? atoi(e) : 1000; }
     CK(cudaMemsetAsync(h->sync, 0, sizeof(StreamSync), st));
+    // sequence tags ride inside the exchanged data: a launch must not see the previous launch's tags
+    CK(cudaMemsetAsync(h->beta, 0, sizeof(uint4) * kBetaCopies * kBetaWords, st));
+    CK(cudaMemsetAsync(h->partial, 0, sizeof(float2) * (size_t)h->grid * kStreamCT * kGStride, st));
     void* args[] = {&p};
     const void* fn = stream_kernel_for(h->ks, h->fam.likelihood);
     if (!fn) { h->err = "stream regime: no kernel instance for this shape"; return B200NUTS_EINVAL; }
@@ -227,18 +241,63 @@ static int stream_launch(B200Nuts* h, int mode, const OutBufs& out, const float*
 
 static int check_stream_abort(B200Nuts* h, cudaStream_t st) {
     StreamSync s;
+    {   // watchdog: a launch that does not finish is reported (with the progress trace, if enabled), never waited on forever
+        double limit_s = 600.0;
+        if (const char* e = getenv("B200NUTS_WATCHDOG_S")) limit_s = atof(e);
+        const auto t0 = std::chrono::steady_clock::now();
+        cudaError_t q;
+        while ((q = cudaStreamQuery(st)) == cudaErrorNotReady) {
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > limit_s) {
+                if (h->trace_host) {
+                    fprintf(stderr, "[b200nuts] watchdog: progress (pass<<8|stage) per CTA: consumer / tick\n");
+                    for (int g = 0; g < h->grid; ++g)
+                        fprintf(stderr, "  cta %3d: cons %u.%u  tick lane0 %u.%u lane16 %u.%u lane31 %u.%u  fetch ballot %08x polls %u\n", g, h->trace_host[32 * g] >> 8, h->trace_host[32 * g] & 255u,
+                                h->trace_host[32 * g + 1] >> 8, h->trace_host[32 * g + 1] & 255u, h->trace_host[32 * g + 4] >> 8, h->trace_host[32 * g + 4] & 255u,
+                                h->trace_host[32 * g + 5] >> 8, h->trace_host[32 * g + 5] & 255u, h->trace_host[32 * g + 2], h->trace_host[32 * g + 3]);
+                }
+                if (getenv("B200NUTS_TRACE")) {      // post-mortem over a side stream (the stuck kernel keeps the main one busy)
+                    cudaStream_t side; cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
+                    std::vector<uint4> hb((size_t)kBetaCopies * kBetaWords);
+                    std::vector<float2> hp((size_t)h->grid * kStreamCT * kGStride);
+                    cudaMemcpyAsync(&s, h->sync, sizeof(s), cudaMemcpyDeviceToHost, side);
+                    cudaMemcpyAsync(hb.data(), h->beta, hb.size() * sizeof(uint4), cudaMemcpyDeviceToHost, side);
+                    cudaMemcpyAsync(hp.data(), h->partial, hp.size() * sizeof(float2), cudaMemcpyDeviceToHost, side);
+                    cudaError_t ce = cudaStreamSynchronize(side);
+                    fprintf(stderr, "[b200nuts] post-mortem copy: %s; abort_flag %u\n", cudaGetErrorString(ce), s.abort_flag);
+                    for (int r = 0; r < kBetaCopies; ++r)
+                        for (int c = 0; c < h->C; ++c) {
+                            fprintf(stderr, "  beta replica %d chain %d tags (k-step 0, t=0..3):", r, c);
+                            for (int t = 0; t < 4; ++t) fprintf(stderr, " %08x/%08x", hb[(size_t)r * kBetaWords + c * 4 + t].y, hb[(size_t)r * kBetaWords + c * 4 + t].w);
+                            fprintf(stderr, "\n");
+                        }
+                    for (int c = 0; c < h->C; ++c) {
+                        fprintf(stderr, "  partial tags chain %d (d = 0) per CTA:", c);
+                        for (int g = 0; g < h->grid; ++g) { unsigned int tg; memcpy(&tg, &hp[((size_t)g * kStreamCT + c) * kGStride].y, 4); fprintf(stderr, " %u", tg); }
+                        fprintf(stderr, "\n");
+                    }
+                }
+                h->err = "stream engine watchdog: the launch did not finish in time"; return B200NUTS_ECUDA;
+            }
+            std::this_thread::sleep_for(std::chrono::microseconds(50));
+        }
+        if (q != cudaSuccess) { h->err = std::string("stream engine: ") + cudaGetErrorString(q); return B200NUTS_ECUDA; }
+    }
     CK(cudaMemcpyAsync(&s, h->sync, sizeof(s), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     h->passes += (long long)s.passes;
     for (int i = 0; i < 16; ++i) h->dbg[i] = s.dbg[i];
     if (getenv("B200NUTS_DEBUG_TICK")) {
         for (int c = 0; c < h->C; ++c)
-            fprintf(stderr, "[b200nuts] owner %d: passes %llu tick avg %.0f max %llu | per pass: finish %.0f advance %.0f publish %.0f gredsum %.0f release %.0f\n", c, s.passes,
-                    s.passes ? (double)s.tick_sum[c] / (double)s.passes : 0.0, s.tick_max[c],
+            fprintf(stderr, "[b200nuts] owner %d: passes %llu tick avg %.0f max %llu | per pass: finish %.0f advance %.0f publish %.0f gredsum %.0f | look-ahead hit/miss: leaf %u/%u doubling %u/%u transition %u/%u\n",
+                    c, s.passes, s.passes ? (double)s.tick_sum[c] / (double)s.passes : 0.0, s.tick_max[c],
                     (double)s.tick_lap[c][0] / s.passes, (double)s.tick_lap[c][1] / s.passes, (double)s.tick_lap[c][2] / s.passes,
-                    (double)s.tick_lap[c][3] / s.passes, (double)s.tick_slow[c] / s.passes);
+                    (double)s.tick_lap[c][3] / s.passes, s.pre_hit[c][0], s.pre_miss[c][0], s.pre_hit[c][1], s.pre_miss[c][1],
+                    s.pre_hit[c][2], s.pre_miss[c][2]);
     }
-    if (s.abort_flag) { h->err = "stream engine aborted: inter-pass exchange timed out"; return B200NUTS_ECUDA; }
+    if (s.abort_flag) {
+        static const char* what[] = {"", "a tile copy never landed", "beta fetch timed out", "partial poll timed out"};
+        h->err = std::string("stream engine aborted: ") + (s.abort_flag < 4 ? what[s.abort_flag] : "?"); return B200NUTS_ECUDA;
+    }
     return 0;
 }
 
@@ -266,6 +325,7 @@ void b200nuts_destroy(B200Nuts* h) {
     if (!h) return;
     cudaFree(h->ctl); cudaFree(h->vecs); cudaFree(h->gtmp); cudaFree(h->scratch); cudaFree(h->keys);
     cudaFree(h->partial); cudaFree(h->beta); cudaFree(h->sync); cudaFree(h->img);
+    if (h->trace_host) cudaFreeHost(h->trace_host);
     delete h;
 }
 
@@ -343,11 +403,9 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
         k_stream_repack<<<h->num_sms * 8, 256>>>(h->fam.X, h->fam.y, h->fam.N, h->fam.Dx, stream_pitch(h->ks), h->n_tiles, h->img);
         if ((ce = cudaGetLastError()) != cudaSuccess) return fail("repack", ce);
         h->launches += 1;
-        if ((ce = cudaMalloc(&h->partial, sizeof(float) * (size_t)h->grid * kStreamCT * kGStride)) != cudaSuccess) return fail("cudaMalloc partial", ce);
-        if ((ce = cudaMalloc(&h->beta, sizeof(float) * 8 * kStreamCT * 16)) != cudaSuccess) return fail("cudaMalloc beta", ce);
+        if ((ce = cudaMalloc(&h->partial, sizeof(float2) * (size_t)h->grid * kStreamCT * kGStride)) != cudaSuccess) return fail("cudaMalloc partial", ce);
+        if ((ce = cudaMalloc(&h->beta, sizeof(uint4) * kBetaCopies * kBetaWords)) != cudaSuccess) return fail("cudaMalloc beta", ce);
         if ((ce = cudaMalloc(&h->sync, sizeof(StreamSync))) != cudaSuccess) return fail("cudaMalloc sync", ce);
-        cudaMemset(h->beta, 0, sizeof(float) * 8 * kStreamCT * 16);
-        cudaMemset(h->partial, 0, sizeof(float) * (size_t)h->grid * kStreamCT * kGStride);
     }
     if ((ce = cudaDeviceSynchronize()) != cudaSuccess) return fail("create", ce);
     *out = h;

@@ -38,9 +38,17 @@
 //             result collect r_hi x, rows 8..15 the r_lo x correction; 8 columns per MMA.  A chunk of 16
 //             columns accumulates over the tile's 2 k-steps on the tensor core, then joins the
 //             per-pass fp32 accumulators with FADDs.
-// Inter-pass exchange (deterministic, no float atomics): per-CTA partials -> global; chain c's
-// CTA sums the partials in fixed order, its tick warp finishes the potential (priors, Jacobians),
-// ticks the chain and publishes the next beta_c; two monotone counters replace grid.sync.
+// Inter-pass exchange (deterministic, no float atomics, no counters, no fences).  Everything that crosses
+// CTAs carries its own sequence tag inside the same 8-byte word as the data ("flag-in-data"), so a reader
+// simply polls the data it needs:
+//   * every CTA reduces its warps' accumulators through the ring slots its warps just drained (one barrier)
+//     and publishes {value, tag} pairs;
+//   * chain c's CTA polls the 148 partials of its chain, sums them in fixed order, its tick warp finishes the
+//     potential (priors, Jacobians), ticks the chain (tick.cuh) and publishes the next beta_c as tagged pairs
+//     in MMA-fragment order (4 replicas to spread the L2 load);
+//   * the tick warp of every CTA fetches all chains' beta, stages them in shared memory and releases the
+//     CTA's consumer warps through a named barrier.  While the consumers sweep, an owner's tick warp looks
+//     ahead in the chain's PRNG streams (Tick::prefetch) so the next tick finds its random numbers ready.
 #pragma once
 #include <cuda_runtime.h>
 #include "tick.cuh"
@@ -57,7 +65,9 @@ constexpr int kGStride = 72;             // floats per (cta, chain) partial: gbe
 constexpr int kRedWarps = (kConsWarps + 1) / 2;   // rows of the two-stage CTA reduction scratch
 constexpr int kXSeg = 7;                 // segments of the cross-CTA reduction (7 x 65 threads)
 constexpr int kXRedFloats = kXSeg * kGStride + 192;   // owner CTA: segment sums + gradient scratch for the tick
-constexpr int kBarTop = 1, kBarCons = 2, kBarTick = 3;
+constexpr int kBarBeta = 1, kBarCons = 2, kBarTick = 3;
+constexpr int kBetaCopies = 4;           // replicas of the published beta (CTA c fetches replica c mod 4)
+constexpr int kBetaWords = 8 * kStreamCT * 4;     // 16-byte words per replica: [k-step][chain][t]
 constexpr int kConsThreads = kConsWarps * 32, kTopThreads = kStreamThreads;
 
 B2_HD constexpr int stream_pitch(int KS) { return (KS % 2 == 0) ? 8 * KS + 8 : 8 * KS; }     // 8 * odd
@@ -69,20 +79,23 @@ B2_HD int stream_tile_index(int P, int r, int c) {
 }
 B2_HD int stream_tile_y_index(int P, int r) { return kTileRows * P + (r & 7) * 2 + ((r >> 3) & 1); }
 B2_HD constexpr int stream_tile_floats(int KS) { return kTileRows * stream_pitch(KS) + kTileRows; }
+// ring slot stride: a drained slot doubles as the warp's reduction scratch (18 values x 32 lanes)
+B2_HD constexpr int stream_slot_floats(int KS) { return stream_tile_floats(KS) > 18 * 32 ? stream_tile_floats(KS) : 18 * 32; }
 B2_HD constexpr int stream_ks_for(int D) { return D <= 8 ? 1 : D <= 16 ? 2 : D <= 32 ? 4 : D <= 56 ? 7 : 8; }
 
 // dbg: clock64 totals on CTA 0 -- [0] wait for betas (incl. the owners' ticks), [1] sweep, [2] CTA reduction +
-// publish partial, [3] wait for all partials, [4] cross-CTA reduction, [5] total loop, [6] tick warp busy,
+// publish partial, [3] (unused), [4] poll + sum the partials, [5] total loop, [6] tick warp busy,
 // [7] beta -> fragments, [8] tick: finish potential, [9] tick: state machine, [10] tick: publish beta
-struct StreamSync { unsigned int arrive, ready, done, abort_flag; unsigned long long passes; unsigned long long dbg[16];
-                    unsigned long long tick_sum[kStreamCT], tick_max[kStreamCT], tick_slow[kStreamCT], tick_lap[kStreamCT][4]; };   // per owner CTA: tick cycles
+struct StreamSync { unsigned int abort_flag, pad_[3]; unsigned long long passes; unsigned long long dbg[16];
+                    unsigned long long tick_sum[kStreamCT], tick_max[kStreamCT], tick_lap[kStreamCT][4];
+                    unsigned int pre_hit[kStreamCT][4], pre_miss[kStreamCT][4]; };   // per owner CTA: tick cycles, look-ahead hits
 
 struct StreamParams {
     TickCfg cfg; FamilySpec fam; OutBufs out;
     int C, Dp, mode;                     // mode 0: run chains, 1: evaluate potential at z_in
     ChainCtl* ctl; float* vecs;          // [C], [V_COUNT][C][Dp]
-    float* partial;                      // [grid][kStreamCT][kGStride]
-    float* beta;                         // [8 k-steps][kStreamCT][4][4]: every chain's beta as ready-made MMA fragments
+    float2* partial;                     // [grid][kStreamCT][kGStride] {value, tag}
+    uint4* beta;                         // [kBetaCopies][8 k-steps][kStreamCT][4] {b0, tag, b1, tag}: beta in MMA-fragment order
     StreamSync* sync;
     const float* z_in; float* u_out; float* g_out;    // mode 1
     const float* img;                    // tile image of (X, y), see above
@@ -93,6 +106,8 @@ struct StreamParams {
     int dbg_sweep;                       // timing experiments only: 1 = copies without compute, 2 = compute without copies
     int dbg_warps;                       // ... only the first dbg_warps consumer warps compute
     long long spin_limit;
+    unsigned int* trace;                 // debug only (B200NUTS_TRACE): host-mapped [grid][8] progress words, see B2_TRACE
+    int no_prefetch;                     // debug only: skip the PRNG look-ahead
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -113,9 +128,29 @@ B2_D bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 B2_D void mbar_wait(uint64_t* bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) {} }
+// bounded variant: gives up after `limit` clocks and raises *abort_flag (returns false)
+// (abort codes: 1 tile copy never landed, 2 beta fetch timed out, 3 partial poll timed out)
+B2_D bool mbar_wait_bounded(uint64_t* bar, uint32_t parity, long long limit, unsigned int* abort_flag) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
+    unsigned int it = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++it & 255u) == 0u) {
+            if (*(volatile unsigned int*)abort_flag) return false;
+            if (clock64() - t0 > limit) { atomicCAS(abort_flag, 0u, 1u); return false; }
+        }
+    }
+    return true;
+}
 B2_D void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+B2_D uint4 ld_volatile_v4(const uint4* p) {
+    uint4 v; asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); return v;
+}
+B2_D float2 ld_volatile_v2(const float2* p) {
+    float2 v; asm volatile("ld.volatile.global.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory"); return v;
 }
 B2_D unsigned int ld_acquire(const unsigned int* p) {
     unsigned int v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
@@ -165,8 +200,15 @@ B2_D void add2f(float& a0, float& a1, float b0, float b1) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pack2f(a0, a1)), "l"(pack2f(b0, b1)));
     unpack2f(d, a0, a1);
 }
-template <int ID, int N> B2_D void bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
-template <int ID, int N> B2_D void bar_arrive() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
+// Named barriers count whole warps: a warp that reaches one while diverged (e.g. after per-lane polling loops)
+// would be counted once per divergent group.  Reconverge first.
+template <int ID, int N> B2_D void bar_sync() { __syncwarp(); asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
+template <int ID, int N> B2_D void bar_arrive() { __syncwarp(); asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
+// Warp barrier that cannot be optimised away (see the gred reduction in the tick warp): a shuffle whose result is consumed.
+B2_D void warp_sync_hard() {
+    unsigned int x = __shfl_sync(0xFFFFFFFFu, threadIdx.x, 0);
+    asm volatile("" ::"r"(x) : "memory");
+}
 B2_D float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 B2_D float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 B2_D float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -204,18 +246,22 @@ B2_D bool spin_ge(const unsigned int* ctr, unsigned int target, StreamSync* sy, 
     return true;
 }
 
+// progress marker of (CTA, role): role 0 = consumer thread 0, 1 = tick lane 0; word = pass << 8 | stage
+#define B2_TRACE(role, stage) do { if (p.trace) { asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p.trace + 32 * blockIdx.x + (role)), "r"((pass << 8) | (unsigned)(stage)) : "memory"); } } while (0)
+
+#define B2_TRACE_LANES(stage) do { if (lane == 0) B2_TRACE(1, stage); if (lane == 16) B2_TRACE(4, stage); if (lane == 31) B2_TRACE(5, stage); } while (0)
+
 B2_HD size_t stream_fixed_smem(int Dp, bool vecs_in_smem) {
     size_t b = 0;
     b += (size_t)kConsWarps * kMaxStages * 8;                      // mbarriers
-    b += (size_t)kRedWarps * 16 * 32 * 4;                          // CTA reduction scratch, [warp][value][lane]
+    b += (size_t)kBetaWords * 16;                                  // staged beta, [k-step][chain][t] {b0, tag, b1, tag}
     b += (size_t)kXRedFloats * 4;                                  // cross-CTA reduction + tick scratch
-    b += 64 * 4 + 64 * 4 + 64 + 128;                               // gred(+nll), flags, timers
-    b += ((sizeof(ChainCtl) + 15) / 16) * 16;
+    b += 64 * 4 + 64 * 4 + 256 + 128;                              // gred(+nll), flags, timers
     if (vecs_in_smem) b += (size_t)V_COUNT * Dp * 4;
     return b + 128;
 }
 B2_HD size_t stream_smem_bytes(int KS, int Dp, int stages, bool vecs_in_smem) {
-    return stream_fixed_smem(Dp, vecs_in_smem) + (size_t)kConsWarps * stages * stream_tile_floats(KS) * 4;
+    return stream_fixed_smem(Dp, vecs_in_smem) + (size_t)kConsWarps * stages * stream_slot_floats(KS) * 4;
 }
 
 // One-time repack of the caller's (X, y) into the tile image (see the header comment).
@@ -239,61 +285,49 @@ __global__ void k_stream_repack(const float* __restrict__ X, const float* __rest
     }
 }
 
-// beta_c = s(z) * u for the next sweep (zero when the chain is done), published to global memory as the B
-// fragments the consumers need: for k-step kk and lane (g = chain, t) the four words
-//   { beta[8kk+2t], beta[8kk+2t+1] (raw fp32: the TF32 MMA reads the top 19 bits),
-//     bf16x2(beta_hi[8kk+2t], beta_hi[8kk+2t+1]), bf16x2(beta_lo[..], beta_lo[..]) }      (see unit() below)
-B2_D void stream_publish_beta(const StreamParams& p, int cta, const float* zsrc, bool active) {
+// beta_c = s(z) * u for the next sweep (zero when the chain needs no gradient), published in the order of the
+// consumers' B fragments: word (k-step kk, chain, t) = { beta[8kk+2t], tag, beta[8kk+2t+1], tag }.  Each 8-byte
+// half is written atomically, so a reader that sees the tag also sees the value next to it.
+B2_D void stream_publish_beta(const StreamParams& p, int cta, const float* zsrc, bool active, uint32_t tag) {
     const int lane = threadIdx.x & 31;
-    {
-        const int kk = lane >> 2, t = lane & 3;          // 8 k-steps x 4 = 32 lanes
-        const int d0 = 8 * kk + 2 * t;
-        float b0 = 0.0f, b1 = 0.0f;
-        if (active && d0 < p.fam.Dx) b0 = glm_scale_at(p.fam, zsrc, d0) * zsrc[p.fam.off_u + d0];
-        if (active && d0 + 1 < p.fam.Dx) b1 = glm_scale_at(p.fam, zsrc, d0 + 1) * zsrc[p.fam.off_u + d0 + 1];
-        const float l0 = tf32_lo(b0), l1 = tf32_lo(b1);
-        float4 w;
-        w.x = b0; w.y = b1;
-        w.z = __uint_as_float(pack_bf16(b0 - l0, b1 - l1));
-        w.w = __uint_as_float(pack_bf16(l0, l1));
-        __stcg(reinterpret_cast<float4*>(p.beta) + (kk * kStreamCT + cta) * 4 + t, w);
-    }
+    const int kk = lane >> 2, t = lane & 3;              // 8 k-steps x 4 = 32 lanes
+    const int d0 = 8 * kk + 2 * t;
+    float b0 = 0.0f, b1 = 0.0f;
+    if (active && d0 < p.fam.Dx) b0 = glm_scale_at(p.fam, zsrc, d0) * zsrc[p.fam.off_u + d0];
+    if (active && d0 + 1 < p.fam.Dx) b1 = glm_scale_at(p.fam, zsrc, d0 + 1) * zsrc[p.fam.off_u + d0 + 1];
+    const uint4 w = make_uint4(__float_as_uint(b0), tag, __float_as_uint(b1), tag);
+#pragma unroll
+    for (int r = 0; r < kBetaCopies; ++r) __stcg(p.beta + r * kBetaWords + (kk * kStreamCT + cta) * 4 + t, w);
     __syncwarp();
 }
 
 // The tick warp's work between two sweeps, for the chain owned by this CTA: finish the potential from the
-// reduced likelihood sums, advance the NUTS state machine, publish the next beta.  Deliberately not inlined:
-// it is the same code for every kernel instance.  Returns true when the chain needs no further gradient.
-__device__ __forceinline__ bool stream_tick_step(const StreamParams& p, ChainCtl* sctl, ChainVecs cv, const float* gred,
-                                              float* gz, float nll, int cta, unsigned long long* tdbg) {
+// reduced likelihood sums and advance the NUTS state machine.  Returns true when the chain needs no further gradient.
+__device__ __forceinline__ bool stream_tick_step(const StreamParams& p, Tick& tk, const float* gred, float* gz, float nll,
+                                                 int cta, unsigned long long* tdbg, unsigned int pass) {
     const int lane = threadIdx.x & 31;
     const bool dbg = (lane == 0);
     long long t0 = dbg ? clock64() : 0ll;
-#define B2_TICK_LAP(k) do { __syncwarp(); if (dbg) { const long long t1 = clock64(); tdbg[k] += (unsigned long long)(t1 - t0); t0 = t1; } } while (0)
+#define B2_TICK_LAP(k) do { warp_sync_hard(); if (dbg) { const long long t1 = clock64(); tdbg[k] += (unsigned long long)(t1 - t0); t0 = t1; } } while (0)
     float u;
     if (p.mode == 1) {
         const float* zin = p.z_in + (size_t)cta * p.cfg.D;
         glm_finish(p.fam, zin, nll, gred, u, gz);
-        __syncwarp();
+        warp_sync_hard();
         if (lane == 0) p.u_out[cta] = u;
         for (int d = lane; d < p.cfg.D; d += 32) p.g_out[(size_t)cta * p.cfg.D + d] = gz[d];
         return true;
     }
-    if (sctl->phase == PH_DONE) return false;
-    ChainCtl c = *sctl;
-    __syncwarp();
-    glm_finish(p.fam, cv.v(V_ZS), nll, gred, u, gz);
+    B2_TRACE_LANES(41);
+    glm_finish(p.fam, tk.v(V_ZS), nll, gred, u, gz);
+    B2_TRACE_LANES(42);
     B2_TICK_LAP(8);
-    Tick tk{p.cfg, c, cv, p.out, cta, p.C};
     tk.advance(u, gz);
-    __syncwarp();
-    if (lane == 0) *sctl = c;
-    const bool finished = (c.phase == PH_DONE);
+    B2_TRACE_LANES(43);
+    warp_sync_hard();                    // the next beta is gathered across lanes from V_ZS
     B2_TICK_LAP(9);
-    stream_publish_beta(p, cta, cv.v(V_ZS), !finished);
-    B2_TICK_LAP(10);
 #undef B2_TICK_LAP
-    return finished;
+    return tk.c.phase == PH_DONE;
 }
 
 struct StreamOne { static constexpr int value = 1; };
@@ -304,7 +338,8 @@ template <int KS, int LIK>
 __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const __grid_constant__ StreamParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int P = stream_pitch(KS);            // row pitch of a tile, floats
-    constexpr int TILE_FLOATS = stream_tile_floats(KS);
+    constexpr int TILE_FLOATS = stream_tile_floats(KS);   // floats moved per tile
+    constexpr int SLOT_FLOATS = stream_slot_floats(KS);   // ring slot stride
     constexpr int NCH = KS / 2;                    // backward: 16-column chunks (two 8-column MMAs per 128-bit load)
     constexpr bool ODD = (KS & 1) != 0;            // ... + one 8-column chunk (64-bit loads) when KS is odd
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -313,14 +348,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
 
     // ---- carve shared memory
     unsigned char* q = smem_raw;
-    float* tiles = (float*)q; q += (size_t)kConsWarps * nst * TILE_FLOATS * 4;
+    float* tiles = (float*)q; q += (size_t)kConsWarps * nst * SLOT_FLOATS * 4;
     uint64_t* full = (uint64_t*)q; q += (size_t)kConsWarps * kMaxStages * 8;
-    float* red = (float*)q; q += (size_t)kRedWarps * 16 * 32 * 4;
+    uint4* bs = (uint4*)q; q += (size_t)kBetaWords * 16;
     float* xred = (float*)q; q += (size_t)kXRedFloats * 4;
     float* gred = (float*)q; q += 64 * 4 + 64 * 4;
-    int* flags = (int*)q; q += 64;
+    int* flags = (int*)q; q += 256;                  // [0] 0 go / 1 all chains done / 2 abort, [16..31] reduction slot of warp w
     unsigned long long* tdbg = (unsigned long long*)q; q += 128;
-    ChainCtl* sctl = (ChainCtl*)q; q += ((sizeof(ChainCtl) + 15) / 16) * 16;
     float* cvecs = (float*)q;
 
     // ---- this CTA's slice of tiles
@@ -343,7 +377,6 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
             }
             cv.base = cvecs; cv.field_stride = p.Dp;
         } else { cv.base = p.vecs + (size_t)cta * p.Dp; cv.field_stride = p.C * p.Dp; }
-        if (tid == 0) *sctl = p.ctl[cta];
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
@@ -351,67 +384,113 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
     StreamSync* sy = p.sync;
     unsigned int pass = 0;
 
-    // =============================================================== tick warp
+    // =============================================================== tick / fetch warp
     if (warp == kConsWarps) {
         const bool dbg = (cta == 0 && lane == 0);
-        unsigned long long tk_sum = 0ull, tk_max = 0ull, tk_slow = 0ull;
-        unsigned long long* tlap = tdbg + 8;          // [0..2] finish / advance / publish, [3] gred sum, [4] release
+        unsigned long long tk_sum = 0ull, tk_max = 0ull;
+        unsigned long long* tlap = tdbg + 8;          // [0..1] finish / advance, [2] publish, [3] gred sum
         float loss0, dl0;
         link_fn<LIK>(0.0f, 0.0f, loss0, dl0);        // what every zero pad row adds to a chain's nll
         const float pad_nll = (float)p.pad_rows * loss0;
+        // the chain's control block lives in this warp's registers for the whole launch (every lane holds a copy)
+        ChainCtl c;
+        if (is_tick && p.mode == 0) c = p.ctl[cta]; else memset(&c, 0, sizeof(c));
+        Tick tk{p.cfg, c, cv, p.out, cta, p.C};
+        bool chain_done = !is_tick || (p.mode == 0 && c.phase == PH_DONE);
+        uint32_t seq = 1;                            // tag of the beta the next sweep needs
         if (is_tick) {                               // prologue: the first beta
             const float* zsrc = (p.mode == 0) ? cv.v(V_ZS) : (p.z_in + (size_t)cta * p.cfg.D);
-            const bool active = (p.mode == 1) || (sctl->phase != PH_DONE);
-            stream_publish_beta(p, cta, zsrc, active);
-            if (lane == 0) {
-                if (p.mode == 0 && sctl->phase == PH_DONE) atomicAdd(&sy->done, 1u);
-                red_release_add(&sy->ready, 1u);     // release: cumulative over the warp's stores ordered by __syncwarp
-            }
+            stream_publish_beta(p, cta, zsrc, !chain_done, seq | (chain_done ? 0x80000000u : 0u));
         }
+        const uint4* bsrc = p.beta + (cta % kBetaCopies) * kBetaWords;
+        const int my_chain = (lane >> 2) & 7;         // chain of this lane's words (word w = lane + 32 kk)
         while (true) {
-            bar_sync<kBarTop, kTopThreads>();
-            if (!flags[1] || flags[2] >= p.C) break;
+            // ---- fetch every chain's beta for sweep `seq` (tags ride in the data: poll until they all match)
+            int status = 0;
+            B2_TRACE_LANES(1);
+            {
+                uint4 w[KS];
+                const long long t_w = clock64();
+                while (true) {
+                    bool ok = true;
+#pragma unroll
+                    for (int kk = 0; kk < KS; ++kk) {
+                        w[kk] = ld_volatile_v4(bsrc + lane + 32 * kk);
+                        ok = ok && ((w[kk].y & 0x7FFFFFFFu) == seq) && ((w[kk].w & 0x7FFFFFFFu) == seq);
+                    }
+                    if (my_chain >= p.C) ok = true;
+                    if (p.trace) {
+                        const unsigned int bal = __ballot_sync(0xFFFFFFFFu, ok);
+                        if (lane == 0) { p.trace[32 * blockIdx.x + 2] = bal; p.trace[32 * blockIdx.x + 3] += 1u; }
+                    }
+                    if (__all_sync(0xFFFFFFFFu, ok)) break;
+                    // (warp-uniform exits: a lane that left alone would deadlock the __all_sync above)
+                    bool give_up = ld_acquire(&sy->abort_flag) != 0u;
+                    if (clock64() - t_w > p.spin_limit) { atomicCAS(&sy->abort_flag, 0u, 2u); give_up = true; }
+                    if (__any_sync(0xFFFFFFFFu, give_up)) { status = 2; break; }
+                }
+                const bool zero = (my_chain >= p.C) || status == 2;
+#pragma unroll
+                for (int kk = 0; kk < KS; ++kk) bs[lane + 32 * kk] = zero ? make_uint4(0u, 0u, 0u, 0u) : w[kk];
+                const bool done_bit = (my_chain >= p.C) || ((w[0].y >> 31) != 0u);
+                if (status == 0 && __all_sync(0xFFFFFFFFu, done_bit)) status = 1;
+            }
+            if (lane == 0) flags[0] = status;
+            __syncwarp();
+            bar_arrive<kBarBeta, kStreamThreads>();  // release the consumers (they read flags[0] and `bs`)
+            if (status) break;
+            B2_TRACE_LANES(2);
+            if (is_tick && p.mode == 0 && !chain_done && !p.no_prefetch) tk.prefetch();     // off the critical path: PRNG look-ahead
             if (is_tick) {
-                bar_sync<kBarTick, kTopThreads>();   // segment sums are in `xred`
-                if (flags[3]) {
-                    const long long t_a = clock64();
-                    for (int d = lane; d < 65; d += 32) {
+                B2_TRACE_LANES(3);
+                bar_sync<kBarTick, kStreamThreads>();    // segment sums are in `xred`
+                B2_TRACE_LANES(4);
+                const long long t_a = clock64();
+                // (uniform trip count + shuffle broadcast on purpose: ptxas 12.9 turned the __syncwarp() after the
+                //  lane-strided form of this loop -- lane 0 runs 3 iterations, the others 2 -- into a NOP and lanes
+                //  1..31 read last pass's gred[64]; gred[j] itself is only ever read back by the lane that wrote it)
+                float a64 = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int d = lane + 32 * k;
+                    if (d < 65) {
                         float a = xred[d];
 #pragma unroll
                         for (int sgm = 1; sgm < kXSeg; ++sgm) a += xred[sgm * kGStride + d];
                         gred[d] = a;
-                    }
-                    __syncwarp();
-                    const float nll = gred[64] - pad_nll;
-                    if (lane == 0) tlap[3] += (unsigned long long)(clock64() - t_a);
-                    float* gz = xred + kXSeg * kGStride; // scratch for the gradient wrt z (<= Dp floats)
-                    const bool finished = stream_tick_step(p, sctl, cv, gred, gz, nll, cta, tdbg);
-                    __syncwarp();
-                    if (lane == 0) {
-                        const long long t_r = clock64();
-                        if (finished) atomicAdd(&sy->done, 1u);
-                        red_release_add(&sy->ready, 1u);
-                        tlap[4] += (unsigned long long)(clock64() - t_r);
-                        const unsigned long long dt = (unsigned long long)(clock64() - t_a);
-                        tk_sum += dt; if (dt > tk_max) tk_max = dt; if (dt > 12000ull) tk_slow += 1ull;
-                        if (dbg) tdbg[6] += dt;
+                        if (k == 2) a64 = a;
                     }
                 }
+                const float nll = __shfl_sync(0xFFFFFFFFu, a64, 0) - pad_nll;
+                if (lane == 0) tlap[3] += (unsigned long long)(clock64() - t_a);
+                float* gz = xred + kXSeg * kGStride; // scratch for the gradient wrt z (<= Dp floats)
+                if (!chain_done) chain_done = stream_tick_step(p, tk, gred, gz, nll, cta, tdbg, pass);
+                B2_TRACE_LANES(5);
+                const long long t_p = clock64();
+                stream_publish_beta(p, cta, cv.v(V_ZS), !chain_done, (seq + 1u) | (chain_done ? 0x80000000u : 0u));
+                if (lane == 0) {
+                    const long long t_e = clock64();
+                    tlap[2] += (unsigned long long)(t_e - t_p);
+                    const unsigned long long dt = (unsigned long long)(t_e - t_a);
+                    tk_sum += dt; if (dt > tk_max) tk_max = dt;
+                    if (dbg) tdbg[6] += dt;
+                }
             }
-            ++pass;
+            ++seq; ++pass;
         }
-        if (is_tick && lane == 0 && p.mode == 0) p.ctl[cta] = *sctl;
+        B2_TRACE_LANES(6);
         if (is_tick && lane == 0) {
-            sy->tick_sum[cta] = tk_sum; sy->tick_max[cta] = tk_max; sy->tick_slow[cta] = tk_slow;
-            for (int k = 0; k < 4; ++k) sy->tick_lap[cta][k] = tlap[k < 3 ? k : 3];
-            sy->tick_slow[cta] = tlap[4];
+            if (p.mode == 0) p.ctl[cta] = c;
+            sy->tick_sum[cta] = tk_sum; sy->tick_max[cta] = tk_max;
+            for (int k = 0; k < 4; ++k) { sy->tick_lap[cta][k] = tlap[k]; sy->pre_hit[cta][k] = c.pre_hit[k]; sy->pre_miss[cta][k] = c.pre_miss[k]; }
         }
+        __syncthreads();                             // pairs with the consumers' shutdown barrier: chain vectors are final
         return;
     }
 
     // =============================================================== consumer warps
-    const int cw = warp;                             // 0..12
-    const int ctid = tid;                            // 0..415
+    const int cw = warp;                             // 0..14
+    const int ctid = tid;                            // 0..479
     const int g = lane >> 2, t = lane & 3;           // mma.sync fragment coordinates (groupID, threadID_in_group)
     // float offsets inside a tile (stream_tile_index): forward lane (g, t) reads pair row g, columns
     // 8kk + 2t, +1; backward lane (g, t) reads pair row 4ks + t, columns 16j + 2g, +1 (or 16*NCH + g)
@@ -425,19 +504,21 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                                                      // [0], [1] = r_hi part, [2], [3] = r_lo part
     float nll[2] = {0.0f, 0.0f};                     // loss of chains 2t, 2t+1 over this lane's rows
 
-    // ---- this warp's private ring: its tiles are w, w + 13, w + 26, ... of the CTA's slice, over and over
+    // ---- this warp's private ring: its tiles are w, w + 15, w + 30, ... of the CTA's slice, over and over
     const int n_mine = (n_tiles > cw) ? (n_tiles - cw + kConsWarps - 1) / kConsWarps : 0;
-    float* my_tiles = tiles + (size_t)cw * nst * TILE_FLOATS;
+    float* my_tiles = tiles + (size_t)cw * nst * SLOT_FLOATS;
     uint64_t* my_full = full + cw * kMaxStages;
     const float* my_src = p.img + (t_begin_tile + cw) * TILE_FLOATS;
     auto issue = [&](int slot, int j) {              // one lane: tile j of this warp -> slot
         mbar_expect_tx(&my_full[slot], TILE_FLOATS * 4u);
-        bulk_g2s(my_tiles + (size_t)slot * TILE_FLOATS, my_src + (size_t)j * kConsWarps * TILE_FLOATS, TILE_FLOATS * 4u, &my_full[slot]);
+        bulk_g2s(my_tiles + (size_t)slot * SLOT_FLOATS, my_src + (size_t)j * kConsWarps * TILE_FLOATS, TILE_FLOATS * 4u, &my_full[slot]);
     };
     int slot = 0; uint32_t parity = 0;               // ring position of the next tile to consume
     if (lane == 0 && n_mine > 0)
         for (int s = 0; s < nst; ++s) issue(s, s % n_mine);
     const bool pairs = (nst == 4);                   // consume two tiles at a time (two independent instruction streams)
+    // A warp with no tiles still owns its (empty) slot 0 as reduction scratch; the others use the slot they drained last.
+    int red_slot = 0, red_tile = -1;
 
     const bool dbg = (cta == 0 && ctid == 0);
     long long t_prev = clock64();
@@ -559,21 +640,23 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         }
     };
 
+    const uint32_t spin_hi = (uint32_t)(p.spin_limit >> 32), spin_lo = (uint32_t)p.spin_limit;   // (kept live across the loop cheaply)
+    (void)spin_hi; (void)spin_lo;
     while (true) {
-        // ---- wait for every chain's beta of this pass
-        if (ctid == 0) {
-            const bool ok = spin_ge(&sy->ready, (unsigned)p.C * (pass + 1u), sy, p.spin_limit);
-            flags[1] = ok ? 1 : 0;
-            flags[2] = (int)ld_acquire(&sy->done);
-            B2_DBG_LAP(0);
-        }
-        bar_sync<kBarTop, kTopThreads>();
-        if (!flags[1] || flags[2] >= p.C) break;
+        // ---- wait until this CTA's tick warp has staged every chain's beta of this pass
+        if (ctid == 0) B2_TRACE(0, 1);
+        bar_sync<kBarBeta, kStreamThreads>();
+        if (flags[0]) break;
+        if (ctid == 0) B2_TRACE(0, 2);
+        if (ctid == 0) B2_DBG_LAP(0);
 #pragma unroll
-        for (int kk = 0; kk < KS; ++kk) {                                   // beta -> B fragments, straight from L2
-            const float4 w = __ldcg(reinterpret_cast<const float4*>(p.beta) + (kk * kStreamCT + g) * 4 + t);
-            bhi[kk][0] = __float_as_uint(w.x); bhi[kk][1] = __float_as_uint(w.y);
-            bbf[kk][0] = __float_as_uint(w.z); bbf[kk][1] = __float_as_uint(w.w);
+        for (int kk = 0; kk < KS; ++kk) {                                   // beta -> B fragments (k = column, n = chain)
+            const uint4 w = bs[(kk * kStreamCT + g) * 4 + t];
+            const float b0 = __uint_as_float(w.x), b1 = __uint_as_float(w.z);
+            float l0, l1; tf32_lo2(b0, b1, l0, l1);
+            bhi[kk][0] = w.x; bhi[kk][1] = w.z;
+            bbf[kk][0] = pack_bf16(b0 - l0, b1 - l1);                       // pairs with xl (k = 2t, 2t+1)
+            bbf[kk][1] = pack_bf16(l0, l1);                                 // pairs with x  (k = 2t+8, 2t+9)
         }
 #pragma unroll
         for (int nt = 0; nt < KS; ++nt) { gacc[nt][0] = 0.0f; gacc[nt][1] = 0.0f; gacc[nt][2] = 0.0f; gacc[nt][3] = 0.0f; }
@@ -590,127 +673,128 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                 if (pairs && j + 1 < n_mine) {
                     const int s1 = slot; const uint32_t p1 = parity;
                     if (++slot == nst) { slot = 0; parity ^= 1u; }
-                    if (p.dbg_sweep != 2) { mbar_wait(&my_full[s0], p0); mbar_wait(&my_full[s1], p1); }
-                    if (p.dbg_sweep != 1 && cw < p.dbg_warps) unit(StreamTwo{}, my_tiles + (size_t)s0 * TILE_FLOATS, my_tiles + (size_t)s1 * TILE_FLOATS);
+                    if (p.dbg_sweep != 2) { mbar_wait_bounded(&my_full[s0], p0, p.spin_limit, &sy->abort_flag); mbar_wait_bounded(&my_full[s1], p1, p.spin_limit, &sy->abort_flag); }
+                    if (p.dbg_sweep != 1 && cw < p.dbg_warps) unit(StreamTwo{}, my_tiles + (size_t)s0 * SLOT_FLOATS, my_tiles + (size_t)s1 * SLOT_FLOATS);
                     __syncwarp();
+                    const bool last = (j + 2 >= n_mine);
                     if (lane == 0 && p.dbg_sweep != 2) {
                         issue(s0, jn); if (++jn == n_mine) jn = 0;
-                        issue(s1, jn); if (++jn == n_mine) jn = 0;
+                        if (!last) issue(s1, jn);
                     }
+                    if (last) { red_slot = s1; red_tile = jn; }        // refilled after the CTA reduction below
+                    if (++jn == n_mine) jn = 0;
                     j += 2;
                 } else {
-                    if (p.dbg_sweep != 2) mbar_wait(&my_full[s0], p0);
-                    if (p.dbg_sweep != 1 && cw < p.dbg_warps) unit(StreamOne{}, my_tiles + (size_t)s0 * TILE_FLOATS, nullptr);
+                    if (p.dbg_sweep != 2) mbar_wait_bounded(&my_full[s0], p0, p.spin_limit, &sy->abort_flag);
+                    if (p.dbg_sweep != 1 && cw < p.dbg_warps) unit(StreamOne{}, my_tiles + (size_t)s0 * SLOT_FLOATS, nullptr);
                     __syncwarp();
-                    if (lane == 0 && p.dbg_sweep != 2) { issue(s0, jn); if (++jn == n_mine) jn = 0; }
+                    const bool last = (j + 1 >= n_mine);
+                    if (lane == 0 && p.dbg_sweep != 2 && !last) issue(s0, jn);
+                    if (last) { red_slot = s0; red_tile = jn; }
+                    if (++jn == n_mine) jn = 0;
                     j += 1;
                 }
             }
         }
-        if (ctid == 0) B2_DBG_LAP(1);
+        if (ctid == 0) { B2_DBG_LAP(1); B2_TRACE(0, 3); }
 
-        // ---- reduce warps -> CTA in two stages through a [7][16][32] scratch (value-major, lane-minor: no bank
-        //      conflicts), then publish the partial.  Fixed order => bit-reproducible.
-        float val[16];
+        // ---- reduce warps -> CTA through the ring slot every warp drained last ([value][lane] floats, conflict
+        //      free), one barrier, fixed order => bit-reproducible; then publish {value, tag} pairs.
+        {
+            float val[16];
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            val[2 * nt] = (nt < KS) ? gacc[nt < KS ? nt : 0][0] + gacc[nt < KS ? nt : 0][2] : 0.0f;
-            val[2 * nt + 1] = (nt < KS) ? gacc[nt < KS ? nt : 0][1] + gacc[nt < KS ? nt : 0][3] : 0.0f;
-        }
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            nll[k] += __shfl_xor_sync(0xFFFFFFFFu, nll[k], 4);
-            nll[k] += __shfl_xor_sync(0xFFFFFFFFu, nll[k], 8);
-            nll[k] += __shfl_xor_sync(0xFFFFFFFFu, nll[k], 16);
-        }
-        constexpr int NV = (KS < 8) ? 2 * KS + 2 : 16;   // values per lane; KS == 8 has no spare slot: nll rides separately
-        if (KS < 8) { val[2 * KS] = nll[0]; val[2 * KS + 1] = nll[1]; }
-        if (cw >= kRedWarps) {
-#pragma unroll
-            for (int k = 0; k < NV; ++k) red[((cw - kRedWarps) * 16 + k) * 32 + lane] = val[k];
-            if (KS == 8 && g == 0) { gred[128 + (cw - kRedWarps) * 8 + 2 * t] = nll[0]; gred[128 + (cw - kRedWarps) * 8 + 2 * t + 1] = nll[1]; }
-        }
-        bar_sync<kBarCons, kConsThreads>();
-        if (cw + kRedWarps < kConsWarps) {
-#pragma unroll
-            for (int k = 0; k < NV; ++k) val[k] += red[(cw * 16 + k) * 32 + lane];
-            if (KS == 8) { nll[0] += gred[128 + cw * 8 + 2 * t]; nll[1] += gred[128 + cw * 8 + 2 * t + 1]; }
-        }
-        bar_sync<kBarCons, kConsThreads>();
-        if (cw < kRedWarps) {
-#pragma unroll
-            for (int k = 0; k < NV; ++k) red[(cw * 16 + k) * 32 + lane] = val[k];
-            if (KS == 8 && g == 0) { gred[128 + cw * 8 + 2 * t] = nll[0]; gred[128 + cw * 8 + 2 * t + 1] = nll[1]; }
-        }
-        bar_sync<kBarCons, kConsThreads>();
-        for (int o = ctid; o < kStreamCT * 65; o += kConsThreads) {
-            const int c = o / 65, d = o - c * 65;
-            float a = 0.0f;
-            if (d < 8 * KS) {                    // (chain c, column d) lives in lane (g = c, t = n >> 1), value 2 nt + (n & 1)
-                int nt, n;
-                if (ODD && d >= 16 * NCH) { nt = KS - 1; n = d - 16 * NCH; }
-                else { nt = 2 * (d >> 4) + (d & 1); n = (d & 15) >> 1; }
-                const int src = (2 * nt + (n & 1)) * 32 + (c << 2) + (n >> 1);
-#pragma unroll
-                for (int w = 0; w < kRedWarps; ++w) a += red[w * 16 * 32 + src];
-            } else if (d == 64) {                // nll of chain c = 2t + e: lane t, value 2 KS + e
-                if (KS < 8) {
-                    const int src = (2 * KS + (c & 1)) * 32 + (c >> 1);
-#pragma unroll
-                    for (int w = 0; w < kRedWarps; ++w) a += red[w * 16 * 32 + src];
-                } else {
-#pragma unroll
-                    for (int w = 0; w < kRedWarps; ++w) a += gred[128 + w * 8 + c];
-                }
+            for (int nt = 0; nt < 8; ++nt) {
+                val[2 * nt] = (nt < KS) ? gacc[nt < KS ? nt : 0][0] + gacc[nt < KS ? nt : 0][2] : 0.0f;
+                val[2 * nt + 1] = (nt < KS) ? gacc[nt < KS ? nt : 0][1] + gacc[nt < KS ? nt : 0][3] : 0.0f;
             }
-            __stcg(p.partial + ((size_t)cta * kStreamCT + c) * kGStride + d, a);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                nll[k] += __shfl_xor_sync(0xFFFFFFFFu, nll[k], 4);
+                nll[k] += __shfl_xor_sync(0xFFFFFFFFu, nll[k], 8);
+                nll[k] += __shfl_xor_sync(0xFFFFFFFFu, nll[k], 16);
+            }
+            float* scr = my_tiles + (size_t)red_slot * SLOT_FLOATS;      // >= 18 * 32 floats in every configuration
+#pragma unroll
+            for (int k = 0; k < 16; ++k) scr[k * 32 + lane] = val[k];
+            scr[16 * 32 + lane] = nll[0]; scr[17 * 32 + lane] = nll[1];
+            if (lane == 0) flags[16 + cw] = red_slot;
         }
-        bar_sync<kBarCons, kConsThreads>();          // orders every thread's partial stores before the release below
-        if (ctid == 0) { red_release_add(&sy->arrive, 1u); B2_DBG_LAP(2); }
+        bar_sync<kBarCons, kConsThreads>();
+        {
+            const uint32_t tag = pass + 1u;
+            for (int o = ctid; o < kStreamCT * 65; o += kConsThreads) {
+                const int c = o / 65, d = o - c * 65;
+                int src = -1;
+                if (d < 8 * KS) {                // (chain c, column d) lives in lane (g = c, t = n >> 1), value 2 nt + (n & 1)
+                    int nt, n;
+                    if (ODD && d >= 16 * NCH) { nt = KS - 1; n = d - 16 * NCH; }
+                    else { nt = 2 * (d >> 4) + (d & 1); n = (d & 15) >> 1; }
+                    src = (2 * nt + (n & 1)) * 32 + (c << 2) + (n >> 1);
+                } else if (d == 64) {            // nll of chain c = 2t + e: lane t (g = 0), value 16 + e
+                    src = (16 + (c & 1)) * 32 + (c >> 1);
+                }
+                float a = 0.0f;
+                if (src >= 0) {
+#pragma unroll
+                    for (int w = 0; w < kConsWarps; ++w) a += tiles[((size_t)w * nst + flags[16 + w]) * SLOT_FLOATS + src];
+                }
+                __stcg(p.partial + ((size_t)cta * kStreamCT + c) * kGStride + d, make_float2(a, __uint_as_float(tag)));
+            }
+        }
+        bar_sync<kBarCons, kConsThreads>();          // every scratch slot has been read: refill them
+        if (lane == 0 && red_tile >= 0 && p.dbg_sweep != 2) issue(red_slot, red_tile);
+        if (ctid == 0) { B2_DBG_LAP(2); B2_TRACE(0, 4); }
 
-        // ---- chain owner: sum the partials of all CTAs in fixed order, hand over to the tick warp
+        // ---- chain owner: poll the partials of all CTAs (tags ride in the data), sum them in fixed order,
+        //      hand over to the tick warp
         if (is_tick) {
-            if (ctid == 0) {
-                const bool ok = spin_ge(&sy->arrive, (unsigned)G * (pass + 1u), sy, p.spin_limit);
-                flags[3] = ok ? 1 : 0;
-                B2_DBG_LAP(3);
-            }
-            bar_sync<kBarCons, kConsThreads>();
-            if (flags[3]) {
-                // kXSeg segments x 65 outputs; each thread adds its segment's CTAs in ascending order.
-                // All loads of a segment are issued together (independent, L2 latency overlapped), adds stay ordered.
-                const int o = ctid % 65, seg = ctid / 65;
-                if (seg < kXSeg) {
-                    float a = 0.0f;
-                    const int g0 = G * seg / kXSeg, g1 = G * (seg + 1) / kXSeg;
-                    const float* src = p.partial + (size_t)cta * kGStride + o;
-                    for (int gg = g0; gg < g1; gg += 24) {
-                        float v[24];
+            const uint32_t tag = pass + 1u;
+            const int o = ctid % 65, seg = ctid / 65;
+            if (seg < kXSeg) {
+                // kXSeg segments x 65 outputs; each thread adds its segment's CTAs in ascending order.  All loads of a
+                // batch are in flight together (L2 latency overlapped); stale entries are simply polled again.
+                float a = 0.0f;
+                const int g0 = G * seg / kXSeg, g1 = G * (seg + 1) / kXSeg;
+                const float2* src = p.partial + (size_t)cta * kGStride + o;
+                const long long t_w = clock64();
+                for (int gg = g0; gg < g1; gg += 24) {
+                    float2 v[24];
+                    while (true) {
+                        bool ok = true;
 #pragma unroll
-                        for (int k = 0; k < 24; ++k)
-                            v[k] = (gg + k < g1) ? __ldcg(src + (size_t)(gg + k) * (kStreamCT * kGStride)) : 0.0f;
-#pragma unroll
-                        for (int k = 0; k < 24; ++k) a += v[k];
+                        for (int k = 0; k < 24; ++k) {
+                            if (gg + k < g1) {
+                                v[k] = ld_volatile_v2(src + (size_t)(gg + k) * (kStreamCT * kGStride));
+                                ok = ok && (__float_as_uint(v[k].y) == tag);
+                            } else v[k] = make_float2(0.0f, 0.0f);
+                        }
+                        if (ok) break;
+                        if (ld_acquire(&sy->abort_flag)) break;
+                        if (clock64() - t_w > p.spin_limit) { atomicCAS(&sy->abort_flag, 0u, 3u); break; }
                     }
-                    xred[seg * kGStride + o] = a;
+#pragma unroll
+                    for (int k = 0; k < 24; ++k) a += v[k].x;
                 }
+                xred[seg * kGStride + o] = a;
             }
             __threadfence_block();
-            bar_arrive<kBarTick, kTopThreads>();     // tick warp takes over; consumers go wait for the next beta
-            if (ctid == 0) B2_DBG_LAP(4);
+            bar_arrive<kBarTick, kStreamThreads>();  // tick warp takes over; consumers go wait for the next beta
+            if (ctid == 0) { B2_DBG_LAP(4); B2_TRACE(0, 5); }
         }
         ++pass;
     }
 
     // ---- shutdown: drain this warp's outstanding copies, write the chain state back
+    if (ctid == 0) B2_TRACE(0, 6);
     if (n_mine > 0 && p.dbg_sweep != 2)
         for (int s = 0; s < nst; ++s) {
-            mbar_wait(&my_full[slot], parity);
+            mbar_wait_bounded(&my_full[slot], parity, p.spin_limit, &sy->abort_flag);
             if (++slot == nst) { slot = 0; parity ^= 1u; }
         }
-    bar_sync<kBarCons, kConsThreads>();
+    if (ctid == 0) B2_TRACE(0, 7);
+    __syncthreads();                                 // tick warp included: the chain vectors are final
+    if (ctid == 0) B2_TRACE(0, 8);
     if (is_tick && p.vecs_in_smem && p.mode == 0) {
-        // the tick warp left the loop through the same top barrier, so the vectors are final
         for (int i = ctid; i < V_COUNT * p.Dp; i += kConsThreads) {
             const int f = i / p.Dp, d = i - f * p.Dp;
             p.vecs[((size_t)f * p.C + cta) * p.Dp + d] = cvecs[i];

@@ -38,6 +38,7 @@ enum VecField {
     V_ZL, V_RL, V_GL, V_ZR, V_RR, V_GR, V_ZP, V_GP, V_RSUM,
     V_ZS, V_RS, V_GS, V_ZPS, V_GPS, V_RSUMS,
     V_R0,                               // momentum at the start of the transition (HMC / heuristic)
+    V_EPS,                              // look-ahead: unit normal draws of the next transition's momentum (prefetch())
     V_CKPT_R,                           // kMaxDepthAlloc rows
     V_CKPT_RSUM = V_CKPT_R + kMaxDepthAlloc,
     V_COUNT = V_CKPT_RSUM + kMaxDepthAlloc
@@ -70,6 +71,17 @@ struct ChainCtl {
     // output cursor + totals
     int32_t n_collected; int32_t init_failed;
     unsigned long long total_leapfrogs;
+    // PRNG look-ahead (Tick::prefetch): values that depend only on keys, each tagged with the key it was
+    // derived from; a consumer uses an entry only when its tag equals the key it is about to expand, so a
+    // stale or missing entry can never change a result -- it only costs the recomputation.
+    uint32_t pre_mask;                                           // populated entries (bits below)
+    uint32_t pl_from[2], pl_ksub[2]; float pl_u;                 // bit 0: on_leaf, from k_sub
+    uint32_t pf_from[2]; float pf_u;                             // bit 1: finish_doubling, from k_fin
+    uint32_t pd_from[2][2], pd_kloop[2][2], pd_ksub[2][2], pd_kfin[2][2]; int32_t pd_right[2];   // bits 2, 3: begin_doubling,
+                                                                 // from k_loop ([0] this tree, [1] first doubling of the next transition)
+    uint32_t pt_from[2], pt_keynext[2], pt_ktr[2];               // bit 4: begin_transition, from key (+ V_EPS)
+    uint32_t pw_from[2], pw_next[2], pw_kss[2];                  // bit 5: adapt_update, from wa_key
+    uint32_t pre_hit[4], pre_miss[4];                            // statistics: leaf, doubling, transition, adaptation
 };
 
 struct TickCfg {
@@ -98,6 +110,7 @@ struct ChainVecs {
 
 B2_HD Key mk(const uint32_t* p) { Key k; k.a = p[0]; k.b = p[1]; return k; }
 B2_HD void st(uint32_t* p, Key k) { p[0] = k.a; p[1] = k.b; }
+B2_HD bool key_is(const uint32_t* p, Key k) { return p[0] == k.a && p[1] == k.b; }
 B2_HD float clip_max1(float p) { return (p > 1.0f) ? 1.0f : p; }      // jnp.clip(p, None, 1): NaN kept
 
 B2_HD float kinetic(int D, const float* imm, const float* r) {
@@ -244,10 +257,18 @@ struct Tick {
     B2_HD void begin_transition() {
         if (c.i >= cfg.total_iters) { c.phase = PH_DONE; return; }
         const Key key = mk(c.key);
-        const Key k_mom = split_at(key, 1), k_tr = split_at(key, 2);
-        st(c.key_next, split_at(key, 0));
+        Key k_tr;
         float* r = v(V_R0);
-        draw_momentum(k_mom, r);
+        if ((c.pre_mask & 16u) && key_is(c.pt_from, key)) {          // looked ahead: same splits, same normals
+            st(c.key_next, mk(c.pt_keynext)); k_tr = mk(c.pt_ktr);
+            const float* sm = v(V_SQRTM); const float* en = v(V_EPS);
+            B2_FOR_D(d, cfg.D) r[d] = sm[d] * en[d]; c.pre_hit[2] += 1u;
+        } else { c.pre_miss[2] += 1u;
+            const Key k_mom = split_at(key, 1);
+            k_tr = split_at(key, 2);
+            st(c.key_next, split_at(key, 0));
+            draw_momentum(k_mom, r);
+        }
         c.eps = c.step_size;
         c.energy0 = c.pe + kinetic(cfg.D, v(V_IMM), r);
         if (cfg.algo == 1) { hmc_begin(k_tr); return; }
@@ -269,10 +290,18 @@ struct Tick {
     // one iteration of build_tree's while loop up to the first leapfrog (hmc_util.py:1159-1162, :920)
     B2_HD void begin_doubling() {
         const Key k = mk(c.k_loop);
-        const Key k_dir = split_at(k, 1), k_dbl = split_at(k, 2);
-        st(c.k_loop, split_at(k, 0));
-        c.going_right = (uniform01_at(k_dir, 0) < 0.5f) ? 1 : 0;
-        st(c.k_sub, split_at(k_dbl, 0)); st(c.k_fin, split_at(k_dbl, 1));
+        if ((c.pre_mask & 4u) && key_is(c.pd_from[0], k)) {          // looked ahead (static indices: ChainCtl stays in registers)
+            st(c.k_loop, mk(c.pd_kloop[0])); c.going_right = c.pd_right[0];
+            st(c.k_sub, mk(c.pd_ksub[0])); st(c.k_fin, mk(c.pd_kfin[0])); c.pre_hit[1] += 1u;
+        } else if ((c.pre_mask & 8u) && key_is(c.pd_from[1], k)) {
+            st(c.k_loop, mk(c.pd_kloop[1])); c.going_right = c.pd_right[1];
+            st(c.k_sub, mk(c.pd_ksub[1])); st(c.k_fin, mk(c.pd_kfin[1])); c.pre_hit[1] += 1u;
+        } else { c.pre_miss[1] += 1u;
+            const Key k_dir = split_at(k, 1), k_dbl = split_at(k, 2);
+            st(c.k_loop, split_at(k, 0));
+            c.going_right = (uniform01_at(k_dir, 0) < 0.5f) ? 1 : 0;
+            st(c.k_sub, split_at(k_dbl, 0)); st(c.k_fin, split_at(k_dbl, 1));
+        }
         c.n_sub = 0; c.sub_div = 0; c.sub_weight = 0.0f; c.sub_sum_acc = 0.0f;
         const float e = c.going_right ? c.eps : -c.eps;
         if (c.going_right) leap_begin(cfg.D, e, v(V_IMM), v(V_ZR), v(V_RR), v(V_GR), v(V_ZS), v(V_RS));
@@ -297,7 +326,9 @@ struct Tick {
         const int leaf_div = (delta > 1000.0f) ? 1 : 0;
         const float leaf_acc = clip_max1(d_exp(-delta));
         const Key ks = mk(c.k_sub);
-        const Key k_leaf = split_at(ks, 1); st(c.k_sub, split_at(ks, 0));
+        float u_leaf;                                              // uniform01(split(k_sub)[1]), the proposal draw of this leaf
+        if ((c.pre_mask & 1u) && key_is(c.pl_from, ks)) { st(c.k_sub, mk(c.pl_ksub)); u_leaf = c.pl_u; c.pre_hit[0] += 1u; }
+        else { c.pre_miss[0] += 1u; const Key k_leaf = split_at(ks, 1); st(c.k_sub, split_at(ks, 0)); u_leaf = uniform01_at(k_leaf, 0); }
         const int leaf_idx = c.n_sub;
         float *zps = v(V_ZPS), *gps = v(V_GPS), *rsum_s = v(V_RSUMS);
         if (leaf_idx == 0) {
@@ -306,7 +337,7 @@ struct Tick {
             c.sub_weight = leaf_w; c.sub_sum_acc = leaf_acc;
         } else {                                                   // _combine_tree, uniform kernel
             const float p = d_expit(leaf_w - c.sub_weight);
-            const bool take = uniform01_at(k_leaf, 0) < p;
+            const bool take = u_leaf < p;
             if (take) {
                 B2_FOR_D(d, Dn) { zps[d] = zs[d]; gps[d] = gs[d]; }
                 c.sub_prop_pe = u; c.sub_prop_energy = energy_new;
@@ -354,7 +385,8 @@ struct Tick {
         float p = clip_max1(d_exp(c.sub_weight - c.weight));
         if (sub_turning || c.sub_div) p = 0.0f;
         const bool turning = sub_turning || is_turning(Dn, v(V_IMM), v(V_RL), v(V_RR), rsum);
-        const bool take = uniform01_at(mk(c.k_fin), 0) < p;
+        const float u_fin = ((c.pre_mask & 2u) && key_is(c.pf_from, mk(c.k_fin))) ? c.pf_u : uniform01_at(mk(c.k_fin), 0);
+        const bool take = u_fin < p;
         if (take) {
             copy(V_ZP, V_ZPS); copy(V_GP, V_GPS);
             c.prop_pe = c.sub_prop_pe; c.prop_energy = c.sub_prop_energy;
@@ -451,7 +483,9 @@ struct Tick {
     // pending and begin_transition will be called from heur_done()).
     B2_HD bool adapt_update(int t, float accept_prob) {
         const Key wk = mk(c.wa_key);
-        const Key k_ss = split_at(wk, 1); st(c.wa_key, split_at(wk, 0));
+        Key k_ss;
+        if ((c.pre_mask & 32u) && key_is(c.pw_from, wk)) { k_ss = mk(c.pw_kss); st(c.wa_key, mk(c.pw_next)); }
+        else { k_ss = split_at(wk, 1); st(c.wa_key, split_at(wk, 0)); }
         if (cfg.adapt_step) {
             // dual_averaging.update_fn (hmc_util.py:113-128), t0 = 10, kappa = 0.75, gamma = 0.05
             const float g = cfg.target_accept - accept_prob;
@@ -506,6 +540,44 @@ struct Tick {
             da_reinit(d_log(10.0f) + d_log(c.step_size));
         }
         return false;
+    }
+
+    // ---------------------------------------------------------------- PRNG look-ahead
+    // Everything the next advance() may draw from the PRNG depends only on keys that are already known while
+    // the gradient is still being computed.  prefetch() derives those values ahead of time (the streaming
+    // engine calls it while the grid sweeps X); advance() picks them up through the key tags.  Results are
+    // identical with or without it (tests/hostsim never calls it, the GPU parity tests always do).
+    template <int e> B2_HD void prefetch_doubling(Key k) {
+        if ((c.pre_mask & (4u << e)) && key_is(c.pd_from[e], k)) return;
+        const Key k_dir = split_at(k, 1), k_dbl = split_at(k, 2);
+        st(c.pd_kloop[e], split_at(k, 0));
+        c.pd_right[e] = (uniform01_at(k_dir, 0) < 0.5f) ? 1 : 0;
+        st(c.pd_ksub[e], split_at(k_dbl, 0)); st(c.pd_kfin[e], split_at(k_dbl, 1));
+        st(c.pd_from[e], k); c.pre_mask |= (4u << e);
+    }
+    B2_HD void prefetch() {
+        if (c.phase != PH_LEAF) return;
+        { const Key ks = mk(c.k_sub);                               // the leaf in flight
+          if (!((c.pre_mask & 1u) && key_is(c.pl_from, ks))) {
+              c.pl_u = uniform01_at(split_at(ks, 1), 0); st(c.pl_ksub, split_at(ks, 0)); st(c.pl_from, ks); c.pre_mask |= 1u;
+          } }
+        { const Key kf = mk(c.k_fin);                               // end of this doubling
+          if (!((c.pre_mask & 2u) && key_is(c.pf_from, kf))) { c.pf_u = uniform01_at(kf, 0); st(c.pf_from, kf); c.pre_mask |= 2u; } }
+        prefetch_doubling<0>(mk(c.k_loop));                         // the next doubling of this tree
+        { const Key key = mk(c.key_next);                           // the next transition
+          if (!((c.pre_mask & 16u) && key_is(c.pt_from, key))) {
+              const Key k_mom = split_at(key, 1), k_tr = split_at(key, 2);
+              st(c.pt_keynext, split_at(key, 0)); st(c.pt_ktr, k_tr);
+              const Key km = cfg.model_built ? split_at(k_mom, 0) : k_mom;
+              float* en = v(V_EPS);
+              B2_FOR_D(d, cfg.D) en[d] = normal_at(km, (uint32_t)d);
+              st(c.pt_from, key); c.pre_mask |= 16u;
+          }
+          prefetch_doubling<1>(mk(c.pt_ktr)); }
+        { const Key wk = mk(c.wa_key);                              // warm-up adaptation key
+          if (!((c.pre_mask & 32u) && key_is(c.pw_from, wk))) {
+              st(c.pw_kss, split_at(wk, 1)); st(c.pw_next, split_at(wk, 0)); st(c.pw_from, wk); c.pre_mask |= 32u;
+          } }
     }
 
     // ---------------------------------------------------------------- dispatcher

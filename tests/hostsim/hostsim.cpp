@@ -17,7 +17,7 @@ struct HostSim {
     B200NutsConfig cfg; FamilySpec fam; SiteLayout sites; TickCfg tick;
     int C, D;
     std::vector<ChainCtl> ctl; std::vector<float> vecs, gtmp, scratch, ylgam;
-    std::string err; bool inited = false;
+    std::string err; bool inited = false; bool lookahead = false;
     ChainVecs cv(int chain) { ChainVecs v; v.base = vecs.data() + (size_t)chain * D; v.field_stride = C * D; return v; }
 };
 
@@ -45,6 +45,8 @@ int hostsim_create(const B200NutsConfig* cfg, HostSim** out) {
 }
 
 void hostsim_destroy(HostSim* h) { delete h; }
+// run Tick::prefetch() before every gradient, like the streaming engine does while it sweeps X
+void hostsim_set_lookahead(HostSim* h, int on) { h->lookahead = on != 0; }
 int hostsim_dim(HostSim* h) { return h->D; }
 
 static void eval(HostSim* h, int chain, potential_cb cb, void* user, float& u) {
@@ -81,6 +83,7 @@ int hostsim_run(HostSim* h, const B200NutsRun* run, potential_cb cb, void* user)
         if (h->ctl[c].phase == PH_DONE && !h->ctl[c].init_failed) t.begin_transition();
         while (h->ctl[c].phase != PH_DONE) {
             float u;
+            if (h->lookahead) t.prefetch();
             eval(h, c, cb, user, u);
             t.advance(u, h->gtmp.data() + (size_t)c * h->D);
         }

@@ -33,6 +33,7 @@ def lib():
         _lib.hostsim_create.argtypes = [C.POINTER(_capi.Config), C.POINTER(C.c_void_p)]
         _lib.hostsim_destroy.argtypes = [C.c_void_p]
         _lib.hostsim_dim.argtypes = [C.c_void_p]
+        _lib.hostsim_set_lookahead.argtypes = [C.c_void_p, C.c_int]
         _lib.hostsim_init.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _lib.hostsim_run.argtypes = [C.c_void_p, C.POINTER(_capi.Run), CB, C.c_void_p]
         _lib.hostsim_get_state.argtypes = [C.c_void_p] * 6
@@ -64,6 +65,10 @@ class HostSim:
         if getattr(self, "h", None):
             lib().hostsim_destroy(self.h)
             self.h = None
+
+    def set_lookahead(self, on=True):
+        """Run Tick::prefetch() (PRNG look-ahead) before every gradient, as the streaming engine does."""
+        lib().hostsim_set_lookahead(self.h, 1 if on else 0)
 
     def init(self, keys, num_warmup, z0=None):
         keys = np.ascontiguousarray(keys, np.uint32).reshape(self.C, 2)

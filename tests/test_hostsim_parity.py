@@ -175,3 +175,20 @@ def test_host_build_of_family_potentials_matches_oracle():
             u64, g64 = fam.potential64(z[c].astype(np.float64))
             np.testing.assert_allclose(U[c], u64, rtol=1e-5, err_msg=fam.name)
             np.testing.assert_allclose(g[c], g64, rtol=1e-5, atol=1e-5 * np.abs(g64).max(), err_msg=fam.name)
+
+
+@pytest.mark.parametrize("heuristic", [0, 1])
+def test_prng_lookahead_changes_nothing(heuristic):
+    """Tick::prefetch (the PRNG look-ahead the streaming engine runs while it sweeps X) must be invisible:
+    same samples, same keys, same adaptation, bit for bit, against the oracle."""
+    fam = families.EightSchools(S8, Y8)
+    keys = prng.split(prng.key(11), 2)
+    sim = hs.HostSim(_eight_schools_cfg(2, find_heuristic_step_size=heuristic, max_tree_depth_warmup=5, max_tree_depth=7))
+    sim.set_lookahead(True)
+    sim.init(keys, 160)
+    out = sim.run(200, 160, potential=lambda c, z: fam.potential_and_grad(z))
+    last = _compare(out, fam, keys, 160, 40, find_heuristic_step_size=bool(heuristic), max_tree_depth=(5, 7))
+    st, z, g, imm, sm = sim.state()
+    np.testing.assert_array_equal(np.array(st[1].rng_key), last.rng_key)
+    np.testing.assert_array_equal(np.array(st[1].adapt_rng_key), last.adapt_state.rng_key)
+    np.testing.assert_array_equal(imm[1], last.adapt_state.inverse_mass_matrix)
