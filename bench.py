@@ -240,7 +240,12 @@ def run_b200(args):
 
     # ---- reduce over ranks
     stats = torch.tensor([ms, float(leap), e2e_ms, float(e2e_leap), float(diverging)], dtype=torch.float64, device=dev)
+    per_rank = [{"rank": rank, "ms": ms, "passes": int(passes), "grad_evals": leap,
+                 "step_size": [round(float(s_.step_size), 5) for s_ in st]}]
     if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, per_rank[0])
+        per_rank = gathered
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone()
@@ -297,7 +302,7 @@ def run_b200(args):
                      "traffic": traffic, "peak_source": peak_src, "kernel": "stream_engine_kernel<7>",
                      "algorithmic_bytes_per_pass": BYTES_PER_PASS, "passes_per_launch": passes / max(launches // 2, 1),
                      "us_per_pass": ms * 1e3 / max(passes, 1)},
-        "cpu_baseline": cpu, "clocks": clk,
+        "cpu_baseline": cpu, "clocks": clk, "per_rank": per_rank,
     }
     print(json.dumps(line))
     if world > 1:

@@ -78,8 +78,10 @@ typedef struct B200NutsConfig {
                                   momentum_generator splits its key once more (hmc.py:93-99) */
     int32_t regime;            /* B200NUTS_REGIME_* */
     /* --- row sharding (data-parallel likelihood, BASELINE config 5) --- */
-    int32_t shard_rank, shard_count;   /* 0,1 when not sharded */
-    void* nccl_comm;           /* ncclComm_t for the per-gradient all-reduce, or NULL */
+    int32_t shard_rank, shard_count;   /* 0,1 when not sharded; <= B200NUTS_MAX_SHARDS */
+    void* nccl_comm;           /* reserved (NULL): the per-gradient all-reduce runs inside the kernel over NVLink peer
+                                  stores in fixed rank order (see b200nuts_shard_connect), not through NCCL */
+    int64_t n_rows_global;     /* row-sharded handles: rows of the whole dataset (0 => n_rows) */
 } B200NutsConfig;
 
 /* Collection window of one run = fori_collect(lower, upper, thinning) (numpyro/util.py:321-454). */
@@ -125,6 +127,20 @@ int b200nuts_get_state(B200Nuts* h, B200NutsChainState* states, float* z, float*
 int b200nuts_set_state(B200Nuts* h, const B200NutsChainState* states, const float* z, const float* z_grad,
                        const float* inv_mass, const float* wf_mean, const float* wf_m2, int32_t num_warmup,
                        void* stream);
+
+/* Row-sharded handles (BASELINE config 5; the reference analogue is a likelihood over GSPMD-sharded model
+ * arguments, numpyro/infer/mcmc.py:240-266, where XLA inserts the all-reduce of log-density and gradient).
+ * Every rank creates a streaming-regime handle over ITS rows with the same chains, keys and options
+ * (shard_rank / shard_count / n_rows_global set).  Each handle owns a small mailbox in device memory; after
+ * b200nuts_shard_connect every rank stores its per-chain likelihood sums {value, tag} into every rank's
+ * mailbox once per gradient and adds the shard_count contributions in rank order, so all ranks see
+ * bit-identical (U, grad) and their replicated chains take identical decisions.  Priors are added after the sum.
+ * export/connect are host calls: exchange the blobs with any host-side transport (torch.distributed
+ * all_gather in numpyro_b200/engine.py).  Ranks may be processes (CUDA IPC) or threads of one process. */
+#define B200NUTS_MAX_SHARDS 16
+#define B200NUTS_SHARD_HANDLE_BYTES 128
+int b200nuts_shard_export(B200Nuts* h, void* blob /* B200NUTS_SHARD_HANDLE_BYTES */);
+int b200nuts_shard_connect(B200Nuts* h, const void* blobs /* [shard_count][B200NUTS_SHARD_HANDLE_BYTES], rank order */);
 
 /* Parity hooks (device pointers). z,g: [num_chains][D]; U: [num_chains]. */
 int b200nuts_potential_and_grad(B200Nuts* h, const float* z, float* U, float* g, void* stream);

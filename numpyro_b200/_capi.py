@@ -21,6 +21,7 @@ LIK_BERNOULLI_LOGIT, LIK_POISSON_LOG, LIK_NORMAL = 0, 1, 2
 SCALE_NONE, SCALE_HALFCAUCHY, SCALE_EXPONENTIAL = 0, 1, 2
 ALGO_NUTS, ALGO_HMC = 0, 1
 REGIME_AUTO, REGIME_WARP, REGIME_STREAM, REGIME_GEMM = 0, 1, 2, 3
+MAX_SHARDS, SHARD_HANDLE_BYTES = 16, 128
 
 
 class Config(C.Structure):
@@ -37,6 +38,7 @@ class Config(C.Structure):
         ("hmc_num_steps", i32), ("trajectory_length", f32), ("init_radius", f32),
         ("model_built", i32), ("regime", i32),
         ("shard_rank", i32), ("shard_count", i32), ("nccl_comm", vp),
+        ("n_rows_global", i64),
     ]
 
 
@@ -93,6 +95,8 @@ EXPORTS = {
     "b200nuts_run": (C.c_int, [vp, C.POINTER(Run), vp]),
     "b200nuts_get_state": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "b200nuts_set_state": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i32, vp]),
+    "b200nuts_shard_export": (C.c_int, [vp, vp]),
+    "b200nuts_shard_connect": (C.c_int, [vp, vp]),
     "b200nuts_potential_and_grad": (C.c_int, [vp, vp, vp, vp, vp]),
     "b200nuts_leapfrog": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i32, vp]),
     "b200nuts_constrain": (C.c_int, [vp, vp, i64, vp, vp]),

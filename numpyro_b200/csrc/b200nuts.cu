@@ -13,6 +13,7 @@
 #include <mutex>
 #include <chrono>
 #include <thread>
+#include <unistd.h>
 #include "engine.cuh"
 #include "stream_engine.cuh"
 
@@ -32,6 +33,10 @@ struct B200Nuts {
     long long launches = 0, passes = 0;
     unsigned long long dbg[16] = {0};
     unsigned int* trace_host = nullptr; unsigned int* trace_dev = nullptr;     // B200NUTS_TRACE: host-mapped progress words
+    // row sharding
+    int shard_rank = 0, shard_count = 1; bool shards_connected = false; unsigned int epoch = 0;
+    float2* mail = nullptr; float2* mail_peer[kMaxShards] = {nullptr}; bool mail_ipc[kMaxShards] = {false};
+    long long n_rows_global = 0; float nll_local_const = 0.0f;
     std::string err;
     std::mutex mu;
 };
@@ -212,6 +217,14 @@ static int stream_launch(B200Nuts* h, int mode, const OutBufs& out, const float*
     }
     if (h->trace_host) memset(h->trace_host, 0, sizeof(unsigned int) * 32 * h->grid);
     p.trace = h->trace_dev;
+    p.shard_rank = h->shard_rank; p.shard_count = h->shard_count;
+    if (h->shard_count > 1) {
+        if (!h->shards_connected) { h->err = "row-sharded handle: call b200nuts_shard_connect first"; return B200NUTS_ESTATE; }
+        h->epoch += 1u; p.epoch = h->epoch & 0xFFu;        // every rank makes the same sequence of launches
+        for (int q = 0; q < h->shard_count; ++q) p.mail[q] = h->mail_peer[q];
+        p.fam.N = h->n_rows_global;                         // the priors / Normal-likelihood constants see the whole dataset
+        p.fam.nll_const = 0.0f; p.nll_local_const = h->nll_local_const;
+    }
     p.img = h->img; p.n_tiles = h->n_tiles; p.pad_rows = h->pad_rows;
     { const char* e = getenv("B200NUTS_DEBUG_SWEEP"); p.dbg_sweep = e ? atoi(e) : 0; }
     { const char* e = getenv("B200NUTS_DEBUG_WARPS"); p.dbg_warps = e ? atoi(e) : 1000; }
@@ -295,8 +308,9 @@ static int check_stream_abort(B200Nuts* h, cudaStream_t st) {
                     s.pre_hit[c][2], s.pre_miss[c][2]);
     }
     if (s.abort_flag) {
-        static const char* what[] = {"", "a tile copy never landed", "beta fetch timed out", "partial poll timed out"};
-        h->err = std::string("stream engine aborted: ") + (s.abort_flag < 4 ? what[s.abort_flag] : "?"); return B200NUTS_ECUDA;
+        static const char* what[] = {"", "a tile copy never landed", "beta fetch timed out", "partial poll timed out",
+                                     "a peer rank's likelihood sums never arrived (row-sharded exchange)"};
+        h->err = std::string("stream engine aborted: ") + (s.abort_flag < 5 ? what[s.abort_flag] : "?"); return B200NUTS_ECUDA;
     }
     return 0;
 }
@@ -326,6 +340,8 @@ void b200nuts_destroy(B200Nuts* h) {
     cudaFree(h->ctl); cudaFree(h->vecs); cudaFree(h->gtmp); cudaFree(h->scratch); cudaFree(h->keys);
     cudaFree(h->partial); cudaFree(h->beta); cudaFree(h->sync); cudaFree(h->img);
     if (h->trace_host) cudaFreeHost(h->trace_host);
+    for (int q = 0; q < kMaxShards; ++q) if (h->mail_ipc[q] && h->mail_peer[q]) cudaIpcCloseMemHandle(h->mail_peer[q]);
+    cudaFree(h->mail);
     delete h;
 }
 
@@ -339,7 +355,8 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
     B200Nuts* h = new B200Nuts();
     h->cfg = *cfg;
     std::string e = make_family(*cfg, h->fam, h->sites);
-    if (e.empty() && cfg->shard_count > 1) e = "row-sharded handles are not implemented yet";
+    if (e.empty() && (cfg->shard_count < 0 || cfg->shard_count > kMaxShards || (cfg->shard_count > 1 && (cfg->shard_rank < 0 || cfg->shard_rank >= cfg->shard_count))))
+        e = "shard_rank / shard_count out of range";
     if (!e.empty()) { g_create_err = e; delete h; return B200NUTS_EINVAL; }
     h->C = cfg->num_chains; h->D = h->fam.D; h->Dp = (h->D + 3) & ~3;
     make_tick_cfg(*cfg, h->fam, h->sites, 0, false, h->tick);
@@ -354,6 +371,12 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
         regime = (stream_ok && (long long)h->fam.N * h->fam.Dx >= (1LL << 20)) ? B200NUTS_REGIME_STREAM : B200NUTS_REGIME_WARP;
     if (regime == B200NUTS_REGIME_STREAM && !stream_ok) {
         g_create_err = "stream regime needs a GLM family with <= 8 chains and <= 64 columns"; delete h; return B200NUTS_EINVAL;
+    }
+    if (cfg->shard_count > 1) {
+        if (!stream_ok) { g_create_err = "row-sharded handles need the streaming regime (GLM, <= 8 chains, <= 64 columns)"; delete h; return B200NUTS_EINVAL; }
+        regime = B200NUTS_REGIME_STREAM;
+        h->shard_rank = cfg->shard_rank; h->shard_count = cfg->shard_count;
+        h->n_rows_global = cfg->n_rows_global > 0 ? cfg->n_rows_global : cfg->n_rows;
     }
     if (regime == B200NUTS_REGIME_GEMM) { g_create_err = "gemm regime is not implemented yet"; delete h; return B200NUTS_EINVAL; }
     h->regime = regime;
@@ -384,6 +407,8 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
     }
     if (regime == B200NUTS_REGIME_STREAM) {
         h->grid = h->num_sms;
+        // testing aid: a smaller grid lets two row-sharded handles run side by side on ONE device (tests/test_gpu_rowshard.py)
+        if (const char* e = getenv("B200NUTS_GRID")) { const int g = atoi(e); if (g >= h->C && g >= 1 && g < h->grid) h->grid = g; }
         int max_smem = 0;
         cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
         h->ks = stream_ks_for(h->fam.Dx);
@@ -406,6 +431,26 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
         if ((ce = cudaMalloc(&h->partial, sizeof(float2) * (size_t)h->grid * kStreamCT * kGStride)) != cudaSuccess) return fail("cudaMalloc partial", ce);
         if ((ce = cudaMalloc(&h->beta, sizeof(uint4) * kBetaCopies * kBetaWords)) != cudaSuccess) return fail("cudaMalloc beta", ce);
         if ((ce = cudaMalloc(&h->sync, sizeof(StreamSync))) != cudaSuccess) return fail("cudaMalloc sync", ce);
+        if (h->shard_count > 1) {
+            if ((ce = cudaMalloc(&h->mail, sizeof(float2) * kMailFloat2)) != cudaSuccess) return fail("cudaMalloc mailbox", ce);
+            cudaMemset(h->mail, 0, sizeof(float2) * kMailFloat2);
+            h->nll_local_const = h->fam.nll_const;
+        }
+    }
+    {   // Load every kernel this handle can launch NOW.  With lazy module loading the first launch of a function may need
+        // a context-wide synchronisation; a persistent kernel of another (row-sharded) handle that is waiting for this
+        // handle's contribution would then never finish.
+        cudaFuncAttributes fa;
+        const void* fns[] = {(const void*)k_chain_begin, (const void*)k_chain_resume, (const void*)k_warp_run, (const void*)k_potential_warp,
+                             (const void*)k_leap_pre, (const void*)k_leap_post, (const void*)k_constrain,
+                             regime == B200NUTS_REGIME_STREAM ? stream_kernel_for(h->ks, h->fam.likelihood) : nullptr};
+        for (const void* fn : fns)
+            if (fn && (ce = cudaFuncGetAttributes(&fa, fn)) != cudaSuccess) return fail("cudaFuncGetAttributes", ce);
+        if (regime == B200NUTS_REGIME_STREAM) {
+            const void* fn = stream_kernel_for(h->ks, h->fam.likelihood);
+            if (!fn) { g_create_err = "stream regime: no kernel instance for this shape"; b200nuts_destroy(h); return B200NUTS_EINVAL; }
+            if ((ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem)) != cudaSuccess) return fail("cudaFuncSetAttribute", ce);
+        }
     }
     if ((ce = cudaDeviceSynchronize()) != cudaSuccess) return fail("create", ce);
     *out = h;
@@ -501,6 +546,47 @@ int b200nuts_set_state(B200Nuts* h, const B200NutsChainState* states, const floa
     return 0;
 }
 
+// blob = { pid, device, raw device pointer, cudaIpcMemHandle_t }
+struct ShardBlob { long long pid; int device; int pad; unsigned long long ptr; cudaIpcMemHandle_t ipc; };
+static_assert(sizeof(ShardBlob) <= B200NUTS_SHARD_HANDLE_BYTES, "shard blob too large");
+
+int b200nuts_shard_export(B200Nuts* h, void* blob) {
+    if (!h || !blob) return B200NUTS_EINVAL;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->shard_count <= 1 || !h->mail) { h->err = "not a row-sharded handle"; return B200NUTS_ESTATE; }
+    ShardBlob b; memset(&b, 0, sizeof(b));
+    b.pid = (long long)getpid(); b.device = h->device; b.ptr = (unsigned long long)(uintptr_t)h->mail;
+    CK(cudaSetDevice(h->device));
+    CK(cudaIpcGetMemHandle(&b.ipc, h->mail));
+    memset(blob, 0, B200NUTS_SHARD_HANDLE_BYTES); memcpy(blob, &b, sizeof(b));
+    return 0;
+}
+
+int b200nuts_shard_connect(B200Nuts* h, const void* blobs) {
+    if (!h || !blobs) return B200NUTS_EINVAL;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->shard_count <= 1 || !h->mail) { h->err = "not a row-sharded handle"; return B200NUTS_ESTATE; }
+    CK(cudaSetDevice(h->device));
+    for (int q = 0; q < h->shard_count; ++q) {
+        ShardBlob b; memcpy(&b, (const unsigned char*)blobs + (size_t)q * B200NUTS_SHARD_HANDLE_BYTES, sizeof(b));
+        if (q == h->shard_rank) { h->mail_peer[q] = h->mail; continue; }
+        if (b.pid == (long long)getpid()) {                 // ranks are threads of one process: plain peer access
+            if (b.device != h->device) {
+                cudaError_t pe = cudaDeviceEnablePeerAccess(b.device, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) { h->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(pe); return B200NUTS_ECUDA; }
+                cudaGetLastError();
+            }
+            h->mail_peer[q] = (float2*)(uintptr_t)b.ptr;
+        } else {                                            // ranks are processes: CUDA IPC
+            void* ptr = nullptr;
+            CK(cudaIpcOpenMemHandle(&ptr, b.ipc, cudaIpcMemLazyEnablePeerAccess));
+            h->mail_peer[q] = (float2*)ptr; h->mail_ipc[q] = true;
+        }
+    }
+    h->shards_connected = true;
+    return 0;
+}
+
 int b200nuts_potential_and_grad(B200Nuts* h, const float* z, float* U, float* g, void* stream) {
     if (!h || !z || !U || !g) return B200NUTS_EINVAL;
     std::lock_guard<std::mutex> lk(h->mu);
@@ -512,7 +598,9 @@ int b200nuts_potential_and_grad(B200Nuts* h, const float* z, float* U, float* g,
         return 0;
     }
     OutBufs none; memset(&none, 0, sizeof(none));
-    return stream_launch(h, 1, none, z, U, g, st);
+    int rc = stream_launch(h, 1, none, z, U, g, st);
+    if (rc) return rc;
+    return check_stream_abort(h, st);       // a parity hook: synchronise and report a timed-out exchange instead of returning stale sums
 }
 
 int b200nuts_leapfrog(B200Nuts* h, const float* eps, const float* inv_mass, float* z, float* r, float* U, float* g,

@@ -69,6 +69,9 @@ constexpr int kBarBeta = 1, kBarCons = 2, kBarTick = 3;
 constexpr int kBetaCopies = 4;           // replicas of the published beta (CTA c fetches replica c mod 4)
 constexpr int kBetaWords = 8 * kStreamCT * 4;     // 16-byte words per replica: [k-step][chain][t]
 constexpr int kConsThreads = kConsWarps * 32, kTopThreads = kStreamThreads;
+constexpr int kMaxShards = 16;           // row-sharded handles: ranks that sweep disjoint rows of the same pass
+// mailbox of a row-sharded handle: [pass parity][chain][source rank][kGStride] {value, tag}
+constexpr size_t kMailFloat2 = (size_t)2 * kStreamCT * kMaxShards * kGStride;
 
 B2_HD constexpr int stream_pitch(int KS) { return (KS % 2 == 0) ? 8 * KS + 8 : 8 * KS; }     // 8 * odd
 // float offset of element (row r, column c) of a tile, r in [0, 16), c in [0, P)
@@ -106,6 +109,11 @@ struct StreamParams {
     int dbg_sweep;                       // timing experiments only: 1 = copies without compute, 2 = compute without copies
     int dbg_warps;                       // ... only the first dbg_warps consumer warps compute
     long long spin_limit;
+    // row sharding (config 5): this rank sweeps its own rows; per-chain likelihood sums are exchanged through the
+    // ranks' mailboxes (peer stores over NVLink) and added in rank order, identically on every rank
+    int shard_rank, shard_count; unsigned int epoch;      // epoch: launch number, part of the exchange tag
+    float2* mail[kMaxShards];            // mailbox of every rank ([shard_rank] = this rank's own)
+    float nll_local_const;               // added to this rank's nll before the exchange (poisson: local sum lgamma(y+1))
     unsigned int* trace;                 // debug only (B200NUTS_TRACE): host-mapped [grid][8] progress words, see B2_TRACE
     int no_prefetch;                     // debug only: skip the PRNG look-ahead
 };
@@ -129,7 +137,7 @@ B2_D bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 B2_D void mbar_wait(uint64_t* bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) {} }
 // bounded variant: gives up after `limit` clocks and raises *abort_flag (returns false)
-// (abort codes: 1 tile copy never landed, 2 beta fetch timed out, 3 partial poll timed out)
+// (abort codes: 1 tile copy never landed, 2 beta fetch timed out, 3 partial poll timed out, 4 a peer rank's sums never arrived)
 B2_D bool mbar_wait_bounded(uint64_t* bar, uint32_t parity, long long limit, unsigned int* abort_flag) {
     if (mbar_try_wait(bar, parity)) return true;
     const long long t0 = clock64();
@@ -151,6 +159,9 @@ B2_D uint4 ld_volatile_v4(const uint4* p) {
 }
 B2_D float2 ld_volatile_v2(const float2* p) {
     float2 v; asm volatile("ld.volatile.global.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory"); return v;
+}
+B2_D void st_sys_v2(float2* p, float2 v) {      // one 8-byte store, visible to peer GPUs (value and tag travel together)
+    asm volatile("st.volatile.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
 }
 B2_D unsigned int ld_acquire(const unsigned int* p) {
     unsigned int v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
@@ -461,7 +472,38 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                         if (k == 2) a64 = a;
                     }
                 }
-                const float nll = __shfl_sync(0xFFFFFFFFu, a64, 0) - pad_nll;
+                if (p.shard_count > 1) {
+                    // ---- all-reduce over the row shards: store this rank's sums into every rank's mailbox, then add the
+                    //      shard_count contributions of this chain in rank order (same order everywhere => identical bits)
+                    const uint32_t xtag = (p.epoch << 24) ^ (seq & 0xFFFFFFu);
+                    const size_t slot0 = (size_t)(seq & 1u) * kStreamCT * kMaxShards * kGStride + (size_t)cta * kMaxShards * kGStride;
+                    const long long t_x = clock64();
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int d = lane + 32 * k;
+                        if (d < 65) {
+                            float mine = gred[d];
+                            if (d == 64) mine = (mine - pad_nll) + p.nll_local_const;
+                            for (int q = 0; q < p.shard_count; ++q)
+                                st_sys_v2(p.mail[q] + slot0 + (size_t)p.shard_rank * kGStride + d, make_float2(mine, __uint_as_float(xtag)));
+                            float tot = 0.0f;
+                            const float2* box = p.mail[p.shard_rank] + slot0 + d;
+                            for (int sr = 0; sr < p.shard_count; ++sr) {
+                                float2 v;
+                                while (true) {
+                                    v = ld_volatile_v2(box + (size_t)sr * kGStride);
+                                    if (__float_as_uint(v.y) == xtag) break;
+                                    if (ld_acquire(&sy->abort_flag)) break;
+                                    if (clock64() - t_x > 16 * p.spin_limit) { atomicCAS(&sy->abort_flag, 0u, 4u); break; }
+                                }
+                                tot += v.x;
+                            }
+                            gred[d] = tot;
+                            if (k == 2) a64 = tot;
+                        }
+                    }
+                }
+                const float nll = __shfl_sync(0xFFFFFFFFu, a64, 0) - (p.shard_count > 1 ? 0.0f : pad_nll);
                 if (lane == 0) tlap[3] += (unsigned long long)(clock64() - t_a);
                 float* gz = xred + kXSeg * kGStride; // scratch for the gradient wrt z (<= Dp floats)
                 if (!chain_done) chain_done = stream_tick_step(p, tk, gred, gz, nll, cta, tdbg, pass);

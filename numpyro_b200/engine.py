@@ -55,6 +55,34 @@ class Engine:
         self.D = self.lib.b200nuts_dim(self.h)
         self.Dc = self.lib.b200nuts_constrained_dim(self.h)
         self.regime = self.lib.b200nuts_regime(self.h)
+        self.shard_rank, self.shard_count = int(c.shard_rank), int(c.shard_count)
+        self._shard_group = None
+
+    # ------------------------------------------------------------------ row-sharded handles (config 5)
+    def shard_blob(self) -> bytes:
+        """This rank's mailbox handle for :meth:`connect_shards` (b200nuts_shard_export)."""
+        buf = C.create_string_buffer(_capi.SHARD_HANDLE_BYTES)
+        self._check(self.lib.b200nuts_shard_export(self.h, buf), "b200nuts_shard_export")
+        return buf.raw
+
+    def connect_shards(self, blobs=None, group=None):
+        """Wire the per-gradient all-reduce of a row-sharded handle.  ``blobs``: the ranks' :meth:`shard_blob` in rank
+        order (ranks = threads of this process), or None to exchange them over ``torch.distributed`` (ranks = processes;
+        every later launch is then preceded by a barrier on ``group`` so that the ranks' kernels start together)."""
+        if blobs is None:
+            import torch.distributed as dist
+            blobs = [None] * dist.get_world_size(group)
+            dist.all_gather_object(blobs, self.shard_blob(), group=group)
+            self._shard_group = group if group is not None else dist.group.WORLD
+        if len(blobs) != self.shard_count:
+            raise EngineError(f"connect_shards: {len(blobs)} handles for shard_count={self.shard_count}")
+        self._check(self.lib.b200nuts_shard_connect(self.h, b"".join(blobs)), "b200nuts_shard_connect")
+
+    def _align_ranks(self):
+        if self._shard_group is not None:
+            import torch.distributed as dist
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self._shard_group)
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
@@ -101,6 +129,7 @@ class Engine:
                 raise ValueError(f"unknown field {f!r}")
             out[f] = t
             setattr(run, f, t.data_ptr() if S > 0 else None)
+        self._align_ranks()
         self._check(self.lib.b200nuts_run(self.h, C.byref(run), self._stream()), "b200nuts_run")
         return out
 
@@ -130,6 +159,7 @@ class Engine:
         z = torch.as_tensor(z, dtype=torch.float32).to(self.device).contiguous().view(self.C, self.D)
         U = torch.zeros(self.C, dtype=torch.float32, device=self.device)
         g = torch.zeros((self.C, self.D), dtype=torch.float32, device=self.device)
+        self._align_ranks()
         self._check(self.lib.b200nuts_potential_and_grad(self.h, _ptr(z), _ptr(U), _ptr(g), self._stream()),
                     "b200nuts_potential_and_grad")
         return U, g

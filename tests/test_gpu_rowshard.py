@@ -1,0 +1,150 @@
+"""Row-sharded handles (BASELINE config 5): every rank sweeps its own rows, the per-chain likelihood
+sums are all-reduced inside the kernel (peer stores into the ranks' mailboxes, added in rank order) and all ranks
+must see bit-identical (U, grad) and produce bit-identical chains.
+
+On a one-GPU box the two ranks are two threads that share the device (each handle takes half of the SMs through the
+B200NUTS_GRID testing aid); with >= 2 GPUs the same test also runs one rank per device, and a torchrun variant
+exercises the CUDA-IPC path (ranks = processes)."""
+import os
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+if not torch.cuda.is_available():
+    pytest.skip("needs a GPU", allow_module_level=True)
+
+from numpyro_b200 import _capi, engine as eng          # noqa: E402
+from oracle import chain, families, prng                # noqa: E402
+
+F = np.float32
+FIELDS = ("z", "num_steps", "accept_prob", "potential_energy", "diverging", "step_size")
+
+
+def _data(N, D, seed, lik="bernoulli"):
+    rng = np.random.default_rng(seed)
+    X = rng.normal(size=(N, D)).astype(F)
+    beta = rng.normal(size=D) * 0.3
+    if lik == "poisson":
+        X = (X * 0.3).astype(F)
+        y = rng.poisson(np.exp(np.clip(X @ beta, -3, 3))).astype(F)
+    else:
+        y = (rng.uniform(size=N) < 1 / (1 + np.exp(-X @ beta))).astype(F)
+    return X, y
+
+
+class Ranks:
+    """W row-sharded handles driven by W threads of this process."""
+
+    def __init__(self, X, y, C, cuts, devices, **cfg):
+        self.W = len(cuts) - 1
+        self.streams, self.engines = [], []
+        for r in range(self.W):
+            dev = torch.device("cuda", devices[r])
+            torch.cuda.set_device(dev)
+            e = eng.Engine(device=dev, family=_capi.FAMILY_GLM, num_chains=C, X=X[cuts[r]:cuts[r + 1]], y=y[cuts[r]:cuts[r + 1]],
+                           regime=_capi.REGIME_STREAM, shard_rank=r, shard_count=self.W, n_rows_global=X.shape[0], **cfg)
+            self.engines.append(e)
+            self.streams.append(torch.cuda.Stream(device=dev))
+        blobs = [e.shard_blob() for e in self.engines]
+        for e in self.engines:
+            e.connect_shards(blobs)
+
+    def each(self, fn):
+        out, err = [None] * self.W, []
+
+        def work(r):
+            try:
+                torch.cuda.set_device(self.engines[r].device)
+                with torch.cuda.stream(self.streams[r]):
+                    out[r] = fn(self.engines[r])
+                    self.streams[r].synchronize()
+            except Exception as ex:                      # noqa: BLE001
+                err.append(ex)
+        ts = [threading.Thread(target=work, args=(r,)) for r in range(self.W)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        if err:
+            raise err[0]
+        return out
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+
+
+def _layouts():
+    n = torch.cuda.device_count()
+    out = [pytest.param((0, 0), id="two-ranks-one-device")]
+    if n >= 2:
+        out.append(pytest.param((0, 1), id="two-devices"))
+    return out
+
+
+@pytest.fixture
+def half_grid(monkeypatch):
+    monkeypatch.setenv("B200NUTS_GRID", str(torch.cuda.get_device_properties(0).multi_processor_count // 2))
+    monkeypatch.setenv("B200NUTS_WATCHDOG_S", "60")
+
+
+@pytest.mark.parametrize("devices", _layouts())
+@pytest.mark.parametrize("lik", ["bernoulli", "poisson"])
+def test_sharded_potential_identical_on_all_ranks_and_equal_to_unsharded(devices, lik, half_grid):
+    N, D, C = 30011, 54, 5
+    X, y = _data(N, D, 3, lik)
+    kw = dict(likelihood=_capi.LIK_POISSON_LOG) if lik == "poisson" else {}
+    rk = Ranks(X, y, C, [0, 17003, N], devices, **kw)
+    rng = np.random.default_rng(0)
+    z = (rng.normal(size=(C, D)) * 0.3).astype(F)
+    res = rk.each(lambda e: tuple(t.cpu().numpy() for t in e.potential_and_grad(z)))
+    (U0, g0), (U1, g1) = res
+    assert np.array_equal(U0, U1) and np.array_equal(g0, g1), "ranks disagree: replicated chains would diverge"
+    fam = families.GLM(X, y, likelihood="poisson") if lik == "poisson" else families.logistic_regression(X, y)
+    for c in range(C):
+        u64, g64 = fam.potential64(z[c].astype(np.float64))
+        np.testing.assert_allclose(U0[c], u64, rtol=1e-5)
+        np.testing.assert_allclose(g0[c], g64, rtol=1e-5, atol=1e-5 * np.abs(g64).max())
+    # same bits again on a second launch (the exchange tags carry the launch epoch)
+    res2 = rk.each(lambda e: tuple(t.cpu().numpy() for t in e.potential_and_grad(z)))
+    assert np.array_equal(res2[0][0], U0) and np.array_equal(res2[1][1], g0)
+    rk.close()
+
+
+@pytest.mark.parametrize("devices", _layouts())
+def test_sharded_run_bit_identical_across_ranks_and_bit_exact_against_oracle(devices, half_grid):
+    N, D, C = 9000, 7, 3
+    X, y = _data(N, D, 4)
+    rk = Ranks(X, y, C, [0, 4000, N], devices, max_tree_depth_warmup=5, max_tree_depth=5)
+    keys = prng.split(prng.key(7), C)
+    rk.each(lambda e: e.init(keys, 40))
+    outs = rk.each(lambda e: {k: v.cpu().numpy() for k, v in e.run(60, 40, fields=FIELDS).items()})
+    for f in FIELDS:
+        assert np.array_equal(outs[0][f], outs[1][f]), f
+    fam = families.logistic_regression(X, y)
+
+    def device_potential(c):
+        def pot(zc):
+            zz = np.zeros((C, D), F)
+            zz[c] = zc
+            U, g = rk.each(lambda e: tuple(t.cpu().numpy() for t in e.potential_and_grad(zz)))[0]
+            return F(U[c]), g[c]
+        return pot
+    kern = chain.Kernel(device_potential(1), max_tree_depth=(5, 5))
+    res, _ = chain.run_chain(kern, fam, keys[1], 40, 20, fields=FIELDS)
+    for f in FIELDS:
+        assert np.array_equal(outs[0][f][1], res[f]), f
+    rk.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (ranks = processes, CUDA IPC)")
+def test_sharded_processes_over_cuda_ipc():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tests", "rowshard_worker.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "ROWSHARD_OK" in p.stdout
