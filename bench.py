@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 N_ROWS, N_COLS, CHAINS_PER_GPU = 581012, 54, 8
 BYTES_PER_PASS = N_ROWS * N_COLS * 4 + N_ROWS * 4          # one sweep of X and y serves every chain
 STEP_TRANSITIONS = 400
-ADAPT_ITERS = 150
+ADAPT_ITERS = 600
 WORKLOAD = ("configs[1]: covtype-shaped Bayesian logistic regression NUTS "
             "(N=581012, D=54 fp32, synthetic, 8 chains per GPU, max_tree_depth=10)")
 
