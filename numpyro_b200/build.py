@@ -44,7 +44,7 @@ def build_engine(force: bool = False, verbose: bool = False) -> str:
     srcs = engine_sources()
     if force or _stale(LIB, srcs):
         fast = os.environ.get("B200NUTS_FAST_KS")          # development only: a single streaming-kernel instance
-        cmd = ([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ([f"-DB2_STREAM_FAST_KS={int(fast)}"] if fast else [])
+        cmd = ([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ([f"-DB2_STREAM_FAST_KS={int(fast)}"] if fast else []) + (["-DB2_TICK_LAPS"] if os.environ.get("B200NUTS_TICK_LAPS") else [])
                + ["-o", LIB, os.path.join(CSRC, "b200nuts.cu")])
         subprocess.check_call(cmd, cwd=CSRC)
     return LIB

@@ -307,6 +307,13 @@ static int check_stream_abort(B200Nuts* h, cudaStream_t st) {
                     (double)s.tick_lap[c][3] / s.passes, s.pre_hit[c][0], s.pre_miss[c][0], s.pre_hit[c][1], s.pre_miss[c][1],
                     s.pre_hit[c][2], s.pre_miss[c][2]);
     }
+#ifdef B2_TICK_LAPS
+    if (getenv("B200NUTS_DEBUG_TICK") && s.passes) {
+        fprintf(stderr, "[b200nuts] chain 0 tick laps per pass:");
+        for (int k = 0; k < 16; ++k) fprintf(stderr, " [%d] %.0f", k, (double)s.laps[k] / (double)s.passes);
+        fprintf(stderr, "\n");
+    }
+#endif
     if (s.abort_flag) {
         static const char* what[] = {"", "a tile copy never landed", "beta fetch timed out", "partial poll timed out",
                                      "a peer rank's likelihood sums never arrived (row-sharded exchange)"};

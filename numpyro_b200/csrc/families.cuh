@@ -107,9 +107,12 @@ B2_HD void glm_finish(const FamilySpec& f, const float* z, float nll, const floa
     float prec = 1.0f;
     if (f.likelihood == LIK_NORMAL) prec = expf(z[f.off_prec]);
     // coefficient block: u ~ N(0, 1)
+    B2_LAPQ(-1);
     float acc = lane_sum(Dx, [&](int j) { const float u = z[f.off_u + j]; return 0.5f * u * u; });
     float U = acc + (float)Dx * kLogSqrt2Pi;
+    B2_LAPQ(8);
     B2_FOR_D(j, Dx) g[f.off_u + j] = z[f.off_u + j] + glm_scale_at(f, z, j) * (prec * gbeta[j]);
+    B2_LAPQ(9);
     if (f.off_lambda >= 0) {             // lambdas ~ HalfCauchy(1), z = log lambda
         float a = lane_sum(Dx, [&](int j) {
             const float zl = z[f.off_lambda + j];
@@ -156,6 +159,7 @@ B2_HD void glm_finish(const FamilySpec& f, const float* z, float nll, const floa
         U = U + (nll + f.nll_const);
     }
     u_out = U;
+    B2_LAPQ(10);
 }
 
 // ---- whole potential inside one warp (tiny models, regime R1) ---------------------------------

@@ -91,7 +91,8 @@ B2_HD constexpr int stream_ks_for(int D) { return D <= 8 ? 1 : D <= 16 ? 2 : D <
 // [7] beta -> fragments, [8] tick: finish potential, [9] tick: state machine, [10] tick: publish beta
 struct StreamSync { unsigned int abort_flag, pad_[3]; unsigned long long passes; unsigned long long dbg[16];
                     unsigned long long tick_sum[kStreamCT], tick_max[kStreamCT], tick_lap[kStreamCT][4];
-                    unsigned int pre_hit[kStreamCT][4], pre_miss[kStreamCT][4]; };   // per owner CTA: tick cycles, look-ahead hits
+                    unsigned int pre_hit[kStreamCT][4], pre_miss[kStreamCT][4];
+                    unsigned long long laps[16]; };     // -DB2_TICK_LAPS builds only   // per owner CTA: tick cycles, look-ahead hits
 
 struct StreamParams {
     TickCfg cfg; FamilySpec fam; OutBufs out;
@@ -521,6 +522,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
             ++seq; ++pass;
         }
         B2_TRACE_LANES(6);
+#ifdef B2_TICK_LAPS
+        if (cta == 0 && lane == 0) for (int k = 0; k < 16; ++k) { sy->laps[k] = b2_tick_laps[k]; b2_tick_laps[k] = 0ull; }
+#endif
         if (is_tick && lane == 0) {
             if (p.mode == 0) p.ctl[cta] = c;
             sy->tick_sum[cta] = tk_sum; sy->tick_max[cta] = tk_max;

@@ -139,6 +139,20 @@ B2_HD void leap_begin(int D, float eps, const float* imm, const float* z, const 
     }
 }
 
+// development only (-DB2_TICK_LAPS): clock64 laps of chain 0's tick, see scripts/exchange_probe.py
+#if defined(__CUDACC__) && defined(B2_TICK_LAPS)
+__device__ unsigned long long b2_tick_laps[16];
+__device__ long long b2_tick_t0;
+__host__ __device__ inline void b2_lapq(int i) {
+#if defined(__CUDA_ARCH__)
+    if (blockIdx.x == 0 && (threadIdx.x & 31u) == 0u) { const long long t_ = clock64(); if (i >= 0) b2_tick_laps[i] += (unsigned long long)(t_ - b2_tick_t0); b2_tick_t0 = t_; }
+#endif
+}
+#define B2_LAPQ(i) b2_lapq(i)
+#else
+#define B2_LAPQ(i) do {} while (0)
+#endif
+
 struct Tick {
     const TickCfg& cfg;
     ChainCtl& c;
@@ -316,10 +330,12 @@ struct Tick {
         const float half = 0.5f * e;
         const float* imm = v(V_IMM);
         float *zs = v(V_ZS), *rs = v(V_RS), *gs = v(V_GS);
+        B2_LAPQ(-1);
         B2_FOR_D(d, Dn) { const float gg = g[d]; gs[d] = gg; rs[d] = rs[d] - half * gg; }
         c.total_leapfrogs += 1ull;
         // _build_basetree (hmc_util.py:866-875)
         const float energy_new = u + kinetic(Dn, imm, rs);
+        B2_LAPQ(0);
         float delta = energy_new - c.energy0;
         if (is_nan(delta)) delta = f_inf();
         const float leaf_w = -delta;
@@ -329,6 +345,7 @@ struct Tick {
         float u_leaf;                                              // uniform01(split(k_sub)[1]), the proposal draw of this leaf
         if ((c.pre_mask & 1u) && key_is(c.pl_from, ks)) { st(c.k_sub, mk(c.pl_ksub)); u_leaf = c.pl_u; c.pre_hit[0] += 1u; }
         else { c.pre_miss[0] += 1u; const Key k_leaf = split_at(ks, 1); st(c.k_sub, split_at(ks, 0)); u_leaf = uniform01_at(k_leaf, 0); }
+        B2_LAPQ(1);
         const int leaf_idx = c.n_sub;
         float *zps = v(V_ZPS), *gps = v(V_GPS), *rsum_s = v(V_RSUMS);
         if (leaf_idx == 0) {
@@ -346,6 +363,7 @@ struct Tick {
             c.sub_weight = d_logaddexp(c.sub_weight, leaf_w);
             c.sub_sum_acc = c.sub_sum_acc + leaf_acc;
         }
+        B2_LAPQ(2);
         c.sub_div = leaf_div;
         c.n_sub = leaf_idx + 1;
         // checkpoints + iterative U-turn (hmc_util.py:941-981, 1034-1058)
@@ -368,11 +386,14 @@ struct Tick {
             }, l, r);
             sub_turning = (l <= 0.0f) || (r <= 0.0f);
         }
+        B2_LAPQ(3);
         if (c.n_sub < (1 << c.depth) && !sub_turning && !c.sub_div) {      // next leaf of this subtree
             leap_begin(Dn, e, imm, zs, rs, gs, zs, rs);
+            B2_LAPQ(4);
             return;
         }
         finish_doubling(sub_turning);
+        B2_LAPQ(5);
     }
 
     // _combine_tree with the biased kernel (hmc_util.py:936-938, 767-848)

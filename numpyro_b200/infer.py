@@ -12,6 +12,7 @@ the CUDA engine.  ``chain_method='parallel'`` shards chains over the GPUs visibl
 """
 from __future__ import annotations
 
+import os
 import warnings
 from collections import namedtuple
 from concurrent.futures import ThreadPoolExecutor
@@ -114,7 +115,10 @@ class MCMC:
     """numpyro.infer.MCMC (mcmc.py:225-809) over the B200 engine."""
 
     def __init__(self, sampler, *, num_warmup, num_samples, num_chains=1, thinning=1, postprocess_fn=None,
-                 chain_method="parallel", progress_bar=True, progress_rate=None, jit_model_args=False):
+                 chain_method="parallel", progress_bar=True, progress_rate=None, jit_model_args=False, row_shards=1):
+        """``row_shards`` (extension; the reference's analogue is passing GSPMD-sharded model arguments,
+        mcmc.py:240-266): split the rows of a tall GLM dataset over ``row_shards`` GPUs of this process; every GPU runs
+        all chains over its rows and the per-gradient all-reduce happens inside the kernels (BASELINE config 5)."""
         if not isinstance(sampler, HMC):
             raise TypeError("sampler must be numpyro_b200.infer.NUTS or HMC")
         if not isinstance(num_warmup, int) or num_warmup < 0:
@@ -127,6 +131,9 @@ class MCMC:
             raise NotImplementedError("postprocess_fn is derived from the declared family")
         self.sampler, self.num_warmup, self.num_samples = sampler, num_warmup, num_samples
         self.num_chains, self.thinning, self.chain_method = num_chains, thinning, chain_method
+        self.row_shards = int(row_shards)
+        if self.row_shards < 1:
+            raise ValueError("row_shards must be a positive integer")
         self.progress_bar = False          # the whole collection loop is device resident (util.py:411-416 path)
         self._shards: List[_Shard] = []
         self._bound = None
@@ -142,6 +149,12 @@ class MCMC:
     def _plan_shards(self):
         C = self.num_chains
         cur = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        if self.row_shards > 1:
+            G, ndev = self.row_shards, torch.cuda.device_count()
+            if ndev < G and not os.environ.get("B200NUTS_GRID"):
+                raise ValueError(f"row_shards={G} needs {G} GPUs (found {ndev})")
+            # (with B200NUTS_GRID set -- a testing aid -- the ranks share the current device, each on a part of its SMs)
+            return [_Shard(torch.device("cuda", k if ndev >= G else cur), 0, C) for k in range(G)]
         if self._dist:
             W, r = torch.distributed.get_world_size(), torch.distributed.get_rank()
             if C % W:
@@ -167,14 +180,29 @@ class MCMC:
                 if s.engine is not None:
                     s.engine.close()
         self._shards = self._plan_shards()
-        for s in self._shards:
+        G = self.row_shards
+        if G > 1:
+            if bound.X is None or bound.y is None:
+                raise ValueError("row_shards needs a GLM family with a design matrix")
+            N = int(bound.X.shape[0])
+            cuts = [N * k // G for k in range(G + 1)]
+        for k, s in enumerate(self._shards):
             cfg = dict(self.sampler._cfg)
             cfg.update(bound.cfg)
             cfg["num_chains"] = s.hi - s.lo
-            s.engine = Engine(device=s.device, X=bound.X, y=bound.y, aux=bound.aux, **cfg)
+            if G > 1:
+                cfg.update(shard_rank=k, shard_count=G, n_rows_global=N, regime=_capi.REGIME_STREAM)
+                s.engine = Engine(device=s.device, X=bound.X[cuts[k]:cuts[k + 1]], y=bound.y[cuts[k]:cuts[k + 1]], aux=bound.aux, **cfg)
+                s.stream = torch.cuda.Stream(device=s.device)     # the ranks' persistent kernels must run concurrently
+            else:
+                s.engine = Engine(device=s.device, X=bound.X, y=bound.y, aux=bound.aux, **cfg)
+        if G > 1:
+            blobs = [s.engine.shard_blob() for s in self._shards]
+            for s in self._shards:
+                s.engine.connect_shards(blobs)
 
     def _for_each_shard(self, fn):
-        if len(self._shards) == 1 or self.chain_method == "sequential":
+        if len(self._shards) == 1 or (self.chain_method == "sequential" and self.row_shards == 1):
             return [fn(s) for s in self._shards]
         with ThreadPoolExecutor(len(self._shards)) as pool:
             return list(pool.map(fn, self._shards))
@@ -229,7 +257,7 @@ class MCMC:
 
         def work(s: _Shard):
             e = s.engine
-            with torch.cuda.device(s.device):
+            with torch.cuda.device(s.device), torch.cuda.stream(getattr(s, "stream", None)):
                 if fresh:
                     e.init(keys[s.lo:s.hi], self.num_warmup, None if z0 is None else z0[s.lo:s.hi])
                 else:
@@ -245,6 +273,8 @@ class MCMC:
                 return host, st, vec
 
         results = self._for_each_shard(work)
+        if self.row_shards > 1:
+            results = results[:1]              # every rank holds the same (bit-identical) chains
         #: gradient evaluations (leapfrogs) spent so far by every local chain, warm-up included
         self.total_grad_evals = int(sum(int(st[k].total_leapfrogs) for _, st, _ in results for k in range(len(st))))
         host = {k: np.concatenate([r[0][k] for r in results], axis=0) for k in results[0][0]}

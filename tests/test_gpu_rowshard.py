@@ -148,3 +148,30 @@ def test_sharded_processes_over_cuda_ipc():
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert "ROWSHARD_OK" in p.stdout
+
+
+@pytest.mark.parametrize("devices", _layouts())
+def test_mcmc_row_shards_matches_engine_level_ranks(devices, half_grid):
+    """Public API: MCMC(NUTS(LogisticRegression()), row_shards=2) == the engine-level ranks over the same row cuts."""
+    if devices == (0, 1):
+        pytest.skip("the API picks cuda:0..G-1 itself; covered by the one-device layout when only the mailboxes differ")
+    from numpyro_b200 import families as model_families, random as b2random
+    from numpyro_b200.infer import MCMC, NUTS
+    N, D, C = 20000, 12, 4
+    X, y = _data(N, D, 9)
+    mcmc = MCMC(NUTS(model_families.LogisticRegression(), max_tree_depth=5), num_warmup=30, num_samples=20, num_chains=C,
+                chain_method="vectorized", progress_bar=False, row_shards=2)
+    mcmc.run(b2random.PRNGKey(4), X, y, extra_fields=("num_steps",))
+    got = mcmc.get_samples(group_by_chain=True)["coefs"]
+    steps = mcmc.get_extra_fields(group_by_chain=True)["num_steps"]
+    assert got.shape == (C, 20, D) and np.isfinite(got).all()
+    for s in mcmc._shards:
+        s.engine.close()
+    rk = Ranks(X, y, C, [0, N // 2, N], (0, 0), max_tree_depth_warmup=5, max_tree_depth=5)
+    keys = prng.split(prng.key(4), C)
+    rk.each(lambda e: e.init(keys, 30))
+    outs = rk.each(lambda e: {k: v.cpu().numpy() for k, v in e.run(50, 30, fields=("z", "num_steps")).items()})
+    rk.close()
+    assert np.array_equal(outs[0]["z"], got) and np.array_equal(outs[0]["num_steps"], steps)
+    # and the posterior is the logistic-regression posterior: coefficient means near the maximum-likelihood direction
+    assert np.abs(got.mean((0, 1))).max() < 2.0
