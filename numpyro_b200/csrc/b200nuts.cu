@@ -29,7 +29,7 @@ struct B200Nuts {
     // R2
     float2* partial = nullptr; uint4* beta = nullptr; StreamSync* sync = nullptr;
     float* img = nullptr; long long n_tiles = 0; int pad_rows = 0, ks = 0;   // engine-owned tile image of (X, y)
-    int grid = 0, stages = 4, vecs_in_smem = 0; size_t smem = 0;
+    int grid = 0, stages = 4, vecs_in_smem = 0, num_groups = 1; size_t smem = 0;
     long long launches = 0, passes = 0;
     unsigned long long dbg[16] = {0};
     unsigned int* trace_host = nullptr; unsigned int* trace_dev = nullptr;     // B200NUTS_TRACE: host-mapped progress words
@@ -206,6 +206,7 @@ static int stream_launch(B200Nuts* h, int mode, const OutBufs& out, const float*
                          cudaStream_t st) {
     StreamParams p; memset(&p, 0, sizeof(p));
     p.cfg = h->tick; p.cfg.D = h->D; p.fam = h->fam; p.out = out; p.C = h->C; p.Dp = h->Dp; p.mode = mode;
+    p.num_groups = h->num_groups;
     p.ctl = h->ctl; p.vecs = h->vecs; p.partial = h->partial; p.beta = h->beta; p.sync = h->sync;
     p.z_in = z_in; p.u_out = u_out; p.g_out = g_out; p.stages = h->stages;
     p.vecs_in_smem = h->vecs_in_smem; p.spin_limit = 2000000000LL;      // ~1 s: every wait in the engine is bounded
@@ -230,8 +231,8 @@ static int stream_launch(B200Nuts* h, int mode, const OutBufs& out, const float*
     { const char* e = getenv("B200NUTS_DEBUG_WARPS"); p.dbg_warps = e ? atoi(e) : 1000; }
     CK(cudaMemsetAsync(h->sync, 0, sizeof(StreamSync), st));
     // sequence tags ride inside the exchanged data: a launch must not see the previous launch's tags
-    CK(cudaMemsetAsync(h->beta, 0, sizeof(uint4) * kBetaCopies * kBetaWords, st));
-    CK(cudaMemsetAsync(h->partial, 0, sizeof(float2) * (size_t)h->grid * kStreamCT * kGStride, st));
+    CK(cudaMemsetAsync(h->beta, 0, sizeof(uint4) * kBetaCopies * h->num_groups * kBetaWords, st));
+    CK(cudaMemsetAsync(h->partial, 0, sizeof(float2) * (size_t)h->grid * h->num_groups * kStreamCT * kGStride, st));
     void* args[] = {&p};
     const void* fn = stream_kernel_for(h->ks, h->fam.likelihood);
     if (!fn) { h->err = "stream regime: no kernel instance for this shape"; return B200NUTS_EINVAL; }
@@ -270,22 +271,22 @@ static int check_stream_abort(B200Nuts* h, cudaStream_t st) {
                 }
                 if (getenv("B200NUTS_TRACE")) {      // post-mortem over a side stream (the stuck kernel keeps the main one busy)
                     cudaStream_t side; cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
-                    std::vector<uint4> hb((size_t)kBetaCopies * kBetaWords);
-                    std::vector<float2> hp((size_t)h->grid * kStreamCT * kGStride);
+                    std::vector<uint4> hb((size_t)kBetaCopies * h->num_groups * kBetaWords);
+                    std::vector<float2> hp((size_t)h->grid * h->num_groups * kStreamCT * kGStride);
                     cudaMemcpyAsync(&s, h->sync, sizeof(s), cudaMemcpyDeviceToHost, side);
                     cudaMemcpyAsync(hb.data(), h->beta, hb.size() * sizeof(uint4), cudaMemcpyDeviceToHost, side);
                     cudaMemcpyAsync(hp.data(), h->partial, hp.size() * sizeof(float2), cudaMemcpyDeviceToHost, side);
                     cudaError_t ce = cudaStreamSynchronize(side);
                     fprintf(stderr, "[b200nuts] post-mortem copy: %s; abort_flag %u\n", cudaGetErrorString(ce), s.abort_flag);
                     for (int r = 0; r < kBetaCopies; ++r)
-                        for (int c = 0; c < h->C; ++c) {
+                        for (int c = 0; c < h->C && c < kStreamCT; ++c) {      // (group 0 only)
                             fprintf(stderr, "  beta replica %d chain %d tags (k-step 0, t=0..3):", r, c);
-                            for (int t = 0; t < 4; ++t) fprintf(stderr, " %08x/%08x", hb[(size_t)r * kBetaWords + c * 4 + t].y, hb[(size_t)r * kBetaWords + c * 4 + t].w);
+                            for (int t = 0; t < 4; ++t) fprintf(stderr, " %08x/%08x", hb[(size_t)r * h->num_groups * kBetaWords + c * 4 + t].y, hb[(size_t)r * h->num_groups * kBetaWords + c * 4 + t].w);
                             fprintf(stderr, "\n");
                         }
-                    for (int c = 0; c < h->C; ++c) {
+                    for (int c = 0; c < h->C && c < kStreamCT; ++c) {
                         fprintf(stderr, "  partial tags chain %d (d = 0) per CTA:", c);
-                        for (int g = 0; g < h->grid; ++g) { unsigned int tg; memcpy(&tg, &hp[((size_t)g * kStreamCT + c) * kGStride].y, 4); fprintf(stderr, " %u", tg); }
+                        for (int g = 0; g < h->grid; ++g) { unsigned int tg; memcpy(&tg, &hp[((size_t)g * h->num_groups * kStreamCT + c) * kGStride].y, 4); fprintf(stderr, " %u", tg); }
                         fprintf(stderr, "\n");
                     }
                 }
@@ -373,14 +374,14 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
     // regime
     int regime = cfg->regime;
     const bool glm = h->fam.family == FAM_GLM;
-    const bool stream_ok = glm && h->C <= kStreamCT && h->fam.Dx <= 64 && h->C <= h->num_sms;
+    const bool stream_ok = glm && h->C <= kMaxStreamChains && h->fam.Dx <= 64 && h->C <= h->num_sms;
     if (regime == B200NUTS_REGIME_AUTO)
         regime = (stream_ok && (long long)h->fam.N * h->fam.Dx >= (1LL << 20)) ? B200NUTS_REGIME_STREAM : B200NUTS_REGIME_WARP;
     if (regime == B200NUTS_REGIME_STREAM && !stream_ok) {
-        g_create_err = "stream regime needs a GLM family with <= 8 chains and <= 64 columns"; delete h; return B200NUTS_EINVAL;
+        g_create_err = "stream regime needs a GLM family with <= 64 columns and one SM per chain (<= 148 chains)"; delete h; return B200NUTS_EINVAL;
     }
     if (cfg->shard_count > 1) {
-        if (!stream_ok) { g_create_err = "row-sharded handles need the streaming regime (GLM, <= 8 chains, <= 64 columns)"; delete h; return B200NUTS_EINVAL; }
+        if (!stream_ok) { g_create_err = "row-sharded handles need the streaming regime (GLM, <= 64 columns, one SM per chain)"; delete h; return B200NUTS_EINVAL; }
         regime = B200NUTS_REGIME_STREAM;
         h->shard_rank = cfg->shard_rank; h->shard_count = cfg->shard_count;
         h->n_rows_global = cfg->n_rows_global > 0 ? cfg->n_rows_global : cfg->n_rows;
@@ -435,8 +436,9 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
         k_stream_repack<<<h->num_sms * 8, 256>>>(h->fam.X, h->fam.y, h->fam.N, h->fam.Dx, stream_pitch(h->ks), h->n_tiles, h->img);
         if ((ce = cudaGetLastError()) != cudaSuccess) return fail("repack", ce);
         h->launches += 1;
-        if ((ce = cudaMalloc(&h->partial, sizeof(float2) * (size_t)h->grid * kStreamCT * kGStride)) != cudaSuccess) return fail("cudaMalloc partial", ce);
-        if ((ce = cudaMalloc(&h->beta, sizeof(uint4) * kBetaCopies * kBetaWords)) != cudaSuccess) return fail("cudaMalloc beta", ce);
+        h->num_groups = (h->C + kStreamCT - 1) / kStreamCT;
+        if ((ce = cudaMalloc(&h->partial, sizeof(float2) * (size_t)h->grid * h->num_groups * kStreamCT * kGStride)) != cudaSuccess) return fail("cudaMalloc partial", ce);
+        if ((ce = cudaMalloc(&h->beta, sizeof(uint4) * kBetaCopies * h->num_groups * kBetaWords)) != cudaSuccess) return fail("cudaMalloc beta", ce);
         if ((ce = cudaMalloc(&h->sync, sizeof(StreamSync))) != cudaSuccess) return fail("cudaMalloc sync", ce);
         if (h->shard_count > 1) {
             if ((ce = cudaMalloc(&h->mail, sizeof(float2) * kMailFloat2)) != cudaSuccess) return fail("cudaMalloc mailbox", ce);

@@ -56,7 +56,9 @@
 
 namespace b2 {
 
-constexpr int kStreamCT = 8;             // chains per pass
+constexpr int kStreamCT = 8;             // chains per pass (= one chain group = the N of the MMAs)
+constexpr int kMaxGroups = 20;           // chain groups per handle: passes rotate over the groups, so one group's exchange
+constexpr int kMaxStreamChains = kMaxGroups * kStreamCT;   // ... hides behind the other groups' sweeps (every chain needs its own owner CTA)
 constexpr int kConsWarps = 15;           // consumer warps
 constexpr int kStreamThreads = 32 * (kConsWarps + 1);
 constexpr int kTileRows = 16;            // rows per ring slot = one consumer warp's unit of work
@@ -70,8 +72,8 @@ constexpr int kBetaCopies = 4;           // replicas of the published beta (CTA 
 constexpr int kBetaWords = 8 * kStreamCT * 4;     // 16-byte words per replica: [k-step][chain][t]
 constexpr int kConsThreads = kConsWarps * 32, kTopThreads = kStreamThreads;
 constexpr int kMaxShards = 16;           // row-sharded handles: ranks that sweep disjoint rows of the same pass
-// mailbox of a row-sharded handle: [pass parity][chain][source rank][kGStride] {value, tag}
-constexpr size_t kMailFloat2 = (size_t)2 * kStreamCT * kMaxShards * kGStride;
+// mailbox of a row-sharded handle: [round parity][chain][source rank][kGStride] {value, tag}
+constexpr size_t kMailFloat2 = (size_t)2 * kMaxStreamChains * kMaxShards * kGStride;
 
 B2_HD constexpr int stream_pitch(int KS) { return (KS % 2 == 0) ? 8 * KS + 8 : 8 * KS; }     // 8 * odd
 // float offset of element (row r, column c) of a tile, r in [0, 16), c in [0, P)
@@ -90,16 +92,17 @@ B2_HD constexpr int stream_ks_for(int D) { return D <= 8 ? 1 : D <= 16 ? 2 : D <
 // publish partial, [3] (unused), [4] poll + sum the partials, [5] total loop, [6] tick warp busy,
 // [7] beta -> fragments, [8] tick: finish potential, [9] tick: state machine, [10] tick: publish beta
 struct StreamSync { unsigned int abort_flag, pad_[3]; unsigned long long passes; unsigned long long dbg[16];
-                    unsigned long long tick_sum[kStreamCT], tick_max[kStreamCT], tick_lap[kStreamCT][4];
-                    unsigned int pre_hit[kStreamCT][4], pre_miss[kStreamCT][4];
+                    unsigned long long tick_sum[kMaxStreamChains], tick_max[kMaxStreamChains], tick_lap[kMaxStreamChains][4];
+                    unsigned int pre_hit[kMaxStreamChains][4], pre_miss[kMaxStreamChains][4];
                     unsigned long long laps[16]; };     // -DB2_TICK_LAPS builds only   // per owner CTA: tick cycles, look-ahead hits
 
 struct StreamParams {
     TickCfg cfg; FamilySpec fam; OutBufs out;
     int C, Dp, mode;                     // mode 0: run chains, 1: evaluate potential at z_in
+    int num_groups;                      // ceil(C / kStreamCT)
     ChainCtl* ctl; float* vecs;          // [C], [V_COUNT][C][Dp]
-    float2* partial;                     // [grid][kStreamCT][kGStride] {value, tag}
-    uint4* beta;                         // [kBetaCopies][8 k-steps][kStreamCT][4] {b0, tag, b1, tag}: beta in MMA-fragment order
+    float2* partial;                     // [grid][num_groups][kStreamCT][kGStride] {value, tag = round of the group}
+    uint4* beta;                         // [kBetaCopies][num_groups][8 k-steps][kStreamCT][4] {b0, tag, b1, tag}: beta in MMA-fragment order
     StreamSync* sync;
     const float* z_in; float* u_out; float* g_out;    // mode 1
     const float* img;                    // tile image of (X, y), see above
@@ -266,7 +269,7 @@ B2_D bool spin_ge(const unsigned int* ctr, unsigned int target, StreamSync* sy, 
 B2_HD size_t stream_fixed_smem(int Dp, bool vecs_in_smem) {
     size_t b = 0;
     b += (size_t)kConsWarps * kMaxStages * 8;                      // mbarriers
-    b += (size_t)kBetaWords * 16;                                  // staged beta, [k-step][chain][t] {b0, tag, b1, tag}
+    b += (size_t)2 * kBetaWords * 16;                              // staged beta (two passes), [k-step][chain][t] {b0, tag, b1, tag}
     b += (size_t)kXRedFloats * 4;                                  // cross-CTA reduction + tick scratch
     b += 64 * 4 + 64 * 4 + 256 + 128;                              // gred(+nll), flags, timers
     if (vecs_in_smem) b += (size_t)V_COUNT * Dp * 4;
@@ -300,7 +303,8 @@ __global__ void k_stream_repack(const float* __restrict__ X, const float* __rest
 // beta_c = s(z) * u for the next sweep (zero when the chain needs no gradient), published in the order of the
 // consumers' B fragments: word (k-step kk, chain, t) = { beta[8kk+2t], tag, beta[8kk+2t+1], tag }.  Each 8-byte
 // half is written atomically, so a reader that sees the tag also sees the value next to it.
-B2_D void stream_publish_beta(const StreamParams& p, int cta, const float* zsrc, bool active, uint32_t tag) {
+B2_D void stream_publish_beta(const StreamParams& p, int chain, const float* zsrc, bool active, uint32_t tag) {
+    const int grp = chain / kStreamCT, slot = chain % kStreamCT;
     const int lane = threadIdx.x & 31;
     const int kk = lane >> 2, t = lane & 3;              // 8 k-steps x 4 = 32 lanes
     const int d0 = 8 * kk + 2 * t;
@@ -309,7 +313,7 @@ B2_D void stream_publish_beta(const StreamParams& p, int cta, const float* zsrc,
     if (active && d0 + 1 < p.fam.Dx) b1 = glm_scale_at(p.fam, zsrc, d0 + 1) * zsrc[p.fam.off_u + d0 + 1];
     const uint4 w = make_uint4(__float_as_uint(b0), tag, __float_as_uint(b1), tag);
 #pragma unroll
-    for (int r = 0; r < kBetaCopies; ++r) __stcg(p.beta + r * kBetaWords + (kk * kStreamCT + cta) * 4 + t, w);
+    for (int r = 0; r < kBetaCopies; ++r) __stcg(p.beta + ((size_t)r * p.num_groups + grp) * kBetaWords + (kk * kStreamCT + slot) * 4 + t, w);
     __syncwarp();
 }
 
@@ -362,10 +366,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
     unsigned char* q = smem_raw;
     float* tiles = (float*)q; q += (size_t)kConsWarps * nst * SLOT_FLOATS * 4;
     uint64_t* full = (uint64_t*)q; q += (size_t)kConsWarps * kMaxStages * 8;
-    uint4* bs = (uint4*)q; q += (size_t)kBetaWords * 16;
+    uint4* bs = (uint4*)q; q += (size_t)2 * kBetaWords * 16;
     float* xred = (float*)q; q += (size_t)kXRedFloats * 4;
     float* gred = (float*)q; q += 64 * 4 + 64 * 4;
-    int* flags = (int*)q; q += 256;                  // [0] 0 go / 1 all chains done / 2 abort, [16..31] reduction slot of warp w
+    int* flags = (int*)q; q += 256;                  // per pass parity: [0..1] 0 go / 1 all chains done / 2 abort, [2..3] chain group, [4..5] its round;
+                                                     // [8] last pass begun by the consumers, [16..31] reduction slot of warp w, [32..51] rounds per group
     unsigned long long* tdbg = (unsigned long long*)q; q += 128;
     float* cvecs = (float*)q;
 
@@ -379,6 +384,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         for (int i = 0; i < kConsWarps * kMaxStages; ++i) mbar_init(&full[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int i = 0; i < 16; ++i) tdbg[i] = 0ull;
+        for (int i = 0; i < 64; ++i) flags[i] = 0;
+        flags[8] = -1;                               // last pass the consumers have begun
     }
     ChainVecs cv; cv.base = nullptr; cv.field_stride = 0;
     if (is_tick) {
@@ -409,18 +416,47 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         if (is_tick && p.mode == 0) c = p.ctl[cta]; else memset(&c, 0, sizeof(c));
         Tick tk{p.cfg, c, cv, p.out, cta, p.C};
         bool chain_done = !is_tick || (p.mode == 0 && c.phase == PH_DONE);
-        uint32_t seq = 1;                            // tag of the beta the next sweep needs
+        // Passes rotate over the chain groups (8 chains each) that still have work; group g's r-th sweep uses the betas its
+        // owners published with tag r.  With several groups the owners' ticks overlap with the other groups' sweeps.
+        const int NGRP = p.num_groups, my_group = cta / kStreamCT;
+        unsigned int* rounds = (unsigned int*)(flags + 32);       // sweeps staged so far, per group (this warp's private copy)
+        volatile int* started = flags + 8;
+        uint32_t done_mask = 0u;                     // groups whose chains have all finished
+        uint32_t my_round = 0u;                      // round of my group's sweep that is waiting for its tick
+        bool pending = false;                        // ... and whether there is one
+        int cur = 0, qpass = 0, status = 0;
         if (is_tick) {                               // prologue: the first beta
             const float* zsrc = (p.mode == 0) ? cv.v(V_ZS) : (p.z_in + (size_t)cta * p.cfg.D);
-            stream_publish_beta(p, cta, zsrc, !chain_done, seq | (chain_done ? 0x80000000u : 0u));
+            stream_publish_beta(p, cta, zsrc, !chain_done, 1u | (chain_done ? 0x80000000u : 0u));
         }
-        const uint4* bsrc = p.beta + (cta % kBetaCopies) * kBetaWords;
-        const int my_chain = (lane >> 2) & 7;         // chain of this lane's words (word w = lane + 32 kk)
-        while (true) {
-            // ---- fetch every chain's beta for sweep `seq` (tags ride in the data: poll until they all match)
-            int status = 0;
+        const int my_chain = (lane >> 2) & 7;         // chain slot of this lane's words (word w = lane + 32 kk)
+
+        uint32_t need = 0u;                          // round (= beta tag) of the sweep being staged
+        int grp = -1;
+        // Stage the next pass for this CTA's consumers: fetch the betas of group `grp` (tag need), put them into the pass's
+        // staging buffer and release the consumers.  Returns 0 = staged, 1 = the group has finished (no pass), 2 = stop.
+        auto stage = [&]() -> int {
             B2_TRACE_LANES(1);
+            // the staging buffer and the barrier phase of pass qpass were last used by pass qpass - 2: the consumers must
+            // have begun pass qpass - 1 before they are reused
             {
+                const long long t_w = clock64();
+                while (true) {                       // (lane 0's view decides: every lane runs the same number of iterations)
+                    const int ready = __shfl_sync(0xFFFFFFFFu, (*started >= qpass - 1) ? 1 : 0, 0);
+                    if (ready) break;
+                    __nanosleep(256);                // (a spinning warp would take issue slots from the consumers of its scheduler)
+                    bool give_up = ld_acquire(&sy->abort_flag) != 0u;
+                    if (clock64() - t_w > 4 * p.spin_limit) { atomicCAS(&sy->abort_flag, 0u, 2u); give_up = true; }
+                    if (__any_sync(0xFFFFFFFFu, give_up)) { status = 2; break; }
+                }
+            }
+            uint4* bsq = bs + (size_t)(qpass & 1) * kBetaWords;
+            need = 0u;
+            if (status == 0) {
+                // fetch the betas of group `grp` for its next sweep (tags ride in the data: poll until they all match)
+                need = rounds[grp] + 1u;
+                const uint4* bsrc = p.beta + ((size_t)(cta % kBetaCopies) * NGRP + grp) * kBetaWords;
+                const bool absent = grp * kStreamCT + my_chain >= p.C;
                 uint4 w[KS];
                 const long long t_w = clock64();
                 while (true) {
@@ -428,9 +464,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
 #pragma unroll
                     for (int kk = 0; kk < KS; ++kk) {
                         w[kk] = ld_volatile_v4(bsrc + lane + 32 * kk);
-                        ok = ok && ((w[kk].y & 0x7FFFFFFFu) == seq) && ((w[kk].w & 0x7FFFFFFFu) == seq);
+                        ok = ok && ((w[kk].y & 0x7FFFFFFFu) == need) && ((w[kk].w & 0x7FFFFFFFu) == need);
                     }
-                    if (my_chain >= p.C) ok = true;
+                    if (absent) ok = true;
                     if (p.trace) {
                         const unsigned int bal = __ballot_sync(0xFFFFFFFFu, ok);
                         if (lane == 0) { p.trace[32 * blockIdx.x + 2] = bal; p.trace[32 * blockIdx.x + 3] += 1u; }
@@ -441,19 +477,43 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                     if (clock64() - t_w > p.spin_limit) { atomicCAS(&sy->abort_flag, 0u, 2u); give_up = true; }
                     if (__any_sync(0xFFFFFFFFu, give_up)) { status = 2; break; }
                 }
-                const bool zero = (my_chain >= p.C) || status == 2;
+                const bool done_bit = absent || ((w[0].y >> 31) != 0u);
+                if (status == 0 && __all_sync(0xFFFFFFFFu, done_bit)) {      // nothing left to sweep for this group
+                    done_mask |= 1u << grp; cur = (grp + 1) % NGRP;
+                    return 1;
+                }
+                const bool zero = absent || status == 2;
 #pragma unroll
-                for (int kk = 0; kk < KS; ++kk) bs[lane + 32 * kk] = zero ? make_uint4(0u, 0u, 0u, 0u) : w[kk];
-                const bool done_bit = (my_chain >= p.C) || ((w[0].y >> 31) != 0u);
-                if (status == 0 && __all_sync(0xFFFFFFFFu, done_bit)) status = 1;
+                for (int kk = 0; kk < KS; ++kk) bsq[lane + 32 * kk] = zero ? make_uint4(0u, 0u, 0u, 0u) : w[kk];
             }
-            if (lane == 0) flags[0] = status;
-            __syncwarp();
-            bar_arrive<kBarBeta, kStreamThreads>();  // release the consumers (they read flags[0] and `bs`)
-            if (status) break;
+            if (lane == 0) {
+                flags[qpass & 1] = status; flags[2 + (qpass & 1)] = grp; flags[4 + (qpass & 1)] = (int)need;
+                if (status == 0) rounds[grp] = need;
+            }
+            warp_sync_hard();
+            bar_arrive<kBarBeta, kStreamThreads>();  // release the consumers (they read flags and the staged betas)
             B2_TRACE_LANES(2);
-            if (is_tick && p.mode == 0 && !chain_done && !p.no_prefetch) tk.prefetch();     // off the critical path: PRNG look-ahead
-            if (is_tick) {
+            return status ? 2 : 0;
+        };
+
+        while (true) {
+            // ---- next group with work (all warps of all CTAs derive the same schedule from the same betas)
+            grp = -1;
+            for (int k = 0; k < NGRP; ++k) { const int cand = (cur + k) % NGRP; if (!((done_mask >> cand) & 1u)) { grp = cand; break; } }
+            if (grp < 0) status = 1;
+            // My own next beta must exist before my group can be swept again (always the case with a single group): tick first.
+            // Otherwise stage the other group's pass first, so that my tick overlaps with its sweep.
+            const bool tick_first = (status == 0) && pending && grp == my_group;
+            int staged = -1;
+            if (!tick_first) {
+                staged = stage();
+                if (staged == 1) continue;
+                if (staged == 2) break;
+            }
+            if (pending) {
+                // ---- the tick of this CTA's chain after a sweep of its group: reduced likelihood sums -> potential -> NUTS
+                //      state machine -> next beta (tag my_round + 1)
+                const uint32_t seq = my_round;
                 B2_TRACE_LANES(3);
                 bar_sync<kBarTick, kStreamThreads>();    // segment sums are in `xred`
                 B2_TRACE_LANES(4);
@@ -477,7 +537,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                     // ---- all-reduce over the row shards: store this rank's sums into every rank's mailbox, then add the
                     //      shard_count contributions of this chain in rank order (same order everywhere => identical bits)
                     const uint32_t xtag = (p.epoch << 24) ^ (seq & 0xFFFFFFu);
-                    const size_t slot0 = (size_t)(seq & 1u) * kStreamCT * kMaxShards * kGStride + (size_t)cta * kMaxShards * kGStride;
+                    const size_t slot0 = ((size_t)(seq & 1u) * kMaxStreamChains + (size_t)cta) * kMaxShards * kGStride;
                     const long long t_x = clock64();
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
@@ -518,8 +578,18 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                     tk_sum += dt; if (dt > tk_max) tk_max = dt;
                     if (dbg) tdbg[6] += dt;
                 }
+                pending = false;
             }
-            ++seq; ++pass;
+            if (tick_first) {
+                staged = stage();
+                if (staged == 1) continue;
+                if (staged == 2) break;
+            }
+            if (is_tick && grp == my_group) {
+                pending = true; my_round = need;
+                if (p.mode == 0 && !chain_done && !p.no_prefetch) tk.prefetch();     // off the critical path: PRNG look-ahead
+            }
+            cur = (grp + 1) % NGRP; ++qpass; ++pass;
         }
         B2_TRACE_LANES(6);
 #ifdef B2_TICK_LAPS
@@ -692,12 +762,15 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         // ---- wait until this CTA's tick warp has staged every chain's beta of this pass
         if (ctid == 0) B2_TRACE(0, 1);
         bar_sync<kBarBeta, kStreamThreads>();
-        if (flags[0]) break;
-        if (ctid == 0) B2_TRACE(0, 2);
+        const int par = (int)(pass & 1u);
+        if (flags[par]) break;
+        const int grp = flags[2 + par];               // chain group served by this pass and the round (tag) of its sweep
+        const uint32_t tag = (uint32_t)flags[4 + par];
+        if (ctid == 0) { *(volatile int*)(flags + 8) = (int)pass; B2_TRACE(0, 2); }
         if (ctid == 0) B2_DBG_LAP(0);
 #pragma unroll
         for (int kk = 0; kk < KS; ++kk) {                                   // beta -> B fragments (k = column, n = chain)
-            const uint4 w = bs[(kk * kStreamCT + g) * 4 + t];
+            const uint4 w = bs[(size_t)par * kBetaWords + (kk * kStreamCT + g) * 4 + t];
             const float b0 = __uint_as_float(w.x), b1 = __uint_as_float(w.z);
             float l0, l1; tf32_lo2(b0, b1, l0, l1);
             bhi[kk][0] = w.x; bhi[kk][1] = w.z;
@@ -767,7 +840,6 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         }
         bar_sync<kBarCons, kConsThreads>();
         {
-            const uint32_t tag = pass + 1u;
             for (int o = ctid; o < kStreamCT * 65; o += kConsThreads) {
                 const int c = o / 65, d = o - c * 65;
                 int src = -1;
@@ -784,7 +856,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
 #pragma unroll
                     for (int w = 0; w < kConsWarps; ++w) a += tiles[((size_t)w * nst + flags[16 + w]) * SLOT_FLOATS + src];
                 }
-                __stcg(p.partial + ((size_t)cta * kStreamCT + c) * kGStride + d, make_float2(a, __uint_as_float(tag)));
+                __stcg(p.partial + (((size_t)cta * p.num_groups + grp) * kStreamCT + c) * kGStride + d, make_float2(a, __uint_as_float(tag)));
             }
         }
         bar_sync<kBarCons, kConsThreads>();          // every scratch slot has been read: refill them
@@ -793,15 +865,14 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
 
         // ---- chain owner: poll the partials of all CTAs (tags ride in the data), sum them in fixed order,
         //      hand over to the tick warp
-        if (is_tick) {
-            const uint32_t tag = pass + 1u;
+        if (is_tick && cta / kStreamCT == grp) {
             const int o = ctid % 65, seg = ctid / 65;
             if (seg < kXSeg) {
                 // kXSeg segments x 65 outputs; each thread adds its segment's CTAs in ascending order.  All loads of a
                 // batch are in flight together (L2 latency overlapped); stale entries are simply polled again.
                 float a = 0.0f;
                 const int g0 = G * seg / kXSeg, g1 = G * (seg + 1) / kXSeg;
-                const float2* src = p.partial + (size_t)cta * kGStride + o;
+                const float2* src = p.partial + ((size_t)grp * kStreamCT + (cta % kStreamCT)) * kGStride + o;
                 const long long t_w = clock64();
                 for (int gg = g0; gg < g1; gg += 24) {
                     float2 v[24];
@@ -810,7 +881,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
 #pragma unroll
                         for (int k = 0; k < 24; ++k) {
                             if (gg + k < g1) {
-                                v[k] = ld_volatile_v2(src + (size_t)(gg + k) * (kStreamCT * kGStride));
+                                v[k] = ld_volatile_v2(src + (size_t)(gg + k) * ((size_t)p.num_groups * kStreamCT * kGStride));
                                 ok = ok && (__float_as_uint(v[k].y) == tag);
                             } else v[k] = make_float2(0.0f, 0.0f);
                         }

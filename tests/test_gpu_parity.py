@@ -257,6 +257,39 @@ def test_stream_regime_run_bit_exact():
     assert sum(int(st[c].total_leapfrogs) for c in range(C)) > 0
 
 
+@pytest.mark.parametrize("C", [9, 20])
+def test_stream_regime_many_chains_rotating_groups(C):
+    """More than 8 chains in the streaming engine: passes rotate over chain groups of 8 (the owners' ticks overlap with
+    the other groups' sweeps).  Potentials of every chain, whole runs bit-exact against the oracle, and chain c of the
+    C-chain run == the same chain of an 8-chain run (the reference's chain-independence, test_mcmc.py:868-914)."""
+    rng = np.random.default_rng(40 + C)
+    N, D = 7000, 11
+    X = rng.normal(size=(N, D)).astype(F)
+    y = (rng.uniform(size=N) < 1 / (1 + np.exp(-(X @ (rng.normal(size=D) * 0.5))))).astype(F)
+    fam = families.logistic_regression(X, y)
+    e = glm_engine(C, X, y, regime=_capi.REGIME_STREAM, max_tree_depth_warmup=5, max_tree_depth=5)
+    z = (rng.normal(size=(C, D)) * 0.3).astype(F)
+    U, g = e.potential_and_grad(z)
+    for c in range(C):
+        u64, g64 = fam.potential64(z[c].astype(np.float64))
+        np.testing.assert_allclose(U[c].item(), u64, rtol=1e-5)
+        np.testing.assert_allclose(g[c].cpu().numpy(), g64, rtol=1e-5, atol=1e-5 * np.abs(g64).max())
+    keys = prng.split(prng.key(9), C)
+    e.init(keys, 30)
+    out = e.run(45, 30, fields=FIELDS)
+    for c in (0, 8, C - 1):
+        kern = chain.Kernel(device_potential(e, c), max_tree_depth=(5, 5))
+        res, _ = chain.run_chain(kern, fam, keys[c], 30, 15, fields=FIELDS)
+        assert_run_equal(out, res, c)
+    e8 = glm_engine(8, X, y, regime=_capi.REGIME_STREAM, max_tree_depth_warmup=5, max_tree_depth=5)
+    e8.init(keys[C - 8:], 30)
+    out8 = e8.run(45, 30, fields=FIELDS)
+    for f in FIELDS:
+        assert torch.equal(out[f][C - 8:], out8[f]), f
+    st, _ = e.state()
+    assert all(st[c].i == 45 and st[c].done == 1 for c in range(C))
+
+
 def test_chain_of_many_equals_single_chain_and_resume():
     """test/infer/test_mcmc.py:868-914 (chain 0 of a 2-chain run == 1-chain run with split(key)[0])
     and :437-485 (warmup then run == run)."""
