@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libb200nuts.so")
+LIB_PATH = os.environ.get("B200NUTS_LIB") or os.path.join(_HERE, "csrc", "libb200nuts.so")   # (override: A/B runs of two builds)
 
 i32, i64, u32, u64, f32 = C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_float
 vp = C.c_void_p

@@ -181,25 +181,30 @@ __global__ void k_detmath(int op, const float* x, long long n, float* out) {
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int KS>
+template <int KS, bool MG>
 static const void* stream_kernel_lik(int lik) {
-    return lik == LIK_BERNOULLI ? (const void*)stream_engine_kernel<KS, LIK_BERNOULLI>
-         : lik == LIK_POISSON   ? (const void*)stream_engine_kernel<KS, LIK_POISSON>
-                                : (const void*)stream_engine_kernel<KS, LIK_NORMAL>;
+    return lik == LIK_BERNOULLI ? (const void*)stream_engine_kernel<KS, LIK_BERNOULLI, MG>
+         : lik == LIK_POISSON   ? (const void*)stream_engine_kernel<KS, LIK_POISSON, MG>
+                                : (const void*)stream_engine_kernel<KS, LIK_NORMAL, MG>;
 }
-static const void* stream_kernel_for(int ks, int lik) {
+template <bool MG>
+static const void* stream_kernel_for_mg(int ks, int lik) {
 #ifdef B2_STREAM_FAST_KS           // development builds: one instance only (B200NUTS_FAST_KS=<ks> python -m numpyro_b200.build)
-    return (ks == B2_STREAM_FAST_KS && lik == LIK_BERNOULLI) ? (const void*)stream_engine_kernel<B2_STREAM_FAST_KS, LIK_BERNOULLI> : nullptr;
+    return (ks == B2_STREAM_FAST_KS && lik == LIK_BERNOULLI) ? (const void*)stream_engine_kernel<B2_STREAM_FAST_KS, LIK_BERNOULLI, MG> : nullptr;
 #else
     switch (ks) {
-    case 1: return stream_kernel_lik<1>(lik);
-    case 2: return stream_kernel_lik<2>(lik);
-    case 4: return stream_kernel_lik<4>(lik);
-    case 7: return stream_kernel_lik<7>(lik);
-    case 8: return stream_kernel_lik<8>(lik);
+    case 1: return stream_kernel_lik<1, MG>(lik);
+    case 2: return stream_kernel_lik<2, MG>(lik);
+    case 4: return stream_kernel_lik<4, MG>(lik);
+    case 7: return stream_kernel_lik<7, MG>(lik);
+    case 8: return stream_kernel_lik<8, MG>(lik);
     default: return nullptr;
     }
 #endif
+}
+// one chain group (<= 8 chains): the group bookkeeping folds away; more: passes rotate over the groups
+static const void* stream_kernel_for(int ks, int lik, int num_groups) {
+    return num_groups > 1 ? stream_kernel_for_mg<true>(ks, lik) : stream_kernel_for_mg<false>(ks, lik);
 }
 
 static int stream_launch(B200Nuts* h, int mode, const OutBufs& out, const float* z_in, float* u_out, float* g_out,
@@ -234,7 +239,7 @@ static int stream_launch(B200Nuts* h, int mode, const OutBufs& out, const float*
     CK(cudaMemsetAsync(h->beta, 0, sizeof(uint4) * kBetaCopies * h->num_groups * kBetaWords, st));
     CK(cudaMemsetAsync(h->partial, 0, sizeof(float2) * (size_t)h->grid * h->num_groups * kStreamCT * kGStride, st));
     void* args[] = {&p};
-    const void* fn = stream_kernel_for(h->ks, h->fam.likelihood);
+    const void* fn = stream_kernel_for(h->ks, h->fam.likelihood, h->num_groups);
     if (!fn) { h->err = "stream regime: no kernel instance for this shape"; return B200NUTS_EINVAL; }
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     {
@@ -452,11 +457,11 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
         cudaFuncAttributes fa;
         const void* fns[] = {(const void*)k_chain_begin, (const void*)k_chain_resume, (const void*)k_warp_run, (const void*)k_potential_warp,
                              (const void*)k_leap_pre, (const void*)k_leap_post, (const void*)k_constrain,
-                             regime == B200NUTS_REGIME_STREAM ? stream_kernel_for(h->ks, h->fam.likelihood) : nullptr};
+                             regime == B200NUTS_REGIME_STREAM ? stream_kernel_for(h->ks, h->fam.likelihood, h->num_groups) : nullptr};
         for (const void* fn : fns)
             if (fn && (ce = cudaFuncGetAttributes(&fa, fn)) != cudaSuccess) return fail("cudaFuncGetAttributes", ce);
         if (regime == B200NUTS_REGIME_STREAM) {
-            const void* fn = stream_kernel_for(h->ks, h->fam.likelihood);
+            const void* fn = stream_kernel_for(h->ks, h->fam.likelihood, h->num_groups);
             if (!fn) { g_create_err = "stream regime: no kernel instance for this shape"; b200nuts_destroy(h); return B200NUTS_EINVAL; }
             if ((ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem)) != cudaSuccess) return fail("cudaFuncSetAttribute", ce);
         }

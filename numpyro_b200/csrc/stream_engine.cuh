@@ -350,8 +350,10 @@ struct StreamOne { static constexpr int value = 1; };
 struct StreamTwo { static constexpr int value = 2; };
 
 // KS = columns / 8 of the padded tile (compile time so every fragment stays in registers), LIK = likelihood.
-template <int KS, int LIK>
+// MG = several chain groups (more than 8 chains); with MG = false everything group-related folds to constants.
+template <int KS, int LIK, bool MG>
 __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const __grid_constant__ StreamParams p) {
+    const int NGRP = MG ? p.num_groups : 1;        // chain groups
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int P = stream_pitch(KS);            // row pitch of a tile, floats
     constexpr int TILE_FLOATS = stream_tile_floats(KS);   // floats moved per tile
@@ -418,7 +420,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         bool chain_done = !is_tick || (p.mode == 0 && c.phase == PH_DONE);
         // Passes rotate over the chain groups (8 chains each) that still have work; group g's r-th sweep uses the betas its
         // owners published with tag r.  With several groups the owners' ticks overlap with the other groups' sweeps.
-        const int NGRP = p.num_groups, my_group = cta / kStreamCT;
+        const int my_group = MG ? cta / kStreamCT : 0;
         unsigned int* rounds = (unsigned int*)(flags + 32);       // sweeps staged so far, per group (this warp's private copy)
         volatile int* started = flags + 8;
         uint32_t done_mask = 0u;                     // groups whose chains have all finished
@@ -637,9 +639,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
     int red_slot = 0, red_tile = -1;
 
     const bool dbg = (cta == 0 && ctid == 0);
-    long long t_prev = clock64();
-    const long long t_begin = t_prev;
-#define B2_DBG_LAP(k) do { if (dbg) { const long long t_now = clock64(); tdbg[k] += (unsigned long long)(t_now - t_prev); t_prev = t_now; } } while (0)
+    // (lap state lives in shared memory -- tdbg[14] last lap, tdbg[15] start -- so that it costs no registers in the sweep)
+    if (dbg) { tdbg[14] = (unsigned long long)clock64(); tdbg[15] = tdbg[14]; }
+#define B2_DBG_LAP(k) do { if (dbg) { const unsigned long long t_now = (unsigned long long)clock64(); tdbg[k] += t_now - tdbg[14]; tdbg[14] = t_now; } } while (0)
 
     // column of X behind n index `n` of backward N-tile `nt`
     auto bwd_col = [&](int nt, int n) { return (ODD && nt == KS - 1) ? 16 * NCH + n : 16 * (nt >> 1) + 2 * n + (nt & 1); };
@@ -762,15 +764,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         // ---- wait until this CTA's tick warp has staged every chain's beta of this pass
         if (ctid == 0) B2_TRACE(0, 1);
         bar_sync<kBarBeta, kStreamThreads>();
-        const int par = (int)(pass & 1u);
-        if (flags[par]) break;
-        const int grp = flags[2 + par];               // chain group served by this pass and the round (tag) of its sweep
-        const uint32_t tag = (uint32_t)flags[4 + par];
+        if (flags[pass & 1u]) break;
         if (ctid == 0) { *(volatile int*)(flags + 8) = (int)pass; B2_TRACE(0, 2); }
         if (ctid == 0) B2_DBG_LAP(0);
 #pragma unroll
         for (int kk = 0; kk < KS; ++kk) {                                   // beta -> B fragments (k = column, n = chain)
-            const uint4 w = bs[(size_t)par * kBetaWords + (kk * kStreamCT + g) * 4 + t];
+            const uint4 w = bs[(size_t)(pass & 1u) * kBetaWords + (kk * kStreamCT + g) * 4 + t];
             const float b0 = __uint_as_float(w.x), b1 = __uint_as_float(w.z);
             float l0, l1; tf32_lo2(b0, b1, l0, l1);
             bhi[kk][0] = w.x; bhi[kk][1] = w.z;
@@ -816,6 +815,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
             }
         }
         if (ctid == 0) { B2_DBG_LAP(1); B2_TRACE(0, 3); }
+        // (read after the sweep so that they do not occupy registers during it; the tick warp rewrites this pass's words only
+        //  after the consumers have begun the next pass)
+        const int grp = MG ? flags[2 + (pass & 1u)] : 0;       // chain group served by this pass and the round (tag) of its sweep
+        const uint32_t tag = (uint32_t)flags[4 + (pass & 1u)];
 
         // ---- reduce warps -> CTA through the ring slot every warp drained last ([value][lane] floats, conflict
         //      free), one barrier, fixed order => bit-reproducible; then publish {value, tag} pairs.
@@ -856,7 +859,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
 #pragma unroll
                     for (int w = 0; w < kConsWarps; ++w) a += tiles[((size_t)w * nst + flags[16 + w]) * SLOT_FLOATS + src];
                 }
-                __stcg(p.partial + (((size_t)cta * p.num_groups + grp) * kStreamCT + c) * kGStride + d, make_float2(a, __uint_as_float(tag)));
+                __stcg(p.partial + (((size_t)cta * NGRP + grp) * kStreamCT + c) * kGStride + d, make_float2(a, __uint_as_float(tag)));
             }
         }
         bar_sync<kBarCons, kConsThreads>();          // every scratch slot has been read: refill them
@@ -865,14 +868,14 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
 
         // ---- chain owner: poll the partials of all CTAs (tags ride in the data), sum them in fixed order,
         //      hand over to the tick warp
-        if (is_tick && cta / kStreamCT == grp) {
+        if (is_tick && (!MG || cta / kStreamCT == grp)) {
             const int o = ctid % 65, seg = ctid / 65;
             if (seg < kXSeg) {
                 // kXSeg segments x 65 outputs; each thread adds its segment's CTAs in ascending order.  All loads of a
                 // batch are in flight together (L2 latency overlapped); stale entries are simply polled again.
                 float a = 0.0f;
                 const int g0 = G * seg / kXSeg, g1 = G * (seg + 1) / kXSeg;
-                const float2* src = p.partial + ((size_t)grp * kStreamCT + (cta % kStreamCT)) * kGStride + o;
+                const float2* src = p.partial + ((size_t)grp * kStreamCT + (MG ? cta % kStreamCT : cta)) * kGStride + o;
                 const long long t_w = clock64();
                 for (int gg = g0; gg < g1; gg += 24) {
                     float2 v[24];
@@ -881,7 +884,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
 #pragma unroll
                         for (int k = 0; k < 24; ++k) {
                             if (gg + k < g1) {
-                                v[k] = ld_volatile_v2(src + (size_t)(gg + k) * ((size_t)p.num_groups * kStreamCT * kGStride));
+                                v[k] = ld_volatile_v2(src + (size_t)(gg + k) * ((size_t)NGRP * kStreamCT * kGStride));
                                 ok = ok && (__float_as_uint(v[k].y) == tag);
                             } else v[k] = make_float2(0.0f, 0.0f);
                         }
@@ -919,7 +922,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
     }
     if (cta == 0 && ctid == 0) {
         sy->passes = pass;
-        tdbg[5] = (unsigned long long)(clock64() - t_begin);
+        tdbg[5] = (unsigned long long)clock64() - tdbg[15];
         for (int i = 0; i < 16; ++i) sy->dbg[i] = tdbg[i];
     }
 #undef B2_DBG_LAP
