@@ -354,6 +354,9 @@ struct StreamTwo { static constexpr int value = 2; };
 template <int KS, int LIK, bool MG>
 __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const __grid_constant__ StreamParams p) {
     const int NGRP = MG ? p.num_groups : 1;        // chain groups
+    // With >= 3 groups the owners' consumers gather the partials of their chain one pass LATE (at the end of the next pass,
+    // when every CTA has long published them), so no CTA ever waits for the slowest CTA of a pass.
+    const bool DEFER = MG && NGRP >= 3;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int P = stream_pitch(KS);            // row pitch of a tile, floats
     constexpr int TILE_FLOATS = stream_tile_floats(KS);   // floats moved per tile
@@ -426,6 +429,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         uint32_t done_mask = 0u;                     // groups whose chains have all finished
         uint32_t my_round = 0u;                      // round of my group's sweep that is waiting for its tick
         bool pending = false;                        // ... and whether there is one
+        int pending_pass = 0;                        // ... and the pass that swept it
         int cur = 0, qpass = 0, status = 0;
         if (is_tick) {                               // prologue: the first beta
             const float* zsrc = (p.mode == 0) ? cv.v(V_ZS) : (p.z_in + (size_t)cta * p.cfg.D);
@@ -512,7 +516,28 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                 if (staged == 1) continue;
                 if (staged == 2) break;
             }
-            if (pending) {
+            if (tick_first && DEFER && pending_pass == qpass - 1) {
+                // deferred gather, but no other group is left to sweep meanwhile: a flush pseudo-pass (status 3) makes this
+                // CTA's consumers gather the partials of the sweep that just ended
+                const long long t_w = clock64();
+                while (true) {
+                    const int ready = __shfl_sync(0xFFFFFFFFu, (*started >= qpass - 1) ? 1 : 0, 0);
+                    if (ready) break;
+                    __nanosleep(256);
+                    bool give_up = ld_acquire(&sy->abort_flag) != 0u;
+                    if (clock64() - t_w > 4 * p.spin_limit) { atomicCAS(&sy->abort_flag, 0u, 2u); give_up = true; }
+                    if (__any_sync(0xFFFFFFFFu, give_up)) { status = 2; break; }
+                }
+                if (status == 0) {
+                    if (lane == 0) flags[qpass & 1] = 3;
+                    warp_sync_hard();
+                    bar_arrive<kBarBeta, kStreamThreads>();
+                    ++qpass; ++pass;
+                }
+            }
+            // (deferred gather: the consumers deliver the sums at the end of the pass AFTER my group's sweep, so the tick waits
+            //  until one more pass has been staged for them -- otherwise they would sit idle while this warp ticks)
+            if (pending && status == 0 && (tick_first || !DEFER || qpass - pending_pass >= 2)) {
                 // ---- the tick of this CTA's chain after a sweep of its group: reduced likelihood sums -> potential -> NUTS
                 //      state machine -> next beta (tag my_round + 1)
                 const uint32_t seq = my_round;
@@ -588,7 +613,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                 if (staged == 2) break;
             }
             if (is_tick && grp == my_group) {
-                pending = true; my_round = need;
+                pending = true; my_round = need; pending_pass = qpass;
                 if (p.mode == 0 && !chain_done && !p.no_prefetch) tk.prefetch();     // off the critical path: PRNG look-ahead
             }
             cur = (grp + 1) % NGRP; ++qpass; ++pass;
@@ -764,9 +789,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         // ---- wait until this CTA's tick warp has staged every chain's beta of this pass
         if (ctid == 0) B2_TRACE(0, 1);
         bar_sync<kBarBeta, kStreamThreads>();
-        if (flags[pass & 1u]) break;
+        const int st = flags[pass & 1u];
+        if (st == 1 || st == 2) break;
+        const bool real = !MG || st == 0;             // (3: flush pseudo-pass of the deferred gather -- nothing to sweep)
         if (ctid == 0) { *(volatile int*)(flags + 8) = (int)pass; B2_TRACE(0, 2); }
         if (ctid == 0) B2_DBG_LAP(0);
+        int grp = 0; uint32_t tag = 0u;
+        if (real) {
 #pragma unroll
         for (int kk = 0; kk < KS; ++kk) {                                   // beta -> B fragments (k = column, n = chain)
             const uint4 w = bs[(size_t)(pass & 1u) * kBetaWords + (kk * kStreamCT + g) * 4 + t];
@@ -817,8 +846,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         if (ctid == 0) { B2_DBG_LAP(1); B2_TRACE(0, 3); }
         // (read after the sweep so that they do not occupy registers during it; the tick warp rewrites this pass's words only
         //  after the consumers have begun the next pass)
-        const int grp = MG ? flags[2 + (pass & 1u)] : 0;       // chain group served by this pass and the round (tag) of its sweep
-        const uint32_t tag = (uint32_t)flags[4 + (pass & 1u)];
+        grp = MG ? flags[2 + (pass & 1u)] : 0;        // chain group served by this pass and the round (tag) of its sweep
+        tag = (uint32_t)flags[4 + (pass & 1u)];
 
         // ---- reduce warps -> CTA through the ring slot every warp drained last ([value][lane] floats, conflict
         //      free), one barrier, fixed order => bit-reproducible; then publish {value, tag} pairs.
@@ -866,16 +895,27 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         if (lane == 0 && red_tile >= 0 && p.dbg_sweep != 2) issue(red_slot, red_tile);
         if (ctid == 0) { B2_DBG_LAP(2); B2_TRACE(0, 4); }
 
+        }   // real pass
         // ---- chain owner: poll the partials of all CTAs (tags ride in the data), sum them in fixed order,
-        //      hand over to the tick warp
-        if (is_tick && (!MG || cta / kStreamCT == grp)) {
+        //      hand over to the tick warp.  Deferred mode: gather what the PREVIOUS pass left, note what this one leaves.
+        int ggrp = grp; uint32_t gtag = tag;
+        bool do_g = is_tick && real && (!MG || cta / kStreamCT == grp);
+        if (DEFER) {
+            const int* dprev = flags + 10 + 3 * (int)((pass + 1u) & 1u);
+            do_g = is_tick && dprev[0] != 0; ggrp = dprev[1]; gtag = (uint32_t)dprev[2];
+            if (ctid == 0) {
+                int* dcur = flags + 10 + 3 * (int)(pass & 1u);
+                dcur[0] = (is_tick && real && cta / kStreamCT == grp) ? 1 : 0; dcur[1] = grp; dcur[2] = (int)tag;
+            }
+        }
+        if (do_g) {
             const int o = ctid % 65, seg = ctid / 65;
             if (seg < kXSeg) {
                 // kXSeg segments x 65 outputs; each thread adds its segment's CTAs in ascending order.  All loads of a
                 // batch are in flight together (L2 latency overlapped); stale entries are simply polled again.
                 float a = 0.0f;
                 const int g0 = G * seg / kXSeg, g1 = G * (seg + 1) / kXSeg;
-                const float2* src = p.partial + ((size_t)grp * kStreamCT + (MG ? cta % kStreamCT : cta)) * kGStride + o;
+                const float2* src = p.partial + ((size_t)ggrp * kStreamCT + (MG ? cta % kStreamCT : cta)) * kGStride + o;
                 const long long t_w = clock64();
                 for (int gg = g0; gg < g1; gg += 24) {
                     float2 v[24];
@@ -885,7 +925,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                         for (int k = 0; k < 24; ++k) {
                             if (gg + k < g1) {
                                 v[k] = ld_volatile_v2(src + (size_t)(gg + k) * ((size_t)NGRP * kStreamCT * kGStride));
-                                ok = ok && (__float_as_uint(v[k].y) == tag);
+                                ok = ok && (__float_as_uint(v[k].y) == gtag);
                             } else v[k] = make_float2(0.0f, 0.0f);
                         }
                         if (ok) break;

@@ -22,4 +22,7 @@ for C in [int(a) for a in sys.argv[1:]] or [8, 16, 32]:
     passes = e.pass_count - p0; ms = t0.elapsed_time(t1); leap = int(out["num_steps"].sum().item())
     print(f"chains {C:3d}: passes {passes} us/pass {ms * 1e3 / passes:.2f} grad-evals/s {leap / ms * 1e3:,.0f} "
           f"(evals/pass {leap / passes:.2f}) achieved {passes * 127822640 / ms / 1e6:.0f} GB/s = {passes * 127822640 / ms / 1e6 / 6545.6:.1%} of HBM roofline", flush=True)
+    names = ["wait_beta", "sweep", "cta_reduce+publish", "wait_partials", "xcta_reduce", "total", "tick_busy", "beta_frags"]
+    dbg = e.debug_clocks().astype(np.float64)
+    print("      cta0 cycles/pass:", {n: round(dbg[i] / passes) for i, n in enumerate(names)}, flush=True)
     e.close()

@@ -257,7 +257,7 @@ def test_stream_regime_run_bit_exact():
     assert sum(int(st[c].total_leapfrogs) for c in range(C)) > 0
 
 
-@pytest.mark.parametrize("C", [9, 20])
+@pytest.mark.parametrize("C", [9, 20, 33])
 def test_stream_regime_many_chains_rotating_groups(C):
     """More than 8 chains in the streaming engine: passes rotate over chain groups of 8 (the owners' ticks overlap with
     the other groups' sweeps).  Potentials of every chain, whole runs bit-exact against the oracle, and chain c of the
