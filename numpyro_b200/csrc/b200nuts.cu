@@ -426,13 +426,19 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
         cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
         h->ks = stream_ks_for(h->fam.Dx);
         h->stages = 0;
+        const bool mg = h->C > kStreamCT;
         for (int vs = 1; vs >= 0 && !h->stages; --vs)
             for (int stg = kMaxStages; stg >= 2; --stg)      // slots per consumer warp: one in use, the others in flight
-                if (stream_smem_bytes(h->ks, h->Dp, stg, vs != 0) <= (size_t)max_smem) {
+                if (stream_smem_bytes(h->ks, h->Dp, stg, vs != 0, mg) <= (size_t)max_smem) {
                     h->stages = stg; h->vecs_in_smem = vs; break;
                 }
         if (!h->stages) { g_create_err = "stream regime: shared memory budget exceeded"; b200nuts_destroy(h); return B200NUTS_EINVAL; }
-        h->smem = stream_smem_bytes(h->ks, h->Dp, h->stages, h->vecs_in_smem != 0);
+        // experiments: force a ring depth / where the chain vectors live (the combination must fit)
+        if (const char* e = getenv("B200NUTS_FORCE_STAGES")) {
+            const int stg = atoi(e); const char* v = getenv("B200NUTS_FORCE_VECS_SMEM"); const int vs = v ? atoi(v) : h->vecs_in_smem;
+            if (stg >= 2 && stg <= kMaxStages && stream_smem_bytes(h->ks, h->Dp, stg, vs != 0, mg) <= (size_t)max_smem) { h->stages = stg; h->vecs_in_smem = vs; }
+        }
+        h->smem = stream_smem_bytes(h->ks, h->Dp, h->stages, h->vecs_in_smem != 0, mg);
         // engine-owned tile image of (X, y): one contiguous block per 32 rows (stream_engine.cuh)
         h->n_tiles = (h->fam.N + kTileRows - 1) / kTileRows;
         h->pad_rows = (int)(h->n_tiles * kTileRows - h->fam.N);

@@ -266,17 +266,17 @@ B2_D bool spin_ge(const unsigned int* ctr, unsigned int target, StreamSync* sy, 
 
 #define B2_TRACE_LANES(stage) do { if (lane == 0) B2_TRACE(1, stage); if (lane == 16) B2_TRACE(4, stage); if (lane == 31) B2_TRACE(5, stage); } while (0)
 
-B2_HD size_t stream_fixed_smem(int Dp, bool vecs_in_smem) {
+B2_HD size_t stream_fixed_smem(int Dp, bool vecs_in_smem, bool multi_group) {
     size_t b = 0;
     b += (size_t)kConsWarps * kMaxStages * 8;                      // mbarriers
-    b += (size_t)2 * kBetaWords * 16;                              // staged beta (two passes), [k-step][chain][t] {b0, tag, b1, tag}
+    b += (size_t)(multi_group ? 2 : 1) * kBetaWords * 16;          // staged beta (two passes with several groups), [k-step][chain][t] {b0, tag, b1, tag}
     b += (size_t)kXRedFloats * 4;                                  // cross-CTA reduction + tick scratch
     b += 64 * 4 + 64 * 4 + 256 + 128;                              // gred(+nll), flags, timers
     if (vecs_in_smem) b += (size_t)V_COUNT * Dp * 4;
     return b + 128;
 }
-B2_HD size_t stream_smem_bytes(int KS, int Dp, int stages, bool vecs_in_smem) {
-    return stream_fixed_smem(Dp, vecs_in_smem) + (size_t)kConsWarps * stages * stream_slot_floats(KS) * 4;
+B2_HD size_t stream_smem_bytes(int KS, int Dp, int stages, bool vecs_in_smem, bool multi_group) {
+    return stream_fixed_smem(Dp, vecs_in_smem, multi_group) + (size_t)kConsWarps * stages * stream_slot_floats(KS) * 4;
 }
 
 // One-time repack of the caller's (X, y) into the tile image (see the header comment).
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
     unsigned char* q = smem_raw;
     float* tiles = (float*)q; q += (size_t)kConsWarps * nst * SLOT_FLOATS * 4;
     uint64_t* full = (uint64_t*)q; q += (size_t)kConsWarps * kMaxStages * 8;
-    uint4* bs = (uint4*)q; q += (size_t)2 * kBetaWords * 16;
+    uint4* bs = (uint4*)q; q += (size_t)(MG ? 2 : 1) * kBetaWords * 16;
     float* xred = (float*)q; q += (size_t)kXRedFloats * 4;
     float* gred = (float*)q; q += 64 * 4 + 64 * 4;
     int* flags = (int*)q; q += 256;                  // per pass parity: [0..1] 0 go / 1 all chains done / 2 abort, [2..3] chain group, [4..5] its round;
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                     if (__any_sync(0xFFFFFFFFu, give_up)) { status = 2; break; }
                 }
             }
-            uint4* bsq = bs + (size_t)(qpass & 1) * kBetaWords;
+            uint4* bsq = bs + (size_t)(MG ? (qpass & 1) : 0) * kBetaWords;
             need = 0u;
             if (status == 0) {
                 // fetch the betas of group `grp` for its next sweep (tags ride in the data: poll until they all match)
@@ -798,7 +798,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         if (real) {
 #pragma unroll
         for (int kk = 0; kk < KS; ++kk) {                                   // beta -> B fragments (k = column, n = chain)
-            const uint4 w = bs[(size_t)(pass & 1u) * kBetaWords + (kk * kStreamCT + g) * 4 + t];
+            const uint4 w = bs[(size_t)(MG ? (pass & 1u) : 0u) * kBetaWords + (kk * kStreamCT + g) * 4 + t];
             const float b0 = __uint_as_float(w.x), b1 = __uint_as_float(w.z);
             float l0, l1; tf32_lo2(b0, b1, l0, l1);
             bhi[kk][0] = w.x; bhi[kk][1] = w.z;
