@@ -467,6 +467,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                 const long long t_w = clock64();
                 while (true) {
                     bool ok = true;
+                    // (the abort flag travels in the same batch of loads: one L2 round trip per poll, not two)
+                    const unsigned int aborted = ld_acquire(&sy->abort_flag);
 #pragma unroll
                     for (int kk = 0; kk < KS; ++kk) {
                         w[kk] = ld_volatile_v4(bsrc + lane + 32 * kk);
@@ -479,7 +481,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                     }
                     if (__all_sync(0xFFFFFFFFu, ok)) break;
                     // (warp-uniform exits: a lane that left alone would deadlock the __all_sync above)
-                    bool give_up = ld_acquire(&sy->abort_flag) != 0u;
+                    bool give_up = aborted != 0u;
                     if (clock64() - t_w > p.spin_limit) { atomicCAS(&sy->abort_flag, 0u, 2u); give_up = true; }
                     if (__any_sync(0xFFFFFFFFu, give_up)) { status = 2; break; }
                 }
@@ -488,9 +490,15 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                     done_mask |= 1u << grp; cur = (grp + 1) % NGRP;
                     return 1;
                 }
+                // staged in the form the consumers' B fragments need: {b0, b1 (raw fp32 bits = the tf32 operand),
+                // bf16x2(hi parts), bf16x2(lo parts)} -- split once here instead of in every consumer lane
                 const bool zero = absent || status == 2;
 #pragma unroll
-                for (int kk = 0; kk < KS; ++kk) bsq[lane + 32 * kk] = zero ? make_uint4(0u, 0u, 0u, 0u) : w[kk];
+                for (int kk = 0; kk < KS; ++kk) {
+                    const float b0 = __uint_as_float(w[kk].x), b1 = __uint_as_float(w[kk].z);
+                    float l0, l1; tf32_lo2(b0, b1, l0, l1);
+                    bsq[lane + 32 * kk] = zero ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(w[kk].x, w[kk].z, pack_bf16(b0 - l0, b1 - l1), pack_bf16(l0, l1));
+                }
             }
             if (lane == 0) {
                 flags[qpass & 1] = status; flags[2 + (qpass & 1)] = grp; flags[4 + (qpass & 1)] = (int)need;
@@ -799,11 +807,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
 #pragma unroll
         for (int kk = 0; kk < KS; ++kk) {                                   // beta -> B fragments (k = column, n = chain)
             const uint4 w = bs[(size_t)(MG ? (pass & 1u) : 0u) * kBetaWords + (kk * kStreamCT + g) * 4 + t];
-            const float b0 = __uint_as_float(w.x), b1 = __uint_as_float(w.z);
-            float l0, l1; tf32_lo2(b0, b1, l0, l1);
-            bhi[kk][0] = w.x; bhi[kk][1] = w.z;
-            bbf[kk][0] = pack_bf16(b0 - l0, b1 - l1);                       // pairs with xl (k = 2t, 2t+1)
-            bbf[kk][1] = pack_bf16(l0, l1);                                 // pairs with x  (k = 2t+8, 2t+9)
+            bhi[kk][0] = w.x; bhi[kk][1] = w.y;                             // staged pre-split by the tick warp
+            bbf[kk][0] = w.z;                                               // hi parts: pairs with xl (k = 2t, 2t+1)
+            bbf[kk][1] = w.w;                                               // lo parts: pairs with x  (k = 2t+8, 2t+9)
         }
 #pragma unroll
         for (int nt = 0; nt < KS; ++nt) { gacc[nt][0] = 0.0f; gacc[nt][1] = 0.0f; gacc[nt][2] = 0.0f; gacc[nt][3] = 0.0f; }

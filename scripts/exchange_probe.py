@@ -5,7 +5,7 @@ import numpy as np, torch
 from numpyro_b200 import _capi, engine as eng
 from oracle import prng
 F = np.float32
-N, D, C = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 15 * 16, 54, 8
+N, D, C = 148 * 15 * 16, (int(sys.argv[1]) if len(sys.argv) > 1 else 54), 8
 rng = np.random.default_rng(1)
 X = rng.standard_normal(size=(N, D), dtype=F)
 beta = (rng.normal(size=D) * 0.3).astype(F)
