@@ -118,9 +118,10 @@ def test_sharded_potential_identical_on_all_ranks_and_equal_to_unsharded(devices
     rk.close()
 
 
+@pytest.mark.parametrize("C", [3, 12])                    # 12 chains = two chain groups with rotating passes
 @pytest.mark.parametrize("devices", _layouts())
-def test_sharded_run_bit_identical_across_ranks_and_bit_exact_against_oracle(devices, half_grid):
-    N, D, C = 9000, 7, 3
+def test_sharded_run_bit_identical_across_ranks_and_bit_exact_against_oracle(devices, C, half_grid):
+    N, D = 9000, 7
     X, y = _data(N, D, 4)
     rk = Ranks(X, y, C, [0, 4000, N], devices, max_tree_depth_warmup=5, max_tree_depth=5)
     keys = prng.split(prng.key(7), C)
@@ -137,10 +138,11 @@ def test_sharded_run_bit_identical_across_ranks_and_bit_exact_against_oracle(dev
             U, g = rk.each(lambda e: tuple(t.cpu().numpy() for t in e.potential_and_grad(zz)))[0]
             return F(U[c]), g[c]
         return pot
-    kern = chain.Kernel(device_potential(1), max_tree_depth=(5, 5))
-    res, _ = chain.run_chain(kern, fam, keys[1], 40, 20, fields=FIELDS)
+    cc = C - 2
+    kern = chain.Kernel(device_potential(cc), max_tree_depth=(5, 5))
+    res, _ = chain.run_chain(kern, fam, keys[cc], 40, 20, fields=FIELDS)
     for f in FIELDS:
-        assert np.array_equal(outs[0][f][1], res[f]), f
+        assert np.array_equal(outs[0][f][cc], res[f]), f
     rk.close()
 
 
