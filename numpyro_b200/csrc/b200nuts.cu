@@ -315,8 +315,8 @@ static int check_stream_abort(B200Nuts* h, cudaStream_t st) {
     }
 #ifdef B2_TICK_LAPS
     if (getenv("B200NUTS_DEBUG_TICK") && s.passes) {
-        fprintf(stderr, "[b200nuts] chain 0 tick laps per pass:");
-        for (int k = 0; k < 16; ++k) fprintf(stderr, " [%d] %.0f", k, (double)s.laps[k] / (double)s.passes);
+        fprintf(stderr, "[b200nuts] chain 0 tick laps, cycles per occurrence (occurrences):");
+        for (int k = 0; k < 16; ++k) if (s.laps[16 + k]) fprintf(stderr, " [%d] %.0f (%llu)", k, (double)s.laps[k] / (double)s.laps[16 + k], s.laps[16 + k]);
         fprintf(stderr, "\n");
     }
 #endif

@@ -94,7 +94,7 @@ B2_HD constexpr int stream_ks_for(int D) { return D <= 8 ? 1 : D <= 16 ? 2 : D <
 struct StreamSync { unsigned int abort_flag, pad_[3]; unsigned long long passes; unsigned long long dbg[16];
                     unsigned long long tick_sum[kMaxStreamChains], tick_max[kMaxStreamChains], tick_lap[kMaxStreamChains][4];
                     unsigned int pre_hit[kMaxStreamChains][4], pre_miss[kMaxStreamChains][4];
-                    unsigned long long laps[16]; };     // -DB2_TICK_LAPS builds only   // per owner CTA: tick cycles, look-ahead hits
+                    unsigned long long laps[32]; };     // -DB2_TICK_LAPS builds only: [i] cycles, [16 + i] occurrences   // per owner CTA: tick cycles, look-ahead hits
 
 struct StreamParams {
     TickCfg cfg; FamilySpec fam; OutBufs out;
@@ -436,6 +436,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
             stream_publish_beta(p, cta, zsrc, !chain_done, 1u | (chain_done ? 0x80000000u : 0u));
         }
         const int my_chain = (lane >> 2) & 7;         // chain slot of this lane's words (word w = lane + 32 kk)
+#ifdef B2_TICK_LAPS
+        if (cta == 0 && lane == 0) for (int k = 0; k < 34; ++k) b2_lap_store()[k] = 0ull;
+        __syncwarp();
+#endif
 
         uint32_t need = 0u;                          // round (= beta tag) of the sweep being staged
         int grp = -1;
@@ -551,6 +555,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                 const uint32_t seq = my_round;
                 B2_TRACE_LANES(3);
                 bar_sync<kBarTick, kStreamThreads>();    // segment sums are in `xred`
+                B2_LAPQ(-1);
                 B2_TRACE_LANES(4);
                 const long long t_a = clock64();
                 // (uniform trip count + shuffle broadcast on purpose: ptxas 12.9 turned the __syncwarp() after the
@@ -601,11 +606,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                 }
                 const float nll = __shfl_sync(0xFFFFFFFFu, a64, 0) - (p.shard_count > 1 ? 0.0f : pad_nll);
                 if (lane == 0) tlap[3] += (unsigned long long)(clock64() - t_a);
+                B2_LAPQ(6);
                 float* gz = xred + kXSeg * kGStride; // scratch for the gradient wrt z (<= Dp floats)
                 if (!chain_done) chain_done = stream_tick_step(p, tk, gred, gz, nll, cta, tdbg, pass);
                 B2_TRACE_LANES(5);
                 const long long t_p = clock64();
                 stream_publish_beta(p, cta, cv.v(V_ZS), !chain_done, (seq + 1u) | (chain_done ? 0x80000000u : 0u));
+                B2_LAPQ(7);
                 if (lane == 0) {
                     const long long t_e = clock64();
                     tlap[2] += (unsigned long long)(t_e - t_p);
@@ -628,7 +635,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         }
         B2_TRACE_LANES(6);
 #ifdef B2_TICK_LAPS
-        if (cta == 0 && lane == 0) for (int k = 0; k < 16; ++k) { sy->laps[k] = b2_tick_laps[k]; b2_tick_laps[k] = 0ull; }
+        if (cta == 0 && lane == 0) for (int k = 0; k < 32; ++k) sy->laps[k] = b2_lap_store()[k];
 #endif
         if (is_tick && lane == 0) {
             if (p.mode == 0) p.ctl[cta] = c;

@@ -141,11 +141,16 @@ B2_HD void leap_begin(int D, float eps, const float* imm, const float* z, const 
 
 // development only (-DB2_TICK_LAPS): clock64 laps of chain 0's tick, see scripts/exchange_probe.py
 #if defined(__CUDACC__) && defined(B2_TICK_LAPS)
-__device__ unsigned long long b2_tick_laps[16];
-__device__ long long b2_tick_t0;
+// accumulators in shared memory (cheap: no global round trip inside the measured code); [i] cycles, [16 + i] occurrences
+__device__ inline unsigned long long* b2_lap_store() { __shared__ unsigned long long s_[34]; return s_; }
 __host__ __device__ inline void b2_lapq(int i) {
 #if defined(__CUDA_ARCH__)
-    if (blockIdx.x == 0 && (threadIdx.x & 31u) == 0u) { const long long t_ = clock64(); if (i >= 0) b2_tick_laps[i] += (unsigned long long)(t_ - b2_tick_t0); b2_tick_t0 = t_; }
+    if (blockIdx.x == 0 && (threadIdx.x & 31u) == 0u) {
+        unsigned long long* s_ = b2_lap_store();
+        const unsigned long long t_ = (unsigned long long)clock64();
+        if (i >= 0) { s_[i] += t_ - s_[32]; s_[16 + i] += 1ull; }
+        s_[32] = t_;
+    }
 #endif
 }
 #define B2_LAPQ(i) b2_lapq(i)
