@@ -328,8 +328,114 @@ struct Tick {
         c.phase = PH_LEAF;
     }
 
+#if defined(__CUDA_ARCH__)
+    // on_leaf for D <= 64 (two elements per lane) with the chain vectors held in registers: every vector is loaded once
+    // (all loads in flight together), the leaf's arithmetic runs on registers, results are stored once.  Same expressions in
+    // the same order per element and per reduction as the generic on_leaf below => identical bits (the GPU parity tests
+    // compare whole runs with the oracle, which follows the generic form).
+    __device__ __forceinline__ void on_leaf_fused(float u, const float* g) {
+        const int Dn = cfg.D;
+        const int lane = (int)(threadIdx.x & 31u);
+        const int d0 = lane, d1 = lane + 32;
+        const bool a0 = d0 < Dn, a1 = d1 < Dn;
+        const float e = c.going_right ? c.eps : -c.eps;
+        const float half = 0.5f * e;
+        const float* imm = v(V_IMM);
+        float *zs = v(V_ZS), *rs = v(V_RS), *gs = v(V_GS);
+        float *zps = v(V_ZPS), *gps = v(V_GPS), *rsum_s = v(V_RSUMS);
+        B2_LAPQ(-1);
+        float g0 = 0.0f, g1 = 0.0f, r0 = 0.0f, r1 = 0.0f, i0 = 0.0f, i1 = 0.0f, z0 = 0.0f, z1 = 0.0f, q0 = 0.0f, q1 = 0.0f;
+        if (a0) { g0 = g[d0]; r0 = rs[d0]; i0 = imm[d0]; z0 = zs[d0]; q0 = rsum_s[d0]; }
+        if (a1) { g1 = g[d1]; r1 = rs[d1]; i1 = imm[d1]; z1 = zs[d1]; q1 = rsum_s[d1]; }
+        r0 = r0 - half * g0; r1 = r1 - half * g1;
+        c.total_leapfrogs += 1ull;
+        float pk = 0.0f;                                           // kinetic(): lane partial in element order, then the butterfly
+        if (a0) pk = pk + (i0 * r0) * r0;
+        if (a1) pk = pk + (i1 * r1) * r1;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) pk = pk + __shfl_xor_sync(0xFFFFFFFFu, pk, off);
+        const float energy_new = u + 0.5f * pk;
+        B2_LAPQ(0);
+        float delta = energy_new - c.energy0;
+        if (is_nan(delta)) delta = f_inf();
+        const float leaf_w = -delta;
+        const int leaf_div = (delta > 1000.0f) ? 1 : 0;
+        const float leaf_acc = clip_max1(d_exp(-delta));
+        const Key ks = mk(c.k_sub);
+        float u_leaf;
+        if ((c.pre_mask & 1u) && key_is(c.pl_from, ks)) { st(c.k_sub, mk(c.pl_ksub)); u_leaf = c.pl_u; c.pre_hit[0] += 1u; }
+        else { c.pre_miss[0] += 1u; const Key k_leaf = split_at(ks, 1); st(c.k_sub, split_at(ks, 0)); u_leaf = uniform01_at(k_leaf, 0); }
+        B2_LAPQ(1);
+        const int leaf_idx = c.n_sub;
+        bool store_prop;
+        if (leaf_idx == 0) {
+            store_prop = true; q0 = r0; q1 = r1;
+            c.sub_prop_pe = u; c.sub_prop_energy = energy_new;
+            c.sub_weight = leaf_w; c.sub_sum_acc = leaf_acc;
+        } else {                                                   // _combine_tree, uniform kernel
+            const float p = d_expit(leaf_w - c.sub_weight);
+            store_prop = u_leaf < p;
+            if (store_prop) { c.sub_prop_pe = u; c.sub_prop_energy = energy_new; }
+            q0 = q0 + r0; q1 = q1 + r1;
+            c.sub_weight = d_logaddexp(c.sub_weight, leaf_w);
+            c.sub_sum_acc = c.sub_sum_acc + leaf_acc;
+        }
+        if (a0) { gs[d0] = g0; rsum_s[d0] = q0; if (store_prop) { zps[d0] = z0; gps[d0] = g0; } }
+        if (a1) { gs[d1] = g1; rsum_s[d1] = q1; if (store_prop) { zps[d1] = z1; gps[d1] = g1; } }
+        B2_LAPQ(2);
+        c.sub_div = leaf_div;
+        c.n_sub = leaf_idx + 1;
+        const uint32_t n = (uint32_t)leaf_idx;
+        const int idx_max = popc32(n >> 1);
+        const int idx_min = idx_max - popc32((~n & (n + 1u)) - 1u) + 1;
+        if ((leaf_idx & 1) == 0) {
+            float* cr = v(V_CKPT_R + idx_max); float* cs = v(V_CKPT_RSUM + idx_max);
+            if (a0) { cr[d0] = r0; cs[d0] = q0; }
+            if (a1) { cr[d1] = r1; cs[d1] = q1; }
+        }
+        bool sub_turning = false;
+        for (int i = idx_max; i >= idx_min && !sub_turning; --i) {
+            const float* cr = v(V_CKPT_R + i); const float* cs = v(V_CKPT_RSUM + i);
+            float pl = 0.0f, pr = 0.0f;
+            if (a0) {
+                const float c_r = cr[d0], c_s = cs[d0];
+                const float sub = (q0 - c_s) + c_r;
+                const float sm = sub - (c_r + r0) / 2.0f;
+                pl = pl + (i0 * c_r) * sm; pr = pr + (i0 * r0) * sm;
+            }
+            if (a1) {
+                const float c_r = cr[d1], c_s = cs[d1];
+                const float sub = (q1 - c_s) + c_r;
+                const float sm = sub - (c_r + r1) / 2.0f;
+                pl = pl + (i1 * c_r) * sm; pr = pr + (i1 * r1) * sm;
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                pl = pl + __shfl_xor_sync(0xFFFFFFFFu, pl, off);
+                pr = pr + __shfl_xor_sync(0xFFFFFFFFu, pr, off);
+            }
+            sub_turning = (pl <= 0.0f) || (pr <= 0.0f);
+        }
+        B2_LAPQ(3);
+        if (c.n_sub < (1 << c.depth) && !sub_turning && !c.sub_div) {      // next leaf of this subtree: leap_begin in registers
+            const float h0 = r0 - half * g0, h1 = r1 - half * g1;
+            if (a0) { rs[d0] = h0; zs[d0] = z0 + e * (i0 * h0); }
+            if (a1) { rs[d1] = h1; zs[d1] = z1 + e * (i1 * h1); }
+            B2_LAPQ(4);
+            return;
+        }
+        if (a0) rs[d0] = r0;
+        if (a1) rs[d1] = r1;
+        finish_doubling(sub_turning);
+        B2_LAPQ(5);
+    }
+#endif
+
     // one iteration of _iterative_build_subtree's loop body, after the gradient arrived
     B2_HD void on_leaf(float u, const float* g) {
+#if defined(__CUDA_ARCH__)
+        if (cfg.D <= 64) { on_leaf_fused(u, g); return; }
+#endif
         const int Dn = cfg.D;
         const float e = c.going_right ? c.eps : -c.eps;
         const float half = 0.5f * e;

@@ -257,6 +257,23 @@ def test_stream_regime_run_bit_exact():
     assert sum(int(st[c].total_leapfrogs) for c in range(C)) > 0
 
 
+def test_stream_and_warp_runs_bit_exact_with_two_elements_per_lane():
+    """32 < D <= 64: every lane of the chain's warp owns two coefficients (the register-resident leaf update)."""
+    rng = np.random.default_rng(77)
+    N, D, C = 5000, 40, 2
+    X = (rng.normal(size=(N, D)) * 0.7).astype(F)
+    y = (rng.uniform(size=N) < 1 / (1 + np.exp(-(X @ (rng.normal(size=D) * 0.4))))).astype(F)
+    fam = families.logistic_regression(X, y)
+    keys = prng.split(prng.key(21), C)
+    for regime in (_capi.REGIME_STREAM, _capi.REGIME_WARP):
+        e = glm_engine(C, X, y, regime=regime, max_tree_depth_warmup=5, max_tree_depth=5)
+        e.init(keys, 25)
+        out = e.run(40, 25, fields=FIELDS)
+        kern = chain.Kernel(device_potential(e, 1), max_tree_depth=(5, 5))
+        res, _ = chain.run_chain(kern, fam, keys[1], 25, 15, fields=FIELDS)
+        assert_run_equal(out, res, 1)
+
+
 @pytest.mark.parametrize("C", [9, 20, 33])
 def test_stream_regime_many_chains_rotating_groups(C):
     """More than 8 chains in the streaming engine: passes rotate over chain groups of 8 (the owners' ticks overlap with
