@@ -104,6 +104,29 @@ B2_HD void glm_coef(const FamilySpec& f, const float* z, float* beta) {
 // nll / gbeta are the raw likelihood sums (for LIK_NORMAL: 0.5*sum res^2 and X^T res).
 B2_HD void glm_finish(const FamilySpec& f, const float* z, float nll, const float* gbeta, float& u_out, float* g) {
     const int Dx = f.Dx;
+#if defined(__CUDA_ARCH__)
+    if (f.off_lambda < 0 && f.gscale == SCALE_NONE && f.likelihood != LIK_NORMAL && Dx <= 64) {
+        // plain GLM (coefs ~ N(0, 1)) with at most two coefficients per lane: loads first, then the same arithmetic as below
+        // (lane partial in element order + butterfly; scale = 1, prec = 1 multiplications kept so that the bits agree)
+        const int lane = (int)(threadIdx.x & 31u);
+        const int d0 = lane, d1 = lane + 32;
+        const bool a0 = d0 < Dx, a1 = d1 < Dx;
+        float z0 = 0.0f, z1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
+        if (a0) { z0 = z[f.off_u + d0]; b0 = gbeta[d0]; }
+        if (a1) { z1 = z[f.off_u + d1]; b1 = gbeta[d1]; }
+        float acc = 0.0f;
+        if (a0) acc = acc + (0.5f * z0) * z0;
+        if (a1) acc = acc + (0.5f * z1) * z1;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc = acc + __shfl_xor_sync(0xFFFFFFFFu, acc, off);
+        float U = acc + (float)Dx * kLogSqrt2Pi;
+        if (a0) g[f.off_u + d0] = z0 + 1.0f * (1.0f * b0);
+        if (a1) g[f.off_u + d1] = z1 + 1.0f * (1.0f * b1);
+        U = U + (nll + f.nll_const);
+        u_out = U;
+        return;
+    }
+#endif
     float prec = 1.0f;
     if (f.likelihood == LIK_NORMAL) prec = expf(z[f.off_prec]);
     // coefficient block: u ~ N(0, 1)

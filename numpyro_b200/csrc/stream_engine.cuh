@@ -309,8 +309,13 @@ B2_D void stream_publish_beta(const StreamParams& p, int chain, const float* zsr
     const int kk = lane >> 2, t = lane & 3;              // 8 k-steps x 4 = 32 lanes
     const int d0 = 8 * kk + 2 * t;
     float b0 = 0.0f, b1 = 0.0f;
-    if (active && d0 < p.fam.Dx) b0 = glm_scale_at(p.fam, zsrc, d0) * zsrc[p.fam.off_u + d0];
-    if (active && d0 + 1 < p.fam.Dx) b1 = glm_scale_at(p.fam, zsrc, d0 + 1) * zsrc[p.fam.off_u + d0 + 1];
+    if (p.fam.off_lambda < 0 && p.fam.gscale == SCALE_NONE) {         // plain GLM: scale 1 (1.0f * u == u exactly)
+        if (active && d0 < p.fam.Dx) b0 = zsrc[p.fam.off_u + d0];
+        if (active && d0 + 1 < p.fam.Dx) b1 = zsrc[p.fam.off_u + d0 + 1];
+    } else {
+        if (active && d0 < p.fam.Dx) b0 = glm_scale_at(p.fam, zsrc, d0) * zsrc[p.fam.off_u + d0];
+        if (active && d0 + 1 < p.fam.Dx) b1 = glm_scale_at(p.fam, zsrc, d0 + 1) * zsrc[p.fam.off_u + d0 + 1];
+    }
     const uint4 w = make_uint4(__float_as_uint(b0), tag, __float_as_uint(b1), tag);
 #pragma unroll
     for (int r = 0; r < kBetaCopies; ++r) __stcg(p.beta + ((size_t)r * p.num_groups + grp) * kBetaWords + (kk * kStreamCT + slot) * 4 + t, w);

@@ -360,7 +360,14 @@ struct Tick {
         if (is_nan(delta)) delta = f_inf();
         const float leaf_w = -delta;
         const int leaf_div = (delta > 1000.0f) ? 1 : 0;
-        const float leaf_acc = clip_max1(d_exp(-delta));
+        // The three exponentials of a leaf -- exp(-delta) (accept prob), exp(-(w_leaf - w_sub)) (inside expit) and
+        // exp(-|w_sub - w_leaf|) (inside logaddexp) -- run on three lanes at once instead of one after the other.
+        const float x_mix = leaf_w - c.sub_weight, d_mix = c.sub_weight - leaf_w;
+        const int sel = lane % 3;
+        const float e_mine = d_exp(sel == 0 ? -delta : (sel == 1 ? -x_mix : -fabsf(d_mix)));
+        const float e_acc = __shfl_sync(0xFFFFFFFFu, e_mine, 0), e_x = __shfl_sync(0xFFFFFFFFu, e_mine, 1),
+                    e_abs = __shfl_sync(0xFFFFFFFFu, e_mine, 2);
+        const float leaf_acc = clip_max1(e_acc);
         const Key ks = mk(c.k_sub);
         float u_leaf;
         if ((c.pre_mask & 1u) && key_is(c.pl_from, ks)) { st(c.k_sub, mk(c.pl_ksub)); u_leaf = c.pl_u; c.pre_hit[0] += 1u; }
@@ -373,11 +380,14 @@ struct Tick {
             c.sub_prop_pe = u; c.sub_prop_energy = energy_new;
             c.sub_weight = leaf_w; c.sub_sum_acc = leaf_acc;
         } else {                                                   // _combine_tree, uniform kernel
-            const float p = d_expit(leaf_w - c.sub_weight);
+            const float p = 1.0f / (1.0f + e_x);                   // d_expit(leaf_w - c.sub_weight)
             store_prop = u_leaf < p;
             if (store_prop) { c.sub_prop_pe = u; c.sub_prop_energy = energy_new; }
             q0 = q0 + r0; q1 = q1 + r1;
-            c.sub_weight = d_logaddexp(c.sub_weight, leaf_w);
+            {   // d_logaddexp(c.sub_weight, leaf_w)
+                const float a_ = c.sub_weight, b_ = leaf_w;
+                c.sub_weight = is_nan(d_mix) ? (a_ + b_) : (((a_ >= b_) ? a_ : b_) + d_log1p(e_abs));
+            }
             c.sub_sum_acc = c.sub_sum_acc + leaf_acc;
         }
         if (a0) { gs[d0] = g0; rsum_s[d0] = q0; if (store_prop) { zps[d0] = z0; gps[d0] = g0; } }
@@ -513,10 +523,50 @@ struct Tick {
         const float *zs = v(V_ZS), *rs = v(V_RS), *gs = v(V_GS), *rsum_s = v(V_RSUMS);
         float *zo = v(c.going_right ? V_ZR : V_ZL), *ro = v(c.going_right ? V_RR : V_RL), *go = v(c.going_right ? V_GR : V_GL);
         float* rsum = v(V_RSUM);
-        B2_FOR_D(d, Dn) { zo[d] = zs[d]; ro[d] = rs[d]; go[d] = gs[d]; rsum[d] = rsum[d] + rsum_s[d]; }
+        bool turning;
+#if defined(__CUDA_ARCH__)
+        if (Dn <= 64) {
+            // two elements per lane, loads first; the tree-level U-turn test (is_turning) runs on the registers
+            const int lane = (int)(threadIdx.x & 31u);
+            const int d0 = lane, d1 = lane + 32;
+            const bool a0 = d0 < Dn, a1 = d1 < Dn;
+            const float* imm = v(V_IMM);
+            const float* other = v(c.going_right ? V_RL : V_RR);        // the edge this doubling did not move
+            float z0 = 0.0f, z1 = 0.0f, r0 = 0.0f, r1 = 0.0f, g0 = 0.0f, g1 = 0.0f, q0 = 0.0f, q1 = 0.0f, t0 = 0.0f, t1 = 0.0f,
+                  o0 = 0.0f, o1 = 0.0f, i0 = 0.0f, i1 = 0.0f;
+            if (a0) { z0 = zs[d0]; r0 = rs[d0]; g0 = gs[d0]; q0 = rsum_s[d0]; t0 = rsum[d0]; o0 = other[d0]; i0 = imm[d0]; }
+            if (a1) { z1 = zs[d1]; r1 = rs[d1]; g1 = gs[d1]; q1 = rsum_s[d1]; t1 = rsum[d1]; o1 = other[d1]; i1 = imm[d1]; }
+            t0 = t0 + q0; t1 = t1 + q1;
+            if (a0) { zo[d0] = z0; ro[d0] = r0; go[d0] = g0; rsum[d0] = t0; }
+            if (a1) { zo[d1] = z1; ro[d1] = r1; go[d1] = g1; rsum[d1] = t1; }
+            turning = sub_turning;
+            if (!sub_turning) {                                           // (the generic form short-circuits the same way)
+                float pl = 0.0f, pr = 0.0f;
+                if (a0) {
+                    const float rl_ = c.going_right ? o0 : r0, rr_ = c.going_right ? r0 : o0;
+                    const float sm = t0 - (rl_ + rr_) / 2.0f;
+                    pl = pl + (i0 * rl_) * sm; pr = pr + (i0 * rr_) * sm;
+                }
+                if (a1) {
+                    const float rl_ = c.going_right ? o1 : r1, rr_ = c.going_right ? r1 : o1;
+                    const float sm = t1 - (rl_ + rr_) / 2.0f;
+                    pl = pl + (i1 * rl_) * sm; pr = pr + (i1 * rr_) * sm;
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    pl = pl + __shfl_xor_sync(0xFFFFFFFFu, pl, off);
+                    pr = pr + __shfl_xor_sync(0xFFFFFFFFu, pr, off);
+                }
+                turning = (pl <= 0.0f) || (pr <= 0.0f);
+            }
+        } else
+#endif
+        {
+            B2_FOR_D(d, Dn) { zo[d] = zs[d]; ro[d] = rs[d]; go[d] = gs[d]; rsum[d] = rsum[d] + rsum_s[d]; }
+            turning = sub_turning || is_turning(Dn, v(V_IMM), v(V_RL), v(V_RR), rsum);
+        }
         float p = clip_max1(d_exp(c.sub_weight - c.weight));
         if (sub_turning || c.sub_div) p = 0.0f;
-        const bool turning = sub_turning || is_turning(Dn, v(V_IMM), v(V_RL), v(V_RR), rsum);
         const float u_fin = ((c.pre_mask & 2u) && key_is(c.pf_from, mk(c.k_fin))) ? c.pf_u : uniform01_at(mk(c.k_fin), 0);
         const bool take = u_fin < p;
         if (take) {
