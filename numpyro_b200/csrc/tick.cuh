@@ -565,6 +565,7 @@ struct Tick {
             B2_FOR_D(d, Dn) { zo[d] = zs[d]; ro[d] = rs[d]; go[d] = gs[d]; rsum[d] = rsum[d] + rsum_s[d]; }
             turning = sub_turning || is_turning(Dn, v(V_IMM), v(V_RL), v(V_RR), rsum);
         }
+        B2_LAPQ(11);
         float p = clip_max1(d_exp(c.sub_weight - c.weight));
         if (sub_turning || c.sub_div) p = 0.0f;
         const float u_fin = ((c.pre_mask & 2u) && key_is(c.pf_from, mk(c.k_fin))) ? c.pf_u : uniform01_at(mk(c.k_fin), 0);
@@ -573,13 +574,15 @@ struct Tick {
             copy(V_ZP, V_ZPS); copy(V_GP, V_GPS);
             c.prop_pe = c.sub_prop_pe; c.prop_energy = c.sub_prop_energy;
         }
+        B2_LAPQ(12);
         c.depth += 1;
         c.weight = d_logaddexp(c.weight, c.sub_weight);
+        B2_LAPQ(13);
         c.t_div = c.sub_div; c.turning = turning ? 1 : 0;
         c.sum_acc = c.sum_acc + c.sub_sum_acc;
         c.n_total += c.n_sub;
-        if (c.depth < c.max_depth && !c.turning && !c.t_div) begin_doubling();
-        else finish_transition();
+        if (c.depth < c.max_depth && !c.turning && !c.t_div) { begin_doubling(); B2_LAPQ(14); }
+        else { finish_transition(); B2_LAPQ(15); }
     }
 
     // ---------------------------------------------------------------- plain HMC (hmc.py:364-414)
