@@ -40,13 +40,38 @@ def engine_sources():
     return srcs
 
 
+STREAM_KS = (1, 2, 4, 7, 8)          # tile widths of the streaming kernel (stream_ks_for in stream_engine.cuh)
+
+
+def _run(cmd):
+    subprocess.check_call(cmd, cwd=CSRC)
+
+
 def build_engine(force: bool = False, verbose: bool = False) -> str:
+    """Compile the engine for sm_100a.  The streaming kernel's instances are split over one object per tile width and
+    compiled in parallel; ``B200NUTS_FAST_KS=<ks>`` (development) builds a single translation unit with one instance."""
     srcs = engine_sources()
-    if force or _stale(LIB, srcs):
-        fast = os.environ.get("B200NUTS_FAST_KS")          # development only: a single streaming-kernel instance
-        cmd = ([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ([f"-DB2_STREAM_FAST_KS={int(fast)}"] if fast else []) + (["-DB2_TICK_LAPS"] if os.environ.get("B200NUTS_TICK_LAPS") else [])
-               + ["-o", LIB, os.path.join(CSRC, "b200nuts.cu")])
-        subprocess.check_call(cmd, cwd=CSRC)
+    if not (force or _stale(LIB, srcs)):
+        return LIB
+    nvcc = _nvcc()
+    common = NVCC_FLAGS[:-1] + (["-Xptxas", "-v"] if verbose else [])          # (without -shared)
+    if os.environ.get("B200NUTS_TICK_LAPS"):
+        common = common + ["-DB2_TICK_LAPS"]
+    fast = os.environ.get("B200NUTS_FAST_KS")
+    if fast:
+        _run([nvcc] + common + ["-shared", f"-DB2_STREAM_FAST_KS={int(fast)}", "-o", LIB, os.path.join(CSRC, "b200nuts.cu")])
+        return LIB
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    jobs = [[nvcc] + common + ["-DB2_SPLIT_BUILD", "-c", "-o", os.path.join(objdir, "b200nuts.o"), os.path.join(CSRC, "b200nuts.cu")]]
+    for ks in STREAM_KS:
+        jobs.append([nvcc] + common + [f"-DB2_INST_KS={ks}", "-c", "-o", os.path.join(objdir, f"stream_ks{ks}.o"),
+                                       os.path.join(CSRC, "stream_instances.cu")])
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
+        list(pool.map(_run, jobs))
+    objs = [os.path.join(objdir, "b200nuts.o")] + [os.path.join(objdir, f"stream_ks{ks}.o") for ks in STREAM_KS]
+    _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs)
     return LIB
 
 

@@ -181,6 +181,23 @@ __global__ void k_detmath(int op, const float* x, long long n, float* out) {
 }
 
 // ------------------------------------------------------------------------------------------------
+#ifdef B2_SPLIT_BUILD
+// the instances live in stream_instances.cu, one object per tile width
+const void* b2_stream_kernel_ks1(int lik, bool mg); const void* b2_stream_kernel_ks2(int lik, bool mg);
+const void* b2_stream_kernel_ks4(int lik, bool mg); const void* b2_stream_kernel_ks7(int lik, bool mg);
+const void* b2_stream_kernel_ks8(int lik, bool mg);
+static const void* stream_kernel_for(int ks, int lik, int num_groups) {
+    const bool mg = num_groups > 1;
+    switch (ks) {
+    case 1: return b2_stream_kernel_ks1(lik, mg);
+    case 2: return b2_stream_kernel_ks2(lik, mg);
+    case 4: return b2_stream_kernel_ks4(lik, mg);
+    case 7: return b2_stream_kernel_ks7(lik, mg);
+    case 8: return b2_stream_kernel_ks8(lik, mg);
+    default: return nullptr;
+    }
+}
+#else
 template <int KS, bool MG>
 static const void* stream_kernel_lik(int lik) {
     return lik == LIK_BERNOULLI ? (const void*)stream_engine_kernel<KS, LIK_BERNOULLI, MG>
@@ -206,6 +223,7 @@ static const void* stream_kernel_for_mg(int ks, int lik) {
 static const void* stream_kernel_for(int ks, int lik, int num_groups) {
     return num_groups > 1 ? stream_kernel_for_mg<true>(ks, lik) : stream_kernel_for_mg<false>(ks, lik);
 }
+#endif
 
 static int stream_launch(B200Nuts* h, int mode, const OutBufs& out, const float* z_in, float* u_out, float* g_out,
                          cudaStream_t st) {

@@ -280,7 +280,7 @@ B2_HD size_t stream_smem_bytes(int KS, int Dp, int stages, bool vecs_in_smem, bo
 }
 
 // One-time repack of the caller's (X, y) into the tile image (see the header comment).
-__global__ void k_stream_repack(const float* __restrict__ X, const float* __restrict__ y, long long N, int D, int P,
+static __global__ void k_stream_repack(const float* __restrict__ X, const float* __restrict__ y, long long N, int D, int P,
                                 long long n_tiles, float* __restrict__ img) {
     const long long tile_floats = (long long)kTileRows * P + kTileRows;
     const long long per_tile = (long long)kTileRows * (P + 1);          // (row, column) pairs incl. the y "column" P
