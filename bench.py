@@ -219,6 +219,8 @@ def run_b200(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches, passes = e.launch_count - l0, e.pass_count - p0
+    # SM cycles per pass of the last timed launch (clock64 on CTA 0): with us_per_pass it gives the SM clock the run really had
+    cyc_per_pass = float(e.debug_clocks()[5]) / max(passes / max(args.steps, 1), 1.0)
     leap = int(sum(int(o["num_steps"].sum().item()) for o in outs))
     z = torch.cat([o["z"] for o in outs], dim=1)                      # [C, K*T, D]
     diverging = int(sum(int(o["diverging"].sum().item()) for o in outs))
@@ -332,7 +334,8 @@ def run_b200(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": "stream_engine_kernel<7>",
                      "algorithmic_bytes_per_pass": BYTES_PER_PASS, "passes_per_launch": passes / max(launches // 2, 1),
-                     "us_per_pass": ms * 1e3 / max(passes, 1)},
+                     "us_per_pass": ms * 1e3 / max(passes, 1), "sm_cycles_per_pass": cyc_per_pass,
+                     "effective_sm_clock_ghz": cyc_per_pass / (ms * 1e6 / max(passes, 1))},
         "cpu_baseline": cpu, "clocks": clk, "per_rank": per_rank, "many_chains": many,
     }
     print(json.dumps(line))
