@@ -6,8 +6,11 @@ covtype-shaped Bayesian logistic regression (BASELINE.json configs[1]: N = 58101
     python bench.py --gpus N --steps K --warmup W          # this repo (CUDA engine)
     python bench.py --impl reference --gpus N ...          # CPU arm: the oracle port on host cores
 
-A *step* is one collection call of the engine: STEP_TRANSITIONS NUTS transitions of every chain
-(post warm-up, adapted step size / mass matrix).  Adaptation runs before the timed region as setup.
+A *step* is one pass-bounded call of the engine: PASSES_PER_STEP sweeps of X per GPU, post warm-up (adapted step size /
+mass matrix).  Every chain advances its NUTS transitions as far as those sweeps carry it and pauses wherever it is in its
+tree; the next step resumes it (bit-identical to an unbounded run, tests/test_gpu_parity.py).  Every GPU therefore does the
+same amount of work per step, whatever tree depths its chains happen to have adapted to.  Adaptation runs before the timed
+region as setup.
 `value` is measured with the dataset resident in HBM; `e2e` runs the public ``MCMC`` API from pinned
 host buffers (H2D of X and y, init, warm-up, sampling, D2H of the samples) inside the timed region.
 Multi-GPU (torchrun, one rank per GPU): chains shard across ranks with no data-path collective
@@ -28,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 N_ROWS, N_COLS, CHAINS_PER_GPU = 581012, 54, 8
 BYTES_PER_PASS = N_ROWS * N_COLS * 4 + N_ROWS * 4          # one sweep of X and y serves every chain
-STEP_TRANSITIONS = 400
+PASSES_PER_STEP = 3000          # sweeps of X per step and GPU (about what 400 transitions of 8 chains need)
 ADAPT_ITERS = 600
 WORKLOAD = ("configs[1]: covtype-shaped Bayesian logistic regression NUTS "
             "(N=581012, D=54 fp32, synthetic, 8 chains per GPU, max_tree_depth=10)")
@@ -189,14 +192,19 @@ def run_b200(args):
     assert e.regime == _capi.REGIME_STREAM
     e.init(keys, ADAPT_ITERS)
     e.run(ADAPT_ITERS, ADAPT_ITERS, fields=())
-    upper = ADAPT_ITERS
     fields = ("z", "num_steps", "diverging")
+    n_steps_total = max(args.warmup, 3) + args.steps + 2
+    lower, upper = ADAPT_ITERS, ADAPT_ITERS + n_steps_total * (PASSES_PER_STEP // 2)     # window no chain can outrun
+    out = None
 
     def step():
-        nonlocal upper
-        out = e.run(upper + STEP_TRANSITIONS, upper, fields=fields)
-        upper += STEP_TRANSITIONS
+        nonlocal out
+        out = e.run(upper, lower, fields=fields, max_passes=PASSES_PER_STEP, out=out)
         return out
+
+    def progress():
+        st_, _ = e.state()
+        return np.array([s_.i for s_ in st_]), np.array([int(s_.total_leapfrogs) for s_ in st_])
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -210,20 +218,29 @@ def run_b200(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    it0, lf0 = progress()
     barrier()
     l0, p0 = e.launch_count, e.pass_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    outs = [step() for _ in range(args.steps)]
+    for _ in range(args.steps):
+        step()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches, passes = e.launch_count - l0, e.pass_count - p0
+    it1, lf1 = progress()
     # SM cycles per pass of the last timed launch (clock64 on CTA 0): with us_per_pass it gives the SM clock the run really had
     cyc_per_pass = float(e.debug_clocks()[5]) / max(passes / max(args.steps, 1), 1.0)
-    leap = int(sum(int(o["num_steps"].sum().item()) for o in outs))
-    z = torch.cat([o["z"] for o in outs], dim=1)                      # [C, K*T, D]
-    diverging = int(sum(int(o["diverging"].sum().item()) for o in outs))
+    leap = int((lf1 - lf0).sum())                                     # leapfrogs of the timed region, partial trees included
+    # samples: the transitions every chain (of every rank) completed inside the timed region
+    rng_t = torch.tensor([float(it0.max()), float(-it1.min())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(rng_t, op=dist.ReduceOp.MAX)
+    t_lo, t_hi = int(rng_t[0].item()), int(-rng_t[1].item())
+    z = out["z"][:, t_lo - lower:t_hi - lower].contiguous()           # [C, T, D]
+    diverging = int(out["diverging"][:, t_lo - lower:t_hi - lower].sum().item())
+    transitions_done = int((it1 - it0).sum())
     st, vec = e.state()
 
     # ---- end to end through the public API (pinned host inputs -> samples on the host)
@@ -271,7 +288,7 @@ def run_b200(args):
         em.close()
 
     # ---- reduce over ranks
-    stats = torch.tensor([ms, float(leap), e2e_ms, float(e2e_leap), float(diverging)], dtype=torch.float64, device=dev)
+    stats = torch.tensor([ms, float(leap), e2e_ms, float(e2e_leap), float(diverging), float(transitions_done)], dtype=torch.float64, device=dev)
     per_rank = [{"rank": rank, "ms": ms, "passes": int(passes), "grad_evals": leap,
                  "step_size": [round(float(s_.step_size), 5) for s_ in st]}]
     if world > 1:
@@ -284,6 +301,7 @@ def run_b200(args):
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         ms, e2e_ms = mx[0].item(), mx[2].item()
         leap, e2e_leap, diverging = int(sm[1].item()), int(sm[3].item()), int(sm[4].item())
+        transitions_done = int(sm[5].item())
         zs = [torch.empty_like(z) for _ in range(world)]
         dist.all_gather(zs, z)                                        # final gather for the diagnostics only
         z = torch.cat(zs, dim=0)
@@ -292,6 +310,7 @@ def run_b200(args):
             dist.destroy_process_group()
         return
     clk = clocks.stop()
+    transitions_done_total = transitions_done
     value = leap / (ms * 1e-3)
     zz = z.cpu().numpy().astype(np.float64)
     ess = diagnostics.effective_sample_size(zz)
@@ -319,13 +338,14 @@ def run_b200(args):
         "metric": "grad_evals_per_sec", "value": value, "unit": "grad-evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "chains_total": C_total, "transitions_per_step": STEP_TRANSITIONS,
+        "config": {"workload": WORKLOAD, "chains_total": C_total, "passes_per_step_per_gpu": PASSES_PER_STEP,
+                   "step": "PASSES_PER_STEP sweeps of X per GPU; chains pause mid-tree and resume in the next step",
                    "untimed_gpu_warm_seconds": args.gpu_warm_seconds,
                    "adaptation_iters_before_timing": ADAPT_ITERS, "l2": "inputs_larger_than_l2 (127.8 MB swept per pass)",
                    "parallelism": f"chains sharded over {world} GPU(s), no data-path collective"},
         "min_ess_per_sec": float(np.min(ess) / (ms * 1e-3)), "min_ess": float(np.min(ess)),
         "max_split_rhat": float(np.max(rhat)), "samples_per_chain": int(zz.shape[1]), "divergences": diverging,
-        "grad_evals": leap, "mean_tree_steps": leap / (C_total * args.steps * STEP_TRANSITIONS),
+        "grad_evals": leap, "transitions_completed": transitions_done_total, "mean_tree_steps": leap / max(transitions_done_total, 1),
         "gpu_launches": int(launches) * world,
         "e2e": {"value": e2e_leap / (e2e_ms * 1e-3), "unit": "grad-evals/s", "h2d_bytes_per_step": int(X.nbytes + y.nbytes),
                 "d2h_bytes_per_step": int(d2h),

@@ -94,6 +94,10 @@ typedef struct B200NutsRun {
     float* z;                  /* unconstrained samples */
     int32_t* diverging; int32_t* num_steps;
     float* accept_prob; float* mean_accept_prob; float* potential_energy; float* energy; float* step_size;
+    /* streaming regime, <= 8 chains: stop after this many sweeps of X (0 = run until every chain reached `upper`).  Chains
+     * pause wherever they are in their trees and the next b200nuts_run continues them -- results are identical to an
+     * unbounded run; it lets a caller give every GPU the same amount of work per call. */
+    int32_t max_passes;
 } B200NutsRun;
 
 /* Host mirror of HMCState + HMCAdaptState for one chain (hmc.py:31-48, hmc_util.py:18-30).

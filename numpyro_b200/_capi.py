@@ -48,6 +48,7 @@ class Run(C.Structure):
         ("upper", i32), ("collect_start", i32), ("thinning", i32), ("collection_size", i32),
         ("z", vp), ("diverging", vp), ("num_steps", vp), ("accept_prob", vp),
         ("mean_accept_prob", vp), ("potential_energy", vp), ("energy", vp), ("step_size", vp),
+        ("max_passes", i32),
     ]
 
 

@@ -226,10 +226,10 @@ static const void* stream_kernel_for(int ks, int lik, int num_groups) {
 #endif
 
 static int stream_launch(B200Nuts* h, int mode, const OutBufs& out, const float* z_in, float* u_out, float* g_out,
-                         cudaStream_t st) {
+                         cudaStream_t st, int max_passes = 0) {
     StreamParams p; memset(&p, 0, sizeof(p));
     p.cfg = h->tick; p.cfg.D = h->D; p.fam = h->fam; p.out = out; p.C = h->C; p.Dp = h->Dp; p.mode = mode;
-    p.num_groups = h->num_groups;
+    p.num_groups = h->num_groups; p.max_passes = (h->num_groups == 1) ? max_passes : 0;
     p.ctl = h->ctl; p.vecs = h->vecs; p.partial = h->partial; p.beta = h->beta; p.sync = h->sync;
     p.z_in = z_in; p.u_out = u_out; p.g_out = g_out; p.stages = h->stages;
     p.vecs_in_smem = h->vecs_in_smem; p.spin_limit = 2000000000LL;      // ~1 s: every wait in the engine is bounded
@@ -532,7 +532,8 @@ int b200nuts_run(B200Nuts* h, const B200NutsRun* run, void* stream) {
         h->launches += 1;
         return 0;
     }
-    int rc = stream_launch(h, 0, out, nullptr, nullptr, nullptr, st);
+    if (run->max_passes < 0 || (run->max_passes > 0 && h->num_groups != 1)) { h->err = "max_passes needs the streaming regime with <= 8 chains"; return B200NUTS_EINVAL; }
+    int rc = stream_launch(h, 0, out, nullptr, nullptr, nullptr, st, run->max_passes);
     if (rc) return rc;
     return check_stream_abort(h, st);
 }

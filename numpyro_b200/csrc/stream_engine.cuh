@@ -100,6 +100,7 @@ struct StreamParams {
     TickCfg cfg; FamilySpec fam; OutBufs out;
     int C, Dp, mode;                     // mode 0: run chains, 1: evaluate potential at z_in
     int num_groups;                      // ceil(C / kStreamCT)
+    int max_passes;                      // single group only: pause after this many sweeps (0 = run to the end)
     ChainCtl* ctl; float* vecs;          // [C], [V_COUNT][C][Dp]
     float2* partial;                     // [grid][num_groups][kStreamCT][kGStride] {value, tag = round of the group}
     uint4* beta;                         // [kBetaCopies][num_groups][8 k-steps][kStreamCT][4] {b0, tag, b1, tag}: beta in MMA-fragment order
@@ -452,6 +453,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         // staging buffer and release the consumers.  Returns 0 = staged, 1 = the group has finished (no pass), 2 = stop.
         auto stage = [&]() -> int {
             B2_TRACE_LANES(1);
+            // pass-bounded launch (single group): every CTA stops at the same pass; the owners have ticked, so each chain
+            // sits in front of its next gradient exactly as at the start of a launch
+            if (!MG && p.max_passes > 0 && qpass >= p.max_passes && status == 0) status = 1;
             // the staging buffer and the barrier phase of pass qpass were last used by pass qpass - 2: the consumers must
             // have begun pass qpass - 1 before they are reused
             {

@@ -113,13 +113,20 @@ class Engine:
         self.num_warmup = int(num_warmup)
 
     # ------------------------------------------------------------------ fori_collect
-    def run(self, upper: int, lower: int, thinning: int = 1, fields: Sequence[str] = ALL_FIELDS) -> Dict[str, torch.Tensor]:
+    def run(self, upper: int, lower: int, thinning: int = 1, fields: Sequence[str] = ALL_FIELDS, max_passes: int = 0,
+            out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """``max_passes`` (streaming regime, <= 8 chains): stop after that many sweeps; call again with the same window and
+        ``out=`` the returned buffers to continue -- the chains resume exactly where they paused."""
         S = max((upper - lower) // thinning, 0)
         start = lower + (upper - lower) % thinning
-        out: Dict[str, torch.Tensor] = {}
-        run = _capi.Run(upper=int(upper), collect_start=int(start), thinning=int(thinning), collection_size=int(S))
+        reuse = out
+        out = {} if out is None else out
+        run = _capi.Run(upper=int(upper), collect_start=int(start), thinning=int(thinning), collection_size=int(S),
+                        max_passes=int(max_passes))
         for f in fields:
-            if f == "z":
+            if reuse is not None:
+                t = reuse[f]
+            elif f == "z":
                 t = torch.zeros((self.C, S, self.D), dtype=torch.float32, device=self.device)
             elif f in _I32_FIELDS:
                 t = torch.zeros((self.C, S), dtype=torch.int32, device=self.device)

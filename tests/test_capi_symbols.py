@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_sizes_match_header_layout():
     from numpyro_b200 import _capi
-    assert C.sizeof(_capi.Run) == 4 * 4 + 8 * 8
+    assert C.sizeof(_capi.Run) == 4 * 4 + 8 * 8 + 8          # + max_passes (int32, padded to the struct alignment)
     assert C.sizeof(_capi.ChainState) % 8 == 0
     assert _capi.Config.X.offset % 8 == 0 and _capi.Config.nccl_comm.offset % 8 == 0
 

@@ -257,6 +257,38 @@ def test_stream_regime_run_bit_exact():
     assert sum(int(st[c].total_leapfrogs) for c in range(C)) > 0
 
 
+def test_pass_bounded_launches_equal_one_unbounded_run():
+    """b200nuts_run with max_passes: the chains pause anywhere in their trees and the next call continues them; the
+    concatenation is bit-identical to a single unbounded run (same samples, same adaptation, same keys)."""
+    rng = np.random.default_rng(12)
+    N, D, C = 8000, 54, 8
+    X = rng.normal(size=(N, D)).astype(F)
+    y = (rng.uniform(size=N) < 1 / (1 + np.exp(-(X @ (rng.normal(size=D) * 0.3))))).astype(F)
+    keys = prng.split(prng.key(31), C)
+    a = glm_engine(C, X, y, regime=_capi.REGIME_STREAM, max_tree_depth_warmup=6, max_tree_depth=6)
+    a.init(keys, 25)
+    ref = a.run(40, 25, fields=FIELDS)
+    passes_ref = a.pass_count
+    b = glm_engine(C, X, y, regime=_capi.REGIME_STREAM, max_tree_depth_warmup=6, max_tree_depth=6)
+    b.init(keys, 25)
+    out, calls = None, 0
+    while True:
+        out = b.run(40, 25, fields=FIELDS, max_passes=37, out=out)
+        calls += 1
+        st, _ = b.state()
+        if all(s.done == 1 and s.i == 40 for s in st):
+            break
+        assert calls < 500
+    assert calls > 3 and b.pass_count == passes_ref
+    for f in FIELDS:
+        assert torch.equal(out[f], ref[f]), f
+    sa, va = a.state()
+    sb, vb = b.state()
+    for c in range(C):
+        assert list(sa[c].rng_key) == list(sb[c].rng_key) and sa[c].total_leapfrogs == sb[c].total_leapfrogs
+    np.testing.assert_array_equal(va["inverse_mass_matrix"], vb["inverse_mass_matrix"])
+
+
 def test_stream_and_warp_runs_bit_exact_with_two_elements_per_lane():
     """32 < D <= 64: every lane of the chain's warp owns two coefficients (the register-resident leaf update)."""
     rng = np.random.default_rng(77)
