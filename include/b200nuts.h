@@ -9,8 +9,9 @@
  *     numpyro/infer/util.py:663-835                                 borrowed device data pointers)
  *   MCMCKernel.init(rng_key, num_warmup, init_params, ...)        b200nuts_init
  *     numpyro/infer/mcmc.py:90-108, hmc.py:740-799, :193-362
- *   MCMCKernel.sample(state, ...) iterated by fori_collect        b200nuts_run (whole collection
- *     mcmc.py:110-124, :466-521; numpyro/util.py:321-454            loop, device resident)
+ *   MCMCKernel.sample(state, ...)  mcmc.py:110-124                b200nuts_transition (n_iter = 1)
+ *   ... iterated by fori_collect                                  b200nuts_run (whole collection
+ *     mcmc.py:466-521; numpyro/util.py:321-454                      loop, device resident) + b200nuts_sync
  *   MCMC.last_state / post_warmup_state (HMCState pytree)         b200nuts_get_state / set_state
  *     mcmc.py:558-587, hmc.py:31-48, hmc_util.py:18-30
  *   postprocess_fn (constrain + deterministic sites)              b200nuts_constrain
@@ -23,8 +24,11 @@
  * B200NUTS_E* code; b200nuts_last_error() gives the message.  Nothing throws across the ABI.
  * Device pointers are caller-owned and borrowed for the lifetime of the handle; the engine owns only
  * its per-chain scratch.  All work is enqueued on the caller's stream (cudaStream_t passed as
- * void*); calls return without synchronising unless stated.  There is no CPU fallback: a missing
- * GPU or an unsupported family/shape is an error.
+ * void*); calls return without synchronising unless stated: b200nuts_init / run / transition only
+ * enqueue, b200nuts_sync waits for the last launch and reports its outcome (every call that needs
+ * results -- get_state, the parity hooks -- synchronises by itself).  At most one launch of a handle
+ * is in flight: a second b200nuts_run first collects the previous one.  There is no CPU fallback: a
+ * missing GPU or an unsupported family/shape is an error.
  */
 #ifndef B200NUTS_H_
 #define B200NUTS_H_
@@ -94,7 +98,8 @@ typedef struct B200NutsRun {
     float* z;                  /* unconstrained samples */
     int32_t* diverging; int32_t* num_steps;
     float* accept_prob; float* mean_accept_prob; float* potential_energy; float* energy; float* step_size;
-    /* streaming regime, <= 8 chains: stop after this many sweeps of X (0 = run until every chain reached `upper`).  Chains
+    /* streaming regime (<= 8 chains) and gemm regime: stop after this many passes over X (0 = run until every chain reached
+     * `upper`).  Chains
      * pause wherever they are in their trees and the next b200nuts_run continues them -- results are identical to an
      * unbounded run; it lets a caller give every GPU the same amount of work per call. */
     int32_t max_passes;
@@ -122,7 +127,13 @@ int b200nuts_regime(const B200Nuts* h);
 /* keys: host uint32 [num_chains][2] (rows of random.split(key, C), mcmc.py:670-671).
  * z0: device [num_chains][D] unconstrained init_params, or NULL => init_to_uniform. */
 int b200nuts_init(B200Nuts* h, const uint32_t* keys, const float* z0, int32_t num_warmup, void* stream);
-int b200nuts_run(B200Nuts* h, const B200NutsRun* run, void* stream);
+int b200nuts_run(B200Nuts* h, const B200NutsRun* run, void* stream);          /* enqueues; see b200nuts_sync */
+/* MCMCKernel.sample (mcmc.py:110-124): advance every chain by n_iter transitions from its current state, collecting
+ * nothing; read the new HMCState with b200nuts_get_state.  Enqueues. */
+int b200nuts_transition(B200Nuts* h, int32_t n_iter, void* stream);
+/* Wait for the last enqueued launch of this handle; returns its outcome (B200NUTS_ECUDA + message when a bounded wait
+ * inside a persistent kernel timed out or the launch failed). */
+int b200nuts_sync(B200Nuts* h);
 
 /* Synchronising. vectors (host, each [num_chains][D], may be NULL): z, z_grad, inverse_mass_matrix,
  * mass_matrix_sqrt, welford mean, welford m2. */
@@ -169,7 +180,10 @@ int b200nuts_detmath(int32_t op, const float* x, int64_t n, float* out);
 int64_t b200nuts_launch_count(const B200Nuts* h);
 /* streaming regime: sweeps over X executed so far by b200nuts_run (one sweep serves one gradient of every chain) */
 int64_t b200nuts_pass_count(const B200Nuts* h);
-/* streaming regime: clock64 totals of the last run on CTA 0 (see StreamSync.dbg in stream_engine.cuh) */
+/* gemm regime: {chain tiles, row chunks, k-blocks, row segments, chunks per segment, column blocks, padded columns,
+ * 1 = device-side WHILE graph / 0 = host loop} */
+int b200nuts_gemm_info(const B200Nuts* h, int32_t* out8);
+/* streaming regime: clock64 totals of the last run on CTA 0 (see StreamSync.dbg in stream_engine.cuh); gemm regime: GemmStatus.dbg */
 int b200nuts_debug_clocks(const B200Nuts* h, uint64_t* out16);
 
 #ifdef __cplusplus

@@ -59,18 +59,21 @@ def build_engine(force: bool = False, verbose: bool = False) -> str:
         common = common + ["-DB2_TICK_LAPS"]
     fast = os.environ.get("B200NUTS_FAST_KS")
     if fast:
-        _run([nvcc] + common + ["-shared", f"-DB2_STREAM_FAST_KS={int(fast)}", "-o", LIB, os.path.join(CSRC, "b200nuts.cu")])
+        _run([nvcc] + common + ["-shared", f"-DB2_STREAM_FAST_KS={int(fast)}", "-o", LIB, os.path.join(CSRC, "b200nuts.cu"),
+                                os.path.join(CSRC, "gemm_engine.cu")])
         return LIB
     objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
     jobs = [[nvcc] + common + ["-DB2_SPLIT_BUILD", "-c", "-o", os.path.join(objdir, "b200nuts.o"), os.path.join(CSRC, "b200nuts.cu")]]
+    jobs.append([nvcc] + common + ["-c", "-o", os.path.join(objdir, "gemm_engine.o"), os.path.join(CSRC, "gemm_engine.cu")])
     for ks in STREAM_KS:
         jobs.append([nvcc] + common + [f"-DB2_INST_KS={ks}", "-c", "-o", os.path.join(objdir, f"stream_ks{ks}.o"),
                                        os.path.join(CSRC, "stream_instances.cu")])
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
         list(pool.map(_run, jobs))
-    objs = [os.path.join(objdir, "b200nuts.o")] + [os.path.join(objdir, f"stream_ks{ks}.o") for ks in STREAM_KS]
+    objs = [os.path.join(objdir, "b200nuts.o"), os.path.join(objdir, "gemm_engine.o")] + \
+           [os.path.join(objdir, f"stream_ks{ks}.o") for ks in STREAM_KS]
     _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs)
     return LIB
 

@@ -14,8 +14,10 @@
 #include <chrono>
 #include <thread>
 #include <unistd.h>
+#include <cmath>
 #include "engine.cuh"
 #include "stream_engine.cuh"
+#include "gemm_engine.h"
 
 using namespace b2;
 
@@ -37,6 +39,11 @@ struct B200Nuts {
     int shard_rank = 0, shard_count = 1; bool shards_connected = false; unsigned int epoch = 0;
     float2* mail = nullptr; float2* mail_peer[kMaxShards] = {nullptr}; bool mail_ipc[kMaxShards] = {false};
     long long n_rows_global = 0; float nll_local_const = 0.0f;
+    // R3
+    GemmRegime* gemm = nullptr;
+    // enqueue-only launches: the launch whose outcome b200nuts_sync has not collected yet
+    bool pending = false; cudaStream_t pending_stream = nullptr;
+    int cur_iter = -1;                         // HMCState.i of every chain when known (b200nuts_transition), else -1
     std::string err;
     std::mutex mu;
 };
@@ -259,8 +266,7 @@ static int stream_launch(B200Nuts* h, int mode, const OutBufs& out, const float*
     void* args[] = {&p};
     const void* fn = stream_kernel_for(h->ks, h->fam.likelihood, h->num_groups);
     if (!fn) { h->err = "stream regime: no kernel instance for this shape"; return B200NUTS_EINVAL; }
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    {
+    {   // (the dynamic shared-memory limit of the kernel was raised once, in b200nuts_create)
         cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(h->grid), dim3(kStreamThreads), args, h->smem, st);
         if (le != cudaSuccess) {
             cudaFuncAttributes fa; memset(&fa, 0, sizeof(fa)); cudaFuncGetAttributes(&fa, fn);
@@ -346,6 +352,24 @@ static int check_stream_abort(B200Nuts* h, cudaStream_t st) {
     return 0;
 }
 
+// Collect the outcome of the last enqueued launch (caller holds h->mu).
+static int sync_locked(B200Nuts* h) {
+    if (!h->pending) return 0;
+    h->pending = false;
+    cudaStream_t st = h->pending_stream;
+    if (h->regime == B200NUTS_REGIME_STREAM) return check_stream_abort(h, st);
+    if (h->regime == B200NUTS_REGIME_GEMM) {
+        GemmStatus gs; memset(&gs, 0, sizeof(gs));
+        const std::string e = gemm_sync(h->gemm, st, &gs, &h->launches);
+        h->passes = (long long)gs.passes_total;
+        for (int i = 0; i < 8; ++i) h->dbg[i] = gs.dbg[i];
+        if (!e.empty()) { h->err = e; return B200NUTS_ECUDA; }
+        return 0;
+    }
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
 extern "C" {
 
 const char* b200nuts_last_error(const B200Nuts* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
@@ -353,6 +377,12 @@ int b200nuts_dim(const B200Nuts* h) { return h ? h->D : B200NUTS_EINVAL; }
 int b200nuts_regime(const B200Nuts* h) { return h ? h->regime : B200NUTS_EINVAL; }
 int64_t b200nuts_launch_count(const B200Nuts* h) { return h ? h->launches : 0; }
 int64_t b200nuts_pass_count(const B200Nuts* h) { return h ? h->passes : 0; }
+int b200nuts_gemm_info(const B200Nuts* h, int32_t* out8) {
+    if (!h || !out8 || !h->gemm) return B200NUTS_EINVAL;
+    int v[8]; gemm_describe(h->gemm, v);
+    for (int i = 0; i < 8; ++i) out8[i] = v[i];
+    return 0;
+}
 int b200nuts_debug_clocks(const B200Nuts* h, uint64_t* out16) {
     if (!h || !out16) return B200NUTS_EINVAL;
     for (int i = 0; i < 16; ++i) out16[i] = h->dbg[i];
@@ -373,6 +403,7 @@ void b200nuts_destroy(B200Nuts* h) {
     if (h->trace_host) cudaFreeHost(h->trace_host);
     for (int q = 0; q < kMaxShards; ++q) if (h->mail_ipc[q] && h->mail_peer[q]) cudaIpcCloseMemHandle(h->mail_peer[q]);
     cudaFree(h->mail);
+    gemm_destroy(h->gemm);
     delete h;
 }
 
@@ -398,10 +429,18 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
     int regime = cfg->regime;
     const bool glm = h->fam.family == FAM_GLM;
     const bool stream_ok = glm && h->C <= kMaxStreamChains && h->fam.Dx <= 64 && h->C <= h->num_sms;
-    if (regime == B200NUTS_REGIME_AUTO)
-        regime = (stream_ok && (long long)h->fam.N * h->fam.Dx >= (1LL << 20)) ? B200NUTS_REGIME_STREAM : B200NUTS_REGIME_WARP;
+    const bool gemm_ok = glm && h->fam.Dx <= 1024 && h->fam.N * (long long)h->fam.Dx >= 4096;
+    if (regime == B200NUTS_REGIME_AUTO) {
+        // many chains: the gradient is a GEMM (tcgen05); tall data with a handful of chains: one HBM sweep per pass; else in-warp
+        if (gemm_ok && h->C >= 128 && (long long)h->fam.N * h->fam.Dx >= (1LL << 17)) regime = B200NUTS_REGIME_GEMM;
+        else if (stream_ok && (long long)h->fam.N * h->fam.Dx >= (1LL << 20)) regime = B200NUTS_REGIME_STREAM;
+        else regime = B200NUTS_REGIME_WARP;
+    }
     if (regime == B200NUTS_REGIME_STREAM && !stream_ok) {
         g_create_err = "stream regime needs a GLM family with <= 64 columns and one SM per chain (<= 148 chains)"; delete h; return B200NUTS_EINVAL;
+    }
+    if (regime == B200NUTS_REGIME_GEMM && !gemm_ok) {
+        g_create_err = "gemm regime needs a GLM family with <= 1024 columns"; delete h; return B200NUTS_EINVAL;
     }
     if (cfg->shard_count > 1) {
         if (!stream_ok) { g_create_err = "row-sharded handles need the streaming regime (GLM, <= 64 columns, one SM per chain)"; delete h; return B200NUTS_EINVAL; }
@@ -409,7 +448,6 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
         h->shard_rank = cfg->shard_rank; h->shard_count = cfg->shard_count;
         h->n_rows_global = cfg->n_rows_global > 0 ? cfg->n_rows_global : cfg->n_rows;
     }
-    if (regime == B200NUTS_REGIME_GEMM) { g_create_err = "gemm regime is not implemented yet"; delete h; return B200NUTS_EINVAL; }
     h->regime = regime;
     auto fail = [&](const char* what, cudaError_t ce) {
         g_create_err = std::string(what) + ": " + cudaGetErrorString(ce); b200nuts_destroy(h); return B200NUTS_ECUDA;
@@ -475,6 +513,10 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
             h->nll_local_const = h->fam.nll_const;
         }
     }
+    if (regime == B200NUTS_REGIME_GEMM) {
+        const std::string ge = gemm_create(&h->gemm, h->fam, h->C, h->Dp, h->num_sms, h->ctl, h->vecs, &h->launches);
+        if (!ge.empty()) { g_create_err = ge; b200nuts_destroy(h); return B200NUTS_ECUDA; }
+    }
     {   // Load every kernel this handle can launch NOW.  With lazy module loading the first launch of a function may need
         // a context-wide synchronisation; a persistent kernel of another (row-sharded) handle that is waiting for this
         // handle's contribution would then never finish.
@@ -498,6 +540,7 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
 int b200nuts_init(B200Nuts* h, const uint32_t* keys, const float* z0, int32_t num_warmup, void* stream) {
     if (!h || !keys || num_warmup < 0) return B200NUTS_EINVAL;
     std::lock_guard<std::mutex> lk(h->mu);
+    if (int rc = sync_locked(h)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     std::string e = make_tick_cfg(h->cfg, h->fam, h->sites, num_warmup, z0 != nullptr, h->tick);
     if (!e.empty()) { h->err = e; return B200NUTS_EINVAL; }
@@ -507,20 +550,23 @@ int b200nuts_init(B200Nuts* h, const uint32_t* keys, const float* z0, int32_t nu
     CK(cudaGetLastError());
     h->launches += 1;
     h->inited = true;
+    h->cur_iter = 0;
     return 0;
 }
 
-int b200nuts_run(B200Nuts* h, const B200NutsRun* run, void* stream) {
-    if (!h || !run || run->thinning < 1 || run->upper < 0) return B200NUTS_EINVAL;
-    std::lock_guard<std::mutex> lk(h->mu);
+// Enqueue only (an XLA-FFI handler must not block); b200nuts_sync collects the outcome.
+static int run_locked(B200Nuts* h, const B200NutsRun* run, cudaStream_t st) {
     if (!h->inited) { h->err = "b200nuts_run called before b200nuts_init"; return B200NUTS_ESTATE; }
-    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = sync_locked(h)) return rc;            // at most one launch of a handle is in flight
     h->tick.total_iters = run->upper;
     h->tick.collect_start = run->collect_start; h->tick.thinning = run->thinning; h->tick.S = run->collection_size;
     OutBufs out;
     out.z = run->z; out.diverging = run->diverging; out.num_steps = run->num_steps; out.accept_prob = run->accept_prob;
     out.mean_accept_prob = run->mean_accept_prob; out.pe = run->potential_energy; out.energy = run->energy;
     out.step_size = run->step_size;
+    if (run->max_passes < 0 || (run->max_passes > 0 && (h->regime == B200NUTS_REGIME_WARP || (h->regime == B200NUTS_REGIME_STREAM && h->num_groups != 1)))) {
+        h->err = "max_passes needs the streaming regime with <= 8 chains or the gemm regime"; return B200NUTS_EINVAL;
+    }
     const int blocks = (h->C + 3) / 4;
     k_chain_resume<<<blocks, 128, 0, st>>>(h->tick, h->ctl, h->vecs, h->C, h->Dp);
     CK(cudaGetLastError());
@@ -530,18 +576,48 @@ int b200nuts_run(B200Nuts* h, const B200NutsRun* run, void* stream) {
                                            (long long)h->fam.N + h->fam.Dx, h->C, h->Dp);
         CK(cudaGetLastError());
         h->launches += 1;
-        return 0;
+    } else if (h->regime == B200NUTS_REGIME_GEMM) {
+        const std::string e = gemm_run(h->gemm, h->tick, out, run->max_passes, st);
+        if (!e.empty()) { h->err = e; return B200NUTS_ECUDA; }
+        h->launches += 2;
+    } else {
+        int rc = stream_launch(h, 0, out, nullptr, nullptr, nullptr, st, run->max_passes);
+        if (rc) return rc;
     }
-    if (run->max_passes < 0 || (run->max_passes > 0 && h->num_groups != 1)) { h->err = "max_passes needs the streaming regime with <= 8 chains"; return B200NUTS_EINVAL; }
-    int rc = stream_launch(h, 0, out, nullptr, nullptr, nullptr, st, run->max_passes);
-    if (rc) return rc;
-    return check_stream_abort(h, st);
+    h->pending = true; h->pending_stream = st;
+    if (run->max_passes > 0) h->cur_iter = -1;         // chains may have paused anywhere
+    else if (h->cur_iter >= 0 && run->upper > h->cur_iter) h->cur_iter = run->upper;
+    return 0;
+}
+
+int b200nuts_run(B200Nuts* h, const B200NutsRun* run, void* stream) {
+    if (!h || !run || run->thinning < 1 || run->upper < 0) return B200NUTS_EINVAL;
+    std::lock_guard<std::mutex> lk(h->mu);
+    return run_locked(h, run, (cudaStream_t)stream);
+}
+
+// MCMCKernel.sample granularity (mcmc.py:110-124): advance every chain by n_iter transitions, collecting nothing.
+int b200nuts_transition(B200Nuts* h, int32_t n_iter, void* stream) {
+    if (!h || n_iter < 0) return B200NUTS_EINVAL;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->cur_iter < 0) { h->err = "b200nuts_transition: the chains' iteration is unknown (pass-bounded run or mixed state); use b200nuts_run"; return B200NUTS_ESTATE; }
+    B200NutsRun run; memset(&run, 0, sizeof(run));
+    run.upper = h->cur_iter + n_iter; run.collect_start = run.upper; run.thinning = 1; run.collection_size = 0;
+    return run_locked(h, &run, (cudaStream_t)stream);
+}
+
+// Wait for the last enqueued launch and report its outcome (a timed-out exchange, a failed launch).
+int b200nuts_sync(B200Nuts* h) {
+    if (!h) return B200NUTS_EINVAL;
+    std::lock_guard<std::mutex> lk(h->mu);
+    return sync_locked(h);
 }
 
 int b200nuts_get_state(B200Nuts* h, B200NutsChainState* states, float* z, float* z_grad, float* inv_mass,
                        float* mass_sqrt, float* wf_mean, float* wf_m2, void* stream) {
     if (!h || !states) return B200NUTS_EINVAL;
     std::lock_guard<std::mutex> lk(h->mu);
+    if (int rc0 = sync_locked(h)) return rc0;
     cudaStream_t st = (cudaStream_t)stream;
     std::vector<ChainCtl> ctl(h->C);
     CK(cudaMemcpyAsync(ctl.data(), h->ctl, sizeof(ChainCtl) * h->C, cudaMemcpyDeviceToHost, st));
@@ -566,13 +642,19 @@ int b200nuts_set_state(B200Nuts* h, const B200NutsChainState* states, const floa
                        void* stream) {
     if (!h || !states || !z || !z_grad || !inv_mass) return B200NUTS_EINVAL;
     std::lock_guard<std::mutex> lk(h->mu);
+    if (int rc0 = sync_locked(h)) return rc0;
     cudaStream_t st = (cudaStream_t)stream;
     std::string e = make_tick_cfg(h->cfg, h->fam, h->sites, num_warmup, true, h->tick);
     if (!e.empty()) { h->err = e; return B200NUTS_EINVAL; }
     std::vector<ChainCtl> ctl(h->C);
     for (int c = 0; c < h->C; ++c) public_to_ctl(states[c], ctl[c]);
     std::vector<float> sqrtm((size_t)h->C * h->D);
-    for (size_t i = 0; i < sqrtm.size(); ++i) sqrtm[i] = 1.0f / sqrtf(inv_mass[i]);
+    for (size_t i = 0; i < sqrtm.size(); ++i) {
+        if (!(inv_mass[i] > 0.0f) || !std::isfinite(inv_mass[i])) { h->err = "b200nuts_set_state: inverse_mass_matrix must be positive and finite"; return B200NUTS_EINVAL; }
+        sqrtm[i] = 1.0f / sqrtf(inv_mass[i]);
+    }
+    h->cur_iter = states[0].i;
+    for (int c = 1; c < h->C; ++c) if (states[c].i != states[0].i) h->cur_iter = -1;
     CK(cudaMemcpyAsync(h->ctl, ctl.data(), sizeof(ChainCtl) * h->C, cudaMemcpyHostToDevice, st));
     const float* src[6] = {z, z_grad, inv_mass, sqrtm.data(), wf_mean, wf_m2};
     const int fld[6] = {V_Z, V_G, V_IMM, V_SQRTM, V_WF_MEAN, V_WF_M2};
@@ -629,12 +711,19 @@ int b200nuts_shard_connect(B200Nuts* h, const void* blobs) {
 int b200nuts_potential_and_grad(B200Nuts* h, const float* z, float* U, float* g, void* stream) {
     if (!h || !z || !U || !g) return B200NUTS_EINVAL;
     std::lock_guard<std::mutex> lk(h->mu);
+    if (int rc0 = sync_locked(h)) return rc0;
     cudaStream_t st = (cudaStream_t)stream;
     if (h->regime == B200NUTS_REGIME_WARP) {
         k_potential_warp<<<(h->C + 3) / 4, 128, 0, st>>>(h->fam, z, U, g, h->scratch, (long long)h->fam.N + h->fam.Dx, h->C);
         CK(cudaGetLastError());
         h->launches += 1;
         return 0;
+    }
+    if (h->regime == B200NUTS_REGIME_GEMM) {
+        const std::string e = gemm_potential(h->gemm, z, U, g, st, &h->launches);
+        if (!e.empty()) { h->err = e; return B200NUTS_ECUDA; }
+        h->pending = true; h->pending_stream = st;
+        return sync_locked(h);               // a parity hook: synchronise and report an aborted pass
     }
     OutBufs none; memset(&none, 0, sizeof(none));
     int rc = stream_launch(h, 1, none, z, U, g, st);

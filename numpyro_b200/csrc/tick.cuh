@@ -774,7 +774,9 @@ struct Tick {
             const bool bad = !is_finite(u) || lane_any(cfg.D, [&](int d) { return !is_finite(g[d]); });
             c.init_tries += 1;
             if (bad && !cfg.init_given && c.init_tries < 100) { init_draw(); return; }
-            if (bad) c.init_failed = 1;
+            // "Cannot find valid initial parameters" (infer/util.py:800-832): the chain stops here; b200nuts_sync /
+            // b200nuts_get_state report B200NUTS_EINIT
+            if (bad) { c.init_failed = 1; c.phase = PH_DONE; return; }
             finish_init(u, g);
             return;
         }

@@ -27,6 +27,18 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _on_device(fn):
+    """Run a method with the handle's GPU current (the C ABI launches on the calling thread's current device) and
+    restore the caller's device afterwards."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **kw):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **kw)
+    return wrapped
+
+
 class Engine:
     """One handle = the chains that live on one GPU."""
 
@@ -35,7 +47,8 @@ class Engine:
             raise EngineError("numpyro_b200 needs a CUDA device: the engine has no CPU fallback")
         self.lib = _capi.load()
         self.device = torch.device(device)
-        torch.cuda.set_device(self.device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         to = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float32).to(self.device).contiguous()
         self.X, self.y, self.aux = to(X), to(y), to(aux)            # borrowed by the handle: keep alive
         c = _capi.default_config(**cfg)
@@ -48,7 +61,8 @@ class Engine:
             c.aux = self.aux.data_ptr()
         self.cfg = c
         self.h = C.c_void_p()
-        rc = self.lib.b200nuts_create(C.byref(c), C.byref(self.h))
+        with torch.cuda.device(self.device):      # (the caller's current device is left as it was)
+            rc = self.lib.b200nuts_create(C.byref(c), C.byref(self.h))
         if rc != 0:
             raise EngineError(f"b200nuts_create failed ({rc}): {self.lib.b200nuts_last_error(None).decode()}")
         self.C = int(c.num_chains)
@@ -59,12 +73,14 @@ class Engine:
         self._shard_group = None
 
     # ------------------------------------------------------------------ row-sharded handles (config 5)
+    @_on_device
     def shard_blob(self) -> bytes:
         """This rank's mailbox handle for :meth:`connect_shards` (b200nuts_shard_export)."""
         buf = C.create_string_buffer(_capi.SHARD_HANDLE_BYTES)
         self._check(self.lib.b200nuts_shard_export(self.h, buf), "b200nuts_shard_export")
         return buf.raw
 
+    @_on_device
     def connect_shards(self, blobs=None, group=None):
         """Wire the per-gradient all-reduce of a row-sharded handle.  ``blobs``: the ranks' :meth:`shard_blob` in rank
         order (ranks = threads of this process), or None to exchange them over ``torch.distributed`` (ranks = processes;
@@ -85,6 +101,7 @@ class Engine:
             dist.barrier(group=self._shard_group)
 
     # ------------------------------------------------------------------ lifetime
+    @_on_device
     def close(self):
         if getattr(self, "h", None) and self.h.value:
             torch.cuda.synchronize(self.device)
@@ -105,6 +122,7 @@ class Engine:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # ------------------------------------------------------------------ MCMCKernel.init
+    @_on_device
     def init(self, keys, num_warmup: int, z0=None):
         keys = np.ascontiguousarray(keys, np.uint32).reshape(self.C, 2)
         self._z0 = None if z0 is None else torch.as_tensor(z0, dtype=torch.float32).to(self.device).contiguous().view(self.C, self.D)
@@ -113,10 +131,13 @@ class Engine:
         self.num_warmup = int(num_warmup)
 
     # ------------------------------------------------------------------ fori_collect
+    @_on_device
     def run(self, upper: int, lower: int, thinning: int = 1, fields: Sequence[str] = ALL_FIELDS, max_passes: int = 0,
-            out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
-        """``max_passes`` (streaming regime, <= 8 chains): stop after that many sweeps; call again with the same window and
-        ``out=`` the returned buffers to continue -- the chains resume exactly where they paused."""
+            out: Optional[Dict[str, torch.Tensor]] = None, sync: bool = True) -> Dict[str, torch.Tensor]:
+        """``max_passes`` (streaming regime with <= 8 chains, gemm regime): stop after that many passes; call again with the
+        same window and ``out=`` the returned buffers to continue -- the chains resume exactly where they paused.
+        ``b200nuts_run`` only enqueues; with ``sync=True`` (default) the outcome is collected before returning
+        (:meth:`sync`), otherwise the caller collects it later."""
         S = max((upper - lower) // thinning, 0)
         start = lower + (upper - lower) % thinning
         reuse = out
@@ -138,9 +159,29 @@ class Engine:
             setattr(run, f, t.data_ptr() if S > 0 else None)
         self._align_ranks()
         self._check(self.lib.b200nuts_run(self.h, C.byref(run), self._stream()), "b200nuts_run")
+        if sync:
+            self.sync()
         return out
 
+    @_on_device
+    def transition(self, n_iter: int = 1, sync: bool = True):
+        """``MCMCKernel.sample`` granularity: advance every chain by ``n_iter`` transitions (b200nuts_transition)."""
+        self._check(self.lib.b200nuts_transition(self.h, int(n_iter), self._stream()), "b200nuts_transition")
+        if sync:
+            self.sync()
+
+    def sync(self):
+        """Wait for the last enqueued launch and raise if it failed (b200nuts_sync)."""
+        self._check(self.lib.b200nuts_sync(self.h), "b200nuts_sync")
+
+    def gemm_info(self) -> Dict[str, int]:
+        out = np.zeros(8, np.int32)
+        self._check(self.lib.b200nuts_gemm_info(self.h, out.ctypes.data_as(C.c_void_p)), "b200nuts_gemm_info")
+        return dict(zip(("chain_tiles", "row_chunks", "k_blocks", "segments", "chunks_per_segment", "column_blocks",
+                         "padded_columns", "device_while_graph"), (int(v) for v in out)))
+
     # ------------------------------------------------------------------ HMCState in / out
+    @_on_device
     def state(self):
         st = (_capi.ChainState * self.C)()
         names = ("z", "z_grad", "inverse_mass_matrix", "mass_matrix_sqrt", "wf_mean", "wf_m2")
@@ -152,6 +193,7 @@ class Engine:
         self._check(rc, "b200nuts_get_state")
         return st, vec
 
+    @_on_device
     def set_state(self, st, vec, num_warmup: int):
         arr = lambda n: None if vec.get(n) is None else np.ascontiguousarray(vec[n], np.float32).ctypes.data_as(C.c_void_p)
         keep = {n: np.ascontiguousarray(v, np.float32) for n, v in vec.items() if v is not None}
@@ -162,6 +204,7 @@ class Engine:
         self.num_warmup = int(num_warmup)
 
     # ------------------------------------------------------------------ parity hooks
+    @_on_device
     def potential_and_grad(self, z):
         z = torch.as_tensor(z, dtype=torch.float32).to(self.device).contiguous().view(self.C, self.D)
         U = torch.zeros(self.C, dtype=torch.float32, device=self.device)
@@ -171,6 +214,7 @@ class Engine:
                     "b200nuts_potential_and_grad")
         return U, g
 
+    @_on_device
     def leapfrog(self, eps, inv_mass, z, r, n_steps: int):
         dev = lambda a, shape: torch.as_tensor(a, dtype=torch.float32).to(self.device).contiguous().view(*shape).clone()
         eps, inv_mass = dev(eps, (self.C,)), dev(inv_mass, (self.C, self.D))
@@ -181,6 +225,7 @@ class Engine:
                                                int(n_steps), self._stream()), "b200nuts_leapfrog")
         return z, r, U, g
 
+    @_on_device
     def constrain(self, z: torch.Tensor) -> torch.Tensor:
         z = z.contiguous().view(-1, self.D)
         out = torch.empty((z.shape[0], self.Dc), dtype=torch.float32, device=self.device)

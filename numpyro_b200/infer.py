@@ -4,10 +4,13 @@ Mirrors the user-facing surface of numpyro/infer/mcmc.py (``MCMC`` :225-809, ``M
 :33-159) and numpyro/infer/hmc.py (``HMC`` :533-822, ``NUTS`` :825-951, ``HMCState`` :31-48) for
 the hot path only: same constructor arguments, same ``run / warmup / get_samples /
 get_extra_fields / last_state / post_warmup_state / print_summary`` semantics and the same
-collection layout ``[num_chains, num_samples // thinning, ...]``.  The model argument is a
-declared family (numpyro_b200.families); arrays are NumPy on the host, every computation runs in
-the CUDA engine.  ``chain_method='parallel'`` shards chains over the GPUs visible to the process
-(or over torch.distributed ranks under torchrun) with no communication except the final gather;
+collection layout ``[num_chains, num_samples // thinning, ...]``.  ``NUTS`` / ``HMC`` implement the
+``MCMCKernel`` plug-in interface (``init`` / ``sample`` / ``postprocess_fn``, mcmc.py:79-124) over the
+C ABI (b200nuts_init / b200nuts_transition / b200nuts_constrain); when numpyro is importable they
+subclass the real ``MCMCKernel``.  The model argument is a declared family
+(numpyro_b200.families); arrays are NumPy on the host, every computation runs in the CUDA engine.
+``chain_method='parallel'`` shards chains over the GPUs visible to the process (or over
+torch.distributed ranks under torchrun) with no communication except the final gather;
 ``'vectorized'`` keeps all chains on one GPU; ``'sequential'`` runs them one after the other.
 """
 from __future__ import annotations
@@ -16,13 +19,19 @@ import os
 import warnings
 from collections import namedtuple
 from concurrent.futures import ThreadPoolExecutor
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Optional
 
 import numpy as np
 import torch
 
 from . import _capi, diagnostics, families, random as b2random
 from .engine import Engine
+
+try:                                   # drop-in: be a real numpyro kernel where numpyro exists
+    from numpyro.infer.mcmc import MCMCKernel as _KernelBase          # pragma: no cover (jax is not in this image)
+except Exception:                      # noqa: BLE001
+    class _KernelBase:                 # the interface of mcmc.py:33-159 is restated by HMC below
+        pass
 
 HMCState = namedtuple("HMCState", ["i", "z", "z_grad", "potential_energy", "energy", "r", "trajectory_length",
                                    "num_steps", "accept_prob", "mean_accept_prob", "diverging", "adapt_state", "rng_key"])
@@ -34,7 +43,108 @@ _STATE_FIELDS = {"potential_energy": "potential_energy", "energy": "energy", "nu
                  "adapt_state.step_size": "step_size"}
 
 
-class HMC:
+# ---------------------------------------------------------------------- init strategies (initialization.py:88-160)
+class _InitStrategy:
+    def __init__(self, kind, radius=2.0, values=None):
+        self.kind, self.radius, self.values = kind, float(radius), values
+
+
+def init_to_uniform(radius=2):
+    """initialization.py:88-122: uniform(-radius, radius) in unconstrained space (the default, radius 2)."""
+    return _InitStrategy("uniform", radius=radius)
+
+
+def init_to_feasible():
+    """initialization.py:125-130 = init_to_uniform(radius=0): every unconstrained coordinate starts at 0."""
+    return _InitStrategy("feasible", radius=0.0)
+
+
+def init_to_value(values=None):
+    """initialization.py:140-155: start from the given (constrained) site values.  Every latent site must be given:
+    the reference's fallback for missing sites draws through the seed handler's key stream, which is not restated."""
+    return _InitStrategy("value", values=dict(values or {}))
+
+
+# ---------------------------------------------------------------------- HMCState <-> engine
+def _state_from_engine(sts, vecs, bound, squeeze_one, trajectory_length):
+    """HMCState (hmc.py:31-48) of the chains behind one or more engine handles, field for field."""
+    cat = lambda name: np.concatenate([v[name] for v in vecs], axis=0)
+    st = [s[k] for s in sts for k in range(len(s))]
+    arr = lambda f, dt: np.array([getattr(s, f) for s in st], dt)
+    unflat = lambda a: {s.name: a[:, s.z_offset:s.z_offset + s.size].reshape((a.shape[0],) + tuple(s.shape))
+                        for s in bound.latent_sites}
+    squeeze = (lambda a: a[0]) if squeeze_one else (lambda a: a)
+    tree = lambda d: {k: squeeze(v) for k, v in d.items()}
+    imm, msq = cat("inverse_mass_matrix"), cat("mass_matrix_sqrt")
+    key = tuple(sorted(s.name for s in bound.latent_sites))        # one-block structured mass matrix (hmc.py:759-769)
+    adapt = HMCAdaptState(
+        squeeze(arr("step_size", np.float32)), {key: squeeze(imm)}, {key: squeeze(msq)}, {key: squeeze(1.0 / msq)},
+        (squeeze(arr("ss_x_t", np.float32)), squeeze(arr("ss_x_avg", np.float32)), squeeze(arr("ss_g_avg", np.float32)),
+         squeeze(arr("ss_t", np.int32)), squeeze(arr("ss_prox", np.float32))),
+        {key: (squeeze(cat("wf_mean")), squeeze(cat("wf_m2")), squeeze(arr("mm_n", np.int32)))},
+        squeeze(arr("window_idx", np.int32)),
+        squeeze(np.array([[s.adapt_rng_key[0], s.adapt_rng_key[1]] for s in st], np.uint32)))
+    return HMCState(squeeze(arr("i", np.int32)), tree(unflat(cat("z"))), tree(unflat(cat("z_grad"))),
+                    squeeze(arr("potential_energy", np.float32)), squeeze(arr("energy", np.float32)), None,
+                    trajectory_length, squeeze(arr("num_steps", np.int32)),
+                    squeeze(arr("accept_prob", np.float32)), squeeze(arr("mean_accept_prob", np.float32)),
+                    squeeze(arr("diverging", np.int32).astype(bool)), adapt,
+                    squeeze(np.array([[s.rng_key[0], s.rng_key[1]] for s in st], np.uint32)))
+
+
+def _state_to_engine(state: HMCState, bound, engine: Engine, n_total: int, lo: int, hi: int, num_warmup: int, keys=None):
+    """Load chains [lo, hi) of ``state`` (which holds ``n_total`` chains) into ``engine`` (b200nuts_set_state);
+    ``keys`` replaces ``state.rng_key`` (mcmc.py:677-679)."""
+    C = n_total
+    D = engine.D
+
+    def flat(tree):
+        out = np.zeros((C, D), np.float32)
+        for s in bound.latent_sites:
+            out[:, s.z_offset:s.z_offset + s.size] = np.asarray(tree[s.name], np.float32).reshape(C, s.size)
+        return out
+    z, g = flat(state.z), flat(state.z_grad)
+    a = state.adapt_state
+    one = lambda d: np.asarray(next(iter(d.values())) if isinstance(d, dict) else d, np.float32).reshape(C, -1)
+    imm = one(a.inverse_mass_matrix)
+    mm = next(iter(a.mm_state.values())) if isinstance(a.mm_state, dict) else a.mm_state
+    sc = lambda v, dt: np.asarray(v, dt).reshape(C)
+    rk = np.asarray(state.rng_key if keys is None else keys, np.uint32).reshape(C, 2)
+    akeys = np.asarray(a.rng_key, np.uint32).reshape(C, 2)
+    n = hi - lo
+    st = (_capi.ChainState * n)()
+    for k in range(n):
+        c = lo + k
+        st[k].i = int(sc(state.i, np.int32)[c]); st[k].rng_key[0], st[k].rng_key[1] = int(rk[c][0]), int(rk[c][1])
+        st[k].potential_energy = float(sc(state.potential_energy, np.float32)[c]); st[k].energy = float(sc(state.energy, np.float32)[c])
+        st[k].num_steps = int(sc(state.num_steps, np.int32)[c]); st[k].accept_prob = float(sc(state.accept_prob, np.float32)[c])
+        st[k].mean_accept_prob = float(sc(state.mean_accept_prob, np.float32)[c]); st[k].diverging = int(sc(state.diverging, np.int32)[c])
+        st[k].step_size = float(sc(a.step_size, np.float32)[c])
+        st[k].ss_x_t, st[k].ss_x_avg, st[k].ss_g_avg = (float(sc(a.ss_state[j], np.float32)[c]) for j in range(3))
+        st[k].ss_t = int(sc(a.ss_state[3], np.int32)[c]); st[k].ss_prox = float(sc(a.ss_state[4], np.float32)[c])
+        st[k].mm_n = int(sc(mm[2], np.int32)[c]); st[k].window_idx = int(sc(a.window_idx, np.int32)[c])
+        st[k].adapt_rng_key[0], st[k].adapt_rng_key[1] = int(akeys[c][0]), int(akeys[c][1])
+    vec = {"z": z[lo:hi], "z_grad": g[lo:hi], "inverse_mass_matrix": imm[lo:hi],
+           "wf_mean": np.asarray(mm[0], np.float32).reshape(C, -1)[lo:hi],
+           "wf_m2": np.asarray(mm[1], np.float32).reshape(C, -1)[lo:hi]}
+    engine.set_state(st, vec, num_warmup)
+
+
+def _flatten_init(init_params, bound, D):
+    if isinstance(init_params, dict):
+        lat = bound.latent_sites
+        name0 = next(iter(init_params))
+        first = np.asarray(init_params[name0])
+        lead = first.shape[:first.ndim - len(next(s for s in lat if s.name == name0).shape)]
+        n = int(np.prod(lead)) if lead else 1
+        z = np.zeros((n, D), np.float32)
+        for s in lat:
+            z[:, s.z_offset:s.z_offset + s.size] = np.asarray(init_params[s.name], np.float32).reshape(n, s.size)
+        return z
+    return np.asarray(init_params, np.float32).reshape(-1, D)
+
+
+class HMC(_KernelBase):
     """Hamiltonian Monte Carlo kernel (hmc.py:533-822) for a declared model family."""
     _algo = _capi.ALGO_HMC
 
@@ -51,8 +161,11 @@ class HMC:
             raise NotImplementedError("dense / user-supplied mass matrices are not implemented yet (SURVEY.md 8(f) rank 1)")
         if forward_mode_differentiation:
             raise NotImplementedError("gradients are hand-derived; forward_mode_differentiation does not apply")
-        if init_strategy is not None:
-            raise NotImplementedError("only init_to_uniform(radius=2) (the default) or init_params are supported")
+        if init_strategy is None:
+            init_strategy = init_to_uniform()
+        if not isinstance(init_strategy, _InitStrategy):
+            raise NotImplementedError("init_strategy must be numpyro_b200.infer.init_to_uniform / init_to_feasible / init_to_value")
+        self._init_strategy = init_strategy
         self._model = model
         depth = max_tree_depth if isinstance(max_tree_depth, tuple) else (max_tree_depth, max_tree_depth)
         self._cfg = dict(algo=self._algo, step_size=float(step_size), adapt_step_size=int(adapt_step_size),
@@ -62,8 +175,17 @@ class HMC:
                          hmc_num_steps=int(num_steps or 0),
                          trajectory_length=float(trajectory_length if num_steps is None else 0.0) or 2 * np.pi,
                          regime={"auto": 0, "warp": 1, "stream": 2, "gemm": 3}[regime])
+        if init_strategy.kind == "uniform":
+            self._cfg["init_radius"] = init_strategy.radius
         self._trajectory_length = None if num_steps is not None else trajectory_length
+        # MCMCKernel state (init / sample driven one transition at a time)
+        self._engine: Optional[Engine] = None
+        self._bound = None
+        self._num_warmup = 0
+        self._single = True
+        self._engine_state = None         # the HMCState object the engine's device state corresponds to
 
+    # ------------------------------------------------------------------ kernel properties (hmc.py:715-738)
     @property
     def model(self):
         return self._model
@@ -83,6 +205,79 @@ class HMC:
     def get_diagnostics_str(self, state):
         return "{} steps of size {:.2e}. acc. prob={:.2f}".format(
             np.ravel(state.num_steps)[0], np.ravel(state.adapt_state.step_size)[0], np.ravel(state.mean_accept_prob)[0])
+
+    # ------------------------------------------------------------------ init strategy -> unconstrained start
+    def _strategy_z0(self, bound, D, n_chains):
+        """None for a PRNG-drawn start, or the [n_chains, D] unconstrained start the strategy fixes."""
+        st = self._init_strategy
+        if st.kind == "uniform":
+            return None
+        if st.kind == "feasible":
+            return np.zeros((n_chains, D), np.float32)
+        missing = [s.name for s in bound.latent_sites if s.name not in st.values]
+        if missing:
+            raise NotImplementedError(f"init_to_value needs a value for every latent site (missing: {missing})")
+        z = np.zeros((1, D), np.float32)
+        for s in bound.latent_sites:
+            v = np.asarray(st.values[s.name], np.float64).reshape(s.size)
+            if s.positive:
+                if np.any(v <= 0):
+                    raise ValueError(f"init_to_value: site {s.name!r} must be positive")
+                v = np.log(v)                           # inverse of ExpTransform (transforms.py:635-646)
+            z[0, s.z_offset:s.z_offset + s.size] = v
+        return np.repeat(z, n_chains, axis=0)
+
+    # ------------------------------------------------------------------ MCMCKernel (mcmc.py:79-124)
+    def init(self, rng_key, num_warmup, init_params=None, model_args=(), model_kwargs=None):
+        """``MCMCKernel.init`` (mcmc.py:90-108; hmc.py:740-799): bind the model, find valid initial parameters and
+        return the initial ``HMCState``.  A batch of keys ``[C, 2]`` gives a vectorised state of C chains."""
+        keys = np.asarray(rng_key, np.uint32)
+        self._single = keys.ndim == 1
+        keys = keys.reshape(-1, 2)
+        bound = self._model.bind(*model_args, **(model_kwargs or {}))
+        if self._engine is not None:
+            self._engine.close()
+        cfg = dict(self._cfg)
+        cfg.update(bound.cfg)
+        cfg["num_chains"] = keys.shape[0]
+        e = Engine(device=torch.device("cuda", torch.cuda.current_device()), X=bound.X, y=bound.y, aux=bound.aux, **cfg)
+        z0 = _flatten_init(init_params, bound, e.D) if init_params is not None else self._strategy_z0(bound, e.D, keys.shape[0])
+        e.init(keys, int(num_warmup), z0)
+        e.run(0, 0, fields=())                      # evaluates the potential at the start (retrying invalid draws): HMCState.i == 0
+        self._engine, self._bound, self._num_warmup = e, bound, int(num_warmup)
+        st, vec = e.state()
+        self._engine_state = _state_from_engine([st], [vec], bound, self._single, self._trajectory_length)
+        return self._engine_state
+
+    def sample(self, state, model_args=(), model_kwargs=None):
+        """``MCMCKernel.sample`` (mcmc.py:110-124; hmc.py:801-816): one transition from ``state``."""
+        e = self._engine
+        if e is None:
+            raise RuntimeError("sample() called before init()")
+        if state is not self._engine_state:          # a state the engine does not hold (e.g. HMCGibbs edited z): load it
+            _state_to_engine(state, self._bound, e, e.C, 0, e.C, self._num_warmup)
+        e.transition(1)
+        st, vec = e.state()
+        self._engine_state = _state_from_engine([st], [vec], self._bound, self._single, self._trajectory_length)
+        return self._engine_state
+
+    def postprocess_fn(self, model_args=(), model_kwargs=None):
+        """mcmc.py:79-88 / hmc.py:712-713: unconstrained ``z`` dict -> constrained sites + deterministic sites."""
+        bound = self._bound if self._bound is not None else self._model.bind(*model_args, **(model_kwargs or {}))
+        e = self._engine
+        if e is None:
+            raise RuntimeError("postprocess_fn needs init() (the transform runs in the engine)")
+
+        def fn(z):
+            first = np.asarray(z[bound.latent_sites[0].name])
+            lead = first.shape[:first.ndim - len(bound.latent_sites[0].shape)]
+            n = int(np.prod(lead)) if lead else 1
+            flat = np.zeros((n, e.D), np.float32)
+            for s in bound.latent_sites:
+                flat[:, s.z_offset:s.z_offset + s.size] = np.asarray(z[s.name], np.float32).reshape(n, s.size)
+            con = e.constrain(torch.from_numpy(flat).to(e.device)).cpu().numpy()
+            return {s.name: con[:, s.c_offset:s.c_offset + s.size].reshape(tuple(lead) + tuple(s.shape)) for s in bound.sites}
+        return fn
 
 
 class NUTS(HMC):
@@ -142,7 +337,7 @@ class MCMC:
         self._last_state = None
         self._warmup_state = None
         self._collect_warmup = False
-        self._lower, self._upper = num_warmup, num_warmup + num_samples
+        self._args, self._kwargs = (), {}
         self._dist = torch.distributed.is_available() and torch.distributed.is_initialized() and chain_method == "parallel"
 
     # ------------------------------------------------------------------ plumbing
@@ -207,6 +402,17 @@ class MCMC:
         with ThreadPoolExecutor(len(self._shards)) as pool:
             return list(pool.map(fn, self._shards))
 
+    @property
+    def _local_lo(self):
+        return self._shards[0].lo if (self._dist and self._shards) else 0
+
+    @property
+    def _local_chains(self):
+        """Chains whose state this process holds (all of them except under torch.distributed)."""
+        if self._dist and self._shards:
+            return self._shards[0].hi - self._shards[0].lo
+        return self.num_chains
+
     # ------------------------------------------------------------------ run / warmup
     def _chain_keys(self, rng_key):
         rng_key = np.asarray(rng_key, np.uint32)
@@ -220,28 +426,38 @@ class MCMC:
         """mcmc.py:589-633: run the adaptation phase only and keep its last state."""
         self._warmup_state = None
         self._collect_warmup = collect_warmup
-        self._lower, self._upper = (0 if collect_warmup else self.num_warmup), self.num_warmup
-        self._run(rng_key, args, kwargs, extra_fields, init_params, fresh=True)
+        self._run(rng_key, args, kwargs, extra_fields, init_params, lower=0 if collect_warmup else self.num_warmup,
+                  upper=self.num_warmup)
         self._warmup_state = self._last_state
 
     def run(self, rng_key, *args, extra_fields=(), init_params=None, **kwargs):
-        """mcmc.py:635-729."""
+        """mcmc.py:635-729.  With a ``post_warmup_state`` the run starts from that state (its ``rng_key`` replaced by the
+        new one, mcmc.py:677-679) and draws ``num_samples`` MORE samples, whatever the state's iteration counter is."""
         if self._warmup_state is not None:
-            self._lower, self._upper = self.num_warmup, self.num_warmup + self.num_samples
-            self._run(rng_key, args, kwargs, extra_fields, init_params, fresh=False)
+            self._run(rng_key, args, kwargs, extra_fields, init_params, resume=self._warmup_state)
         else:
-            self._lower, self._upper = self.num_warmup, self.num_warmup + self.num_samples
-            self._run(rng_key, args, kwargs, extra_fields, init_params, fresh=True)
+            self._run(rng_key, args, kwargs, extra_fields, init_params, lower=self.num_warmup,
+                      upper=self.num_warmup + self.num_samples)
 
-    def _run(self, rng_key, args, kwargs, extra_fields, init_params, fresh):
+    def _run(self, rng_key, args, kwargs, extra_fields, init_params, lower=None, upper=None, resume=None):
         keys = self._chain_keys(rng_key)
-        if fresh or not self._shards:
+        fresh = resume is None
+        same = lambda a, b: len(a) == len(b) and all(x is y for x, y in zip(a, b))
+        same_data = bool(self._shards) and same(args, self._args) and sorted(kwargs) == sorted(self._kwargs) and \
+            same([kwargs[k] for k in sorted(kwargs)], [self._kwargs[k] for k in sorted(kwargs)])
+        if fresh or not same_data:
             self._ensure_engines(args, kwargs)
+        self._args, self._kwargs = args, kwargs
         bound = self._bound
         D = self._shards[0].engine.D
         z0 = None
-        if init_params is not None:
-            z0 = self._flatten_init(init_params, bound, D)
+        if fresh:
+            z0 = _flatten_init(init_params, bound, D) if init_params is not None else self.sampler._strategy_z0(bound, D, self.num_chains)
+        else:
+            i0 = np.unique(np.asarray(resume.i))
+            if i0.size != 1:
+                raise ValueError("post_warmup_state: every chain must be at the same iteration")
+            lower, upper = int(i0[0]), int(i0[0]) + self.num_samples       # fori_collect(0, num_samples) from that state
         fields = ["z", "diverging"]
         unc_sites, remove = [], set()
         for f in tuple(extra_fields):
@@ -254,6 +470,7 @@ class MCMC:
                     fields.append(_STATE_FIELDS[f])
             else:
                 raise ValueError(f"unsupported extra field {f!r}")
+        n_local, lo0 = self._local_chains, self._local_lo
 
         def work(s: _Shard):
             e = s.engine
@@ -261,13 +478,11 @@ class MCMC:
                 if fresh:
                     e.init(keys[s.lo:s.hi], self.num_warmup, None if z0 is None else z0[s.lo:s.hi])
                 else:
-                    st, vec = e.state()
-                    for k in range(e.C):                      # mcmc.py:677-679: replace the state's rng_key
-                        st[k].rng_key[0], st[k].rng_key[1] = int(keys[s.lo + k][0]), int(keys[s.lo + k][1])
-                    e.set_state(st, vec, self.num_warmup)
-                out = e.run(self._upper, self._lower, self.thinning, fields=fields)
+                    _state_to_engine(resume, bound, e, n_local, s.lo - lo0, s.hi - lo0, self.num_warmup,
+                                     keys=keys[lo0:lo0 + n_local])
+                out = e.run(upper, lower, self.thinning, fields=fields)
                 con = e.constrain(out["z"]).view(e.C, -1, e.Dc)
-                st, vec = e.state()
+                st, vec = e.state()                                  # raises "Cannot find valid initial parameters" (EINIT)
                 host = {k: v.cpu().numpy() for k, v in out.items()}
                 host["_constrained"] = con.cpu().numpy()
                 return host, st, vec
@@ -298,7 +513,8 @@ class MCMC:
             states["z." + name] = block.reshape(block.shape[:2] + tuple(s.shape))
         self._states = states
         self._states_flat = None
-        self._last_state = self._make_state([r[1] for r in results], [r[2] for r in results], bound)
+        self._last_state = _state_from_engine([r[1] for r in results], [r[2] for r in results], bound,
+                                              self.num_chains == 1 and not self._dist, self.sampler._trajectory_length)
 
     def _all_gather(self, host):
         dist = torch.distributed
@@ -312,43 +528,6 @@ class MCMC:
             out[k] = torch.cat(parts, dim=0).cpu().numpy()
         return out
 
-    @staticmethod
-    def _flatten_init(init_params, bound, D):
-        if isinstance(init_params, dict):
-            first = np.asarray(next(iter(init_params.values())))
-            lat = bound.latent_sites
-            lead = first.shape[:first.ndim - len(next(s for s in lat if s.name == next(iter(init_params))).shape)]
-            n = int(np.prod(lead)) if lead else 1
-            z = np.zeros((n, D), np.float32)
-            for s in lat:
-                z[:, s.z_offset:s.z_offset + s.size] = np.asarray(init_params[s.name], np.float32).reshape(n, s.size)
-            return z
-        return np.asarray(init_params, np.float32).reshape(-1, D)
-
-    def _make_state(self, sts, vecs, bound):
-        cat = lambda name: np.concatenate([v[name] for v in vecs], axis=0)
-        st = [s[k] for s in sts for k in range(len(s))]
-        arr = lambda f, dt: np.array([getattr(s, f) for s in st], dt)
-        unflat = lambda a: {s.name: a[:, s.z_offset:s.z_offset + s.size].reshape((a.shape[0],) + tuple(s.shape))
-                            for s in bound.latent_sites}
-        squeeze = (lambda a: a[0]) if self.num_chains == 1 and not self._dist else (lambda a: a)
-        tree = lambda d: {k: squeeze(v) for k, v in d.items()}
-        imm, msq = cat("inverse_mass_matrix"), cat("mass_matrix_sqrt")
-        key = tuple(sorted(s.name for s in bound.latent_sites))        # one-block structured mass matrix (hmc.py:759-769)
-        adapt = HMCAdaptState(
-            squeeze(arr("step_size", np.float32)), {key: squeeze(imm)}, {key: squeeze(msq)}, {key: squeeze(1.0 / msq)},
-            (squeeze(arr("ss_x_t", np.float32)), squeeze(arr("ss_x_avg", np.float32)), squeeze(arr("ss_g_avg", np.float32)),
-             squeeze(arr("ss_t", np.int32)), squeeze(arr("ss_prox", np.float32))),
-            {key: (squeeze(cat("wf_mean")), squeeze(cat("wf_m2")), squeeze(arr("mm_n", np.int32)))},
-            squeeze(arr("window_idx", np.int32)),
-            squeeze(np.array([[s.adapt_rng_key[0], s.adapt_rng_key[1]] for s in st], np.uint32)))
-        return HMCState(squeeze(arr("i", np.int32)), tree(unflat(cat("z"))), tree(unflat(cat("z_grad"))),
-                        squeeze(arr("potential_energy", np.float32)), squeeze(arr("energy", np.float32)), None,
-                        self.sampler._trajectory_length, squeeze(arr("num_steps", np.int32)),
-                        squeeze(arr("accept_prob", np.float32)), squeeze(arr("mean_accept_prob", np.float32)),
-                        squeeze(arr("diverging", np.int32).astype(bool)), adapt,
-                        squeeze(np.array([[s.rng_key[0], s.rng_key[1]] for s in st], np.uint32)))
-
     # ------------------------------------------------------------------ results
     @property
     def last_state(self):
@@ -360,47 +539,8 @@ class MCMC:
 
     @post_warmup_state.setter
     def post_warmup_state(self, state):
-        """mcmc.py:558-587: continue sampling from a previous (post warm-up) state."""
+        """mcmc.py:558-587: continue sampling from a previous (post warm-up) state; ``run`` loads it into the engine."""
         self._warmup_state = state
-        if state is not None and self._shards:
-            self._push_state(state)
-
-    def _push_state(self, state: HMCState):
-        bound = self._bound
-        C = self.num_chains
-        lead = lambda a: np.asarray(a).reshape((C,) + np.asarray(a).shape[(0 if C == 1 and np.asarray(a).ndim == 0 else (1 if C > 1 else 0)):])
-        def flat(tree):
-            out = np.zeros((C, self._shards[0].engine.D), np.float32)
-            for s in bound.latent_sites:
-                out[:, s.z_offset:s.z_offset + s.size] = np.asarray(tree[s.name], np.float32).reshape(C, s.size)
-            return out
-        z, g = flat(state.z), flat(state.z_grad)
-        a = state.adapt_state
-        one = lambda d: np.asarray(next(iter(d.values())) if isinstance(d, dict) else d, np.float32).reshape(C, -1)
-        imm = one(a.inverse_mass_matrix)
-        mm = next(iter(a.mm_state.values())) if isinstance(a.mm_state, dict) else a.mm_state
-        sc = lambda v, dt: np.asarray(v, dt).reshape(C)
-        keys = np.asarray(state.rng_key, np.uint32).reshape(C, 2)
-        akeys = np.asarray(a.rng_key, np.uint32).reshape(C, 2)
-        for s in self._shards:
-            n = s.hi - s.lo
-            st = (_capi.ChainState * n)()
-            for k in range(n):
-                c = s.lo + k
-                st[k].i = int(sc(state.i, np.int32)[c]); st[k].rng_key[0], st[k].rng_key[1] = int(keys[c][0]), int(keys[c][1])
-                st[k].potential_energy = float(sc(state.potential_energy, np.float32)[c]); st[k].energy = float(sc(state.energy, np.float32)[c])
-                st[k].num_steps = int(sc(state.num_steps, np.int32)[c]); st[k].accept_prob = float(sc(state.accept_prob, np.float32)[c])
-                st[k].mean_accept_prob = float(sc(state.mean_accept_prob, np.float32)[c]); st[k].diverging = int(sc(state.diverging, np.int32)[c])
-                st[k].step_size = float(sc(a.step_size, np.float32)[c])
-                st[k].ss_x_t, st[k].ss_x_avg, st[k].ss_g_avg = (float(sc(a.ss_state[j], np.float32)[c]) for j in range(3))
-                st[k].ss_t = int(sc(a.ss_state[3], np.int32)[c]); st[k].ss_prox = float(sc(a.ss_state[4], np.float32)[c])
-                st[k].mm_n = int(sc(mm[2], np.int32)[c]); st[k].window_idx = int(sc(a.window_idx, np.int32)[c])
-                st[k].adapt_rng_key[0], st[k].adapt_rng_key[1] = int(akeys[c][0]), int(akeys[c][1])
-            vec = {"z": z[s.lo:s.hi], "z_grad": g[s.lo:s.hi], "inverse_mass_matrix": imm[s.lo:s.hi],
-                   "wf_mean": np.asarray(mm[0], np.float32).reshape(C, -1)[s.lo:s.hi],
-                   "wf_m2": np.asarray(mm[1], np.float32).reshape(C, -1)[s.lo:s.hi]}
-            with torch.cuda.device(s.device):
-                s.engine.set_state(st, vec, self.num_warmup)
 
     def get_samples(self, group_by_chain=False):
         """mcmc.py:549-556."""

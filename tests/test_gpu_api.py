@@ -51,14 +51,85 @@ def test_warmup_then_run_matches_single_run_and_state_resume():
     b = MCMC(NUTS(families.EightSchoolsNonCentered()), **kw)
     b.run(key, J, S8, y=Y8)
     np.testing.assert_array_equal(first["mu"], b.get_samples()["mu"])
-    # continue sampling from the last state (mcmc.py:558-587)
+    # continue sampling from the last state (mcmc.py:558-587): num_samples MORE draws, bit-identical to the tail of one
+    # longer run because every chain keeps its own key stream
+    long = MCMC(NUTS(families.EightSchoolsNonCentered()), num_warmup=100, num_samples=100, num_chains=2,
+                chain_method="vectorized", progress_bar=False)
+    long.run(key, J, S8, y=Y8)
+    want = long.get_samples(group_by_chain=True)
+    b.post_warmup_state = b.last_state
+    b.run(b.last_state.rng_key, J, S8, y=Y8)
+    got = b.get_samples(group_by_chain=True)
+    assert np.all(b.last_state.i == 200)
+    for k in want:
+        assert got[k].shape == (2, 50) + want[k].shape[2:]
+        np.testing.assert_array_equal(got[k], want[k][:, 50:])
+        assert np.all(np.isfinite(got[k])) and np.std(got[k]) > 0
+    assert not np.array_equal(got["tau"], first["tau"].reshape(2, 50))
+    # the reference pattern with a FRESH MCMC object (no engine yet when the state is assigned)
     c = MCMC(NUTS(families.EightSchoolsNonCentered()), **kw)
-    c.warmup(key, J, S8, y=Y8)
-    c.post_warmup_state = b.last_state
-    c.run(b.last_state.rng_key, J, S8, y=Y8)
-    a.post_warmup_state = a.last_state
-    a.run(a.last_state.rng_key, J, S8, y=Y8)
-    np.testing.assert_array_equal(a.get_samples()["tau"], c.get_samples()["tau"])
+    c.post_warmup_state = a.last_state
+    c.run(a.last_state.rng_key, J, S8, y=Y8)
+    np.testing.assert_array_equal(c.get_samples(group_by_chain=True)["tau"], want["tau"][:, 50:])
+    # a second run() after warmup() + run() restarts from the post warm-up state (mcmc.py:677-679)
+    a.run(wstate.rng_key, J, S8, y=Y8)
+    np.testing.assert_array_equal(a.get_samples()["mu"], first["mu"])
+
+
+def test_mcmc_kernel_interface_init_sample_postprocess():
+    """The MCMCKernel plug-in surface (mcmc.py:79-124): kernel.init + repeated kernel.sample reproduce MCMC.run
+    transition by transition; postprocess_fn constrains like the collection path."""
+    key = b2random.PRNGKey(3)
+    nw, ns = 40, 15
+    ref = MCMC(NUTS(families.EightSchoolsNonCentered()), num_warmup=nw, num_samples=ns, num_chains=1, progress_bar=False)
+    ref.run(key, J, S8, y=Y8, extra_fields=("num_steps", "z.tau"))
+    want = ref.get_samples()
+    kern = NUTS(families.EightSchoolsNonCentered())
+    assert kern.sample_field == "z" and kern.default_fields == ("z", "diverging") and not kern.is_ensemble_kernel
+    state = kern.init(key, nw, None, model_args=(J, S8), model_kwargs=dict(y=Y8))
+    assert int(state.i) == 0 and state.z["theta_base"].shape == (8,) and state.adapt_state.step_size == 1.0
+    post = kern.postprocess_fn((J, S8), dict(y=Y8))
+    steps = []
+    for t in range(nw + ns):
+        state = kern.sample(state, (J, S8), dict(y=Y8))
+        assert int(state.i) == t + 1
+        if t >= nw:
+            con = post(state.z)
+            np.testing.assert_array_equal(con["mu"], want["mu"][t - nw])
+            np.testing.assert_array_equal(con["theta"], want["theta"][t - nw])
+            np.testing.assert_allclose(con["tau"], np.exp(state.z["tau"]), rtol=1e-6)
+            steps.append(int(state.num_steps))
+    np.testing.assert_array_equal(steps, ref.get_extra_fields()["num_steps"])
+    assert "steps of size" in kern.get_diagnostics_str(state)
+    # a state the engine does not hold (edited by an outer kernel such as HMCGibbs) is loaded before the transition
+    edited = ref.last_state
+    again = kern.sample(edited, (J, S8), dict(y=Y8))
+    assert int(again.i) == nw + ns + 1
+    # vectorised: a batch of keys gives a batched state
+    vstate = kern.init(b2random.split(key, 3), 5, None, model_args=(J, S8), model_kwargs=dict(y=Y8))
+    assert vstate.z["mu"].shape == (3,) and kern.sample(vstate, (J, S8), dict(y=Y8)).i.tolist() == [1, 1, 1]
+
+
+def test_init_strategies():
+    """initialization.py:88-155."""
+    from numpyro_b200.infer import init_to_feasible, init_to_uniform, init_to_value
+    key = b2random.PRNGKey(4)
+    kw = dict(num_warmup=0, num_samples=1, num_chains=2, chain_method="vectorized", progress_bar=False)
+    vals = {"mu": 1.5, "tau": 2.0, "theta_base": np.linspace(-1, 1, 8)}
+    z0 = {"mu": np.full(2, 1.5), "tau": np.full((2,), np.log(2.0)), "theta_base": np.tile(np.linspace(-1, 1, 8), (2, 1))}
+    a = MCMC(NUTS(families.EightSchoolsNonCentered(), init_strategy=init_to_value(values=vals)), **kw)
+    a.run(key, J, S8, y=Y8)
+    b = MCMC(NUTS(families.EightSchoolsNonCentered()), **kw)
+    b.run(key, J, S8, y=Y8, init_params=z0)
+    np.testing.assert_array_equal(a.get_samples()["theta"], b.get_samples()["theta"])      # same start, same key stream
+    f = NUTS(families.EightSchoolsNonCentered(), init_strategy=init_to_feasible())
+    st = f.init(key, 0, None, model_args=(J, S8), model_kwargs=dict(y=Y8))
+    assert np.all(st.z["theta_base"] == 0) and st.z["mu"] == 0 and st.z["tau"] == 0
+    u = NUTS(families.EightSchoolsNonCentered(), init_strategy=init_to_uniform(radius=0.5))
+    st = u.init(key, 0, None, model_args=(J, S8), model_kwargs=dict(y=Y8))
+    assert np.all(np.abs(st.z["theta_base"]) <= 0.5) and np.any(st.z["theta_base"] != 0)
+    with pytest.raises(NotImplementedError):
+        MCMC(NUTS(families.EightSchoolsNonCentered(), init_strategy=init_to_value(values={"mu": 0.0})), **kw).run(key, J, S8, y=Y8)
 
 
 def test_hmc_and_thinning_and_sequential_chains():
