@@ -135,6 +135,13 @@ int b200nuts_transition(B200Nuts* h, int32_t n_iter, void* stream);
  * inside a persistent kernel timed out or the launch failed). */
 int b200nuts_sync(B200Nuts* h);
 
+/* Enqueue-only export of the HMCState fields MCMC collects, into caller-owned DEVICE buffers (any may be NULL):
+ * z, z_grad [num_chains][D]; scalars [num_chains][B200NUTS_STATE_SCALARS] = {i, potential_energy, energy, num_steps,
+ * accept_prob, mean_accept_prob, diverging, step_size} as floats.  Stream-ordered after b200nuts_transition / run; this
+ * is what the XLA-FFI handler returns (ffi/b200nuts_ffi.cc). */
+#define B200NUTS_STATE_SCALARS 8
+int b200nuts_state_to_device(B200Nuts* h, float* z, float* z_grad, float* scalars, void* stream);
+
 /* Synchronising. vectors (host, each [num_chains][D], may be NULL): z, z_grad, inverse_mass_matrix,
  * mass_matrix_sqrt, welford mean, welford m2. */
 int b200nuts_get_state(B200Nuts* h, B200NutsChainState* states, float* z, float* z_grad, float* inv_mass,

@@ -97,6 +97,7 @@ EXPORTS = {
     "b200nuts_transition": (C.c_int, [vp, i32, vp]),
     "b200nuts_sync": (C.c_int, [vp]),
     "b200nuts_gemm_info": (C.c_int, [vp, vp]),
+    "b200nuts_state_to_device": (C.c_int, [vp, vp, vp, vp, vp]),
     "b200nuts_get_state": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "b200nuts_set_state": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i32, vp]),
     "b200nuts_shard_export": (C.c_int, [vp, vp]),

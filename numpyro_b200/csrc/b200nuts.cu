@@ -156,6 +156,19 @@ __global__ void k_constrain(FamilySpec f, const float* z, long long n, float* ou
     if (Dc > f.D) { B2_FOR_D(j, f.Dx) o[f.D + j] = glm_scale_at(f, zr, j) * zr[f.off_u + j]; }   // betas
 }
 
+// HMCState fields of every chain -> caller's device buffers (the outputs of the XLA-FFI transition call)
+__global__ void k_state_export(const ChainCtl* ctl, const float* vecs, int C, int D, int Dp, float* z, float* z_grad, float* scalars) {
+    const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (chain >= C) return;
+    const float* vz = vecs + ((size_t)V_Z * C + chain) * Dp; const float* vg = vecs + ((size_t)V_G * C + chain) * Dp;
+    B2_FOR_D(d, D) { if (z) z[(size_t)chain * D + d] = vz[d]; if (z_grad) z_grad[(size_t)chain * D + d] = vg[d]; }
+    if (scalars && (threadIdx.x & 31) == 0) {
+        const ChainCtl& c = ctl[chain]; float* o = scalars + (size_t)chain * B200NUTS_STATE_SCALARS;
+        o[0] = (float)c.i; o[1] = c.pe; o[2] = c.energy; o[3] = (float)c.num_steps; o[4] = c.accept_prob; o[5] = c.mean_accept_prob;
+        o[6] = (float)c.diverging; o[7] = c.step_size;
+    }
+}
+
 __global__ void k_lgamma_sum(const float* y, long long n, double* out) {
     double a = 0.0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -611,6 +624,15 @@ int b200nuts_sync(B200Nuts* h) {
     if (!h) return B200NUTS_EINVAL;
     std::lock_guard<std::mutex> lk(h->mu);
     return sync_locked(h);
+}
+
+int b200nuts_state_to_device(B200Nuts* h, float* z, float* z_grad, float* scalars, void* stream) {
+    if (!h) return B200NUTS_EINVAL;
+    std::lock_guard<std::mutex> lk(h->mu);
+    k_state_export<<<(h->C + 3) / 4, 128, 0, (cudaStream_t)stream>>>(h->ctl, h->vecs, h->C, h->D, h->Dp, z, z_grad, scalars);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return 0;
 }
 
 int b200nuts_get_state(B200Nuts* h, B200NutsChainState* states, float* z, float* z_grad, float* inv_mass,

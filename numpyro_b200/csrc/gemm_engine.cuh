@@ -12,7 +12,8 @@
 //     SWIZZLE_128B tiles moved by cp.async.bulk = the TMA engine, 3-stage mbarrier ring), D = logits in tensor memory;
 //   * epilogue warps pull the logits out of TMEM (tcgen05.ld), apply the link function (loss + residual), and write the
 //     residuals back INTO tensor memory (tcgen05.st) -- they become the A operand of the backward MMAs straight from TMEM,
-//     so R never touches shared or global memory;
+//     so R never touches shared or global memory; they are delivered in four row groups so that the backward MMAs of
+//     group 0 start after a quarter of the epilogue;
 //   * backward: tcgen05.mma with A = R from TMEM, B = X^T [<= 256 columns x 32 rows] from shared memory (a transposed tile
 //     image of X, also K-major), D = gbeta^T [128 chains x <= 256 columns] in TMEM.
 //
@@ -67,7 +68,8 @@ struct GemmParams {
     int CT, RC, KB, S, cps, NDB, Dxp;          // cps = chunks per segment
     long long N;
     unsigned int* abort_flag; long long spin_limit;
-    unsigned long long* dbg;                   // [0] cycles of CTA 0, [1] its units, [2] MMA thread waiting for the epilogue
+    unsigned long long* dbg;                   // CTA 0: [0] cycles, [1] units, MMA thread waiting [2] for the epilogue, [3] for tile
+                                               // copies, [4] for its own backward MMAs to complete
 };
 
 B2_HD size_t gemm_smem_bytes() { return (size_t)kGtStages * kGtStageBytes + kGtYSlots * 512 + 1024 /* alignment */ + 2048; }
@@ -85,16 +87,17 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_pass_kernel(const __grid_c
     uint64_t* empty = bars + kGtStages;        // [kGtStages]
     uint64_t* ybar = bars + 2 * kGtStages;     // [kGtYSlots]
     uint64_t* l_full = ybar + kGtYSlots;       // forward MMAs of a chunk done
-    uint64_t* r_ready = l_full + 1;            // residuals are in TMEM
-    uint64_t* g_full = l_full + 2;             // backward MMAs of a chunk done
-    uint64_t* g_free = l_full + 3;             // gbeta drained
-    uint32_t* tmem_slot = (uint32_t*)(l_full + 4);
+    uint64_t* g_full = l_full + 1;             // backward MMAs of a chunk done
+    uint64_t* g_free = l_full + 2;             // gbeta drained
+    uint64_t* r_ready = l_full + 3;            // [4] residuals of rows [32 rk, 32 rk + 32) of the chunk are in TMEM
+    uint32_t* tmem_slot = (uint32_t*)(l_full + 7);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int i = 0; i < kGtStages; ++i) { u_mbar_init(&full[i], 1); u_mbar_init(&empty[i], 1); }
         for (int i = 0; i < kGtYSlots; ++i) u_mbar_init(&ybar[i], 1);
-        u_mbar_init(l_full, 1); u_mbar_init(r_ready, kGtEpiWarps); u_mbar_init(g_full, 1); u_mbar_init(g_free, kGtEpiWarps);
+        u_mbar_init(l_full, 1); u_mbar_init(g_full, 1); u_mbar_init(g_free, kGtEpiWarps);
+        for (int i = 0; i < 4; ++i) u_mbar_init(&r_ready[i], kGtEpiWarps);
         u_fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_pass_kernel(const __grid_c
     const int per_block = n_active * p.S;                 // units per column block
     const int n_units = per_block * p.NDB;
     const long long t_start = clock64();
-    unsigned long long wait_epi = 0ull;
+    unsigned long long wait_epi = 0ull, wait_tma = 0ull, wait_mma = 0ull;
 
     if (warp == 0) {
         // ================================================================= producer: one lane feeds the ring
@@ -159,10 +162,18 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_pass_kernel(const __grid_c
                     const uint32_t cpar = chunk_no & 1u;
                     // the previous chunk's backward MMAs read the residuals from the columns the logits go to: they must
                     // have completed (g_full of the previous chunk) before the forward MMAs of this chunk are issued
-                    if (chunk_no > 0) ok = u_mbar_wait(g_full, cpar ^ 1u, p.spin_limit, p.abort_flag, 13u);
+                    if (chunk_no > 0) {
+                        const long long tw = clock64();
+                        ok = u_mbar_wait(g_full, cpar ^ 1u, p.spin_limit, p.abort_flag, 13u);
+                        wait_mma += (unsigned long long)(clock64() - tw);
+                    }
                     tc_fence_after();
                     for (int kb = 0; kb < p.KB && ok; ++kb) {
-                        ok = u_mbar_wait(&full[st], ph, p.spin_limit, p.abort_flag, 14u);
+                        {
+                            const long long tw = clock64();
+                            ok = u_mbar_wait(&full[st], ph, p.spin_limit, p.abort_flag, 14u);
+                            wait_tma += (unsigned long long)(clock64() - tw);
+                        }
                         tc_fence_after();
                         const uint32_t sa = u_smem(stage + (size_t)st * kGtStageBytes);
                         const uint64_t bh = umma_desc_k_sw128(sa), bl = umma_desc_k_sw128(sa + 16384u);
@@ -178,15 +189,20 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_pass_kernel(const __grid_c
                         if (++st == kGtStages) { st = 0; ph ^= 1u; }
                     }
                     umma_commit(l_full);
-                    {
-                        const long long tw = clock64();
-                        ok = ok && u_mbar_wait(r_ready, cpar, p.spin_limit, p.abort_flag, 15u);
-                        if (chunk_no > 0) ok = ok && u_mbar_wait(g_free, cpar ^ 1u, p.spin_limit, p.abort_flag, 16u);
-                        wait_epi += (unsigned long long)(clock64() - tw);
-                    }
-                    tc_fence_after();
+                    // the epilogue delivers the residuals in four groups of 32 rows (= one backward k-block each): the backward
+                    // MMAs of a group start while the link function of the next groups is still being evaluated
                     for (uint32_t rk = 0; rk < 4 && ok; ++rk) {
-                        ok = u_mbar_wait(&full[st], ph, p.spin_limit, p.abort_flag, 17u);
+                        {
+                            const long long tw = clock64();
+                            ok = u_mbar_wait(&r_ready[rk], cpar, p.spin_limit, p.abort_flag, 15u);
+                            if (rk == 0 && chunk_no > 0) ok = ok && u_mbar_wait(g_free, cpar ^ 1u, p.spin_limit, p.abort_flag, 16u);
+                            wait_epi += (unsigned long long)(clock64() - tw);
+                        }
+                        {
+                            const long long tw = clock64();
+                            ok = ok && u_mbar_wait(&full[st], ph, p.spin_limit, p.abort_flag, 17u);
+                            wait_tma += (unsigned long long)(clock64() - tw);
+                        }
                         tc_fence_after();
                         const uint32_t sa = u_smem(stage + (size_t)st * kGtStageBytes);
                         const uint64_t th = umma_desc_k_sw128(sa), tl = umma_desc_k_sw128(sa + (uint32_t)nb * 128u);
@@ -230,17 +246,19 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_pass_kernel(const __grid_c
                 ok = __all_sync(0xFFFFFFFFu, ok);            // (tcgen05.ld / st are warp-collective: leave together)
                 if (!ok) break;
                 tc_fence_after();
-                // ---- logits -> loss, residual (hi, lo) back into TMEM.  Columns [32 cg, 32 cg + 32) of this thread's chain.
+                // ---- logits -> loss, residual (hi, lo) back into TMEM.  Row group rk (32 rows = one backward k-block) is
+                //      shared by all 16 warps: this warp takes its chains' columns [32 rk + 8 cg, +8), so group 0 is complete
+                //      after a quarter of the epilogue and the backward MMAs overlap with the rest.
                 float nl0 = 0.0f, nl1 = 0.0f;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int col = 32 * cg + 16 * h;
-                    uint32_t a[16], b[16];
-                    tmem_ld16(tmem + lane_base + kColLa + col, a);
-                    tmem_ld16(tmem + lane_base + kColLb + col, b);
+                for (int rk = 0; rk < 4; ++rk) {
+                    const int col = 32 * rk + 8 * cg;
+                    uint32_t a[8], b[8];
+                    tmem_ld8(tmem + lane_base + kColLa + col, a);
+                    tmem_ld8(tmem + lane_base + kColLb + col, b);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
+                    for (int i = 0; i < 8; ++i) {
                         const float eta = __uint_as_float(a[i]) + __uint_as_float(b[i]);
                         float loss, dl;
                         link_fn<LIK>(eta, ysm[ys * 128 + col + i], loss, dl);
@@ -249,13 +267,13 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_pass_kernel(const __grid_c
                         a[i] = __float_as_uint(dl);
                         b[i] = __float_as_uint(u_tf32_lo(dl));
                     }
-                    tmem_st16(tmem + lane_base + kColLa + col, a);
-                    tmem_st16(tmem + lane_base + kColLb + col, b);
+                    tmem_st8(tmem + lane_base + kColLa + col, a);
+                    tmem_st8(tmem + lane_base + kColLb + col, b);
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) u_mbar_arrive(&r_ready[rk]);
                 }
-                tmem_wait_st();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) u_mbar_arrive(r_ready);
                 nll_unit += nl0 + nl1;
                 // ---- drain gbeta of this chunk into the fp32 sums (columns [64 cg, 64 cg + 64) of this thread's chain)
                 ok = u_mbar_wait(g_full, cpar, p.spin_limit, p.abort_flag, 20u);
@@ -301,7 +319,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_pass_kernel(const __grid_c
     if (blockIdx.x == 0 && tid == 32 && p.dbg) {
         p.dbg[0] += (unsigned long long)(clock64() - t_start);
         p.dbg[1] += (unsigned long long)((n_units + (int)gridDim.x - 1) / (int)gridDim.x);
-        p.dbg[2] += wait_epi;
+        p.dbg[2] += wait_epi; p.dbg[3] += wait_tma; p.dbg[4] += wait_mma;
     }
 }
 

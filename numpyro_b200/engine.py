@@ -170,6 +170,15 @@ class Engine:
         if sync:
             self.sync()
 
+    @_on_device
+    def state_to_device(self):
+        """Enqueue-only export of (z, z_grad, scalars[C, 8]) into device tensors (b200nuts_state_to_device)."""
+        z = torch.empty((self.C, self.D), dtype=torch.float32, device=self.device)
+        g = torch.empty_like(z)
+        sc = torch.empty((self.C, 8), dtype=torch.float32, device=self.device)
+        self._check(self.lib.b200nuts_state_to_device(self.h, _ptr(z), _ptr(g), _ptr(sc), self._stream()), "b200nuts_state_to_device")
+        return z, g, sc
+
     def sync(self):
         """Wait for the last enqueued launch and raise if it failed (b200nuts_sync)."""
         self._check(self.lib.b200nuts_sync(self.h), "b200nuts_sync")

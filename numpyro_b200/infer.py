@@ -440,6 +440,8 @@ class MCMC:
                       upper=self.num_warmup + self.num_samples)
 
     def _run(self, rng_key, args, kwargs, extra_fields, init_params, lower=None, upper=None, resume=None):
+        import time as _time
+        t_begin = _time.perf_counter()
         keys = self._chain_keys(rng_key)
         fresh = resume is None
         same = lambda a, b: len(a) == len(b) and all(x is y for x, y in zip(a, b))
@@ -448,6 +450,7 @@ class MCMC:
         if fresh or not same_data:
             self._ensure_engines(args, kwargs)
         self._args, self._kwargs = args, kwargs
+        t_engines = _time.perf_counter()
         bound = self._bound
         D = self._shards[0].engine.D
         z0 = None
@@ -488,6 +491,7 @@ class MCMC:
                 return host, st, vec
 
         results = self._for_each_shard(work)
+        t_work = _time.perf_counter()
         if self.row_shards > 1:
             results = results[:1]              # every rank holds the same (bit-identical) chains
         #: gradient evaluations (leapfrogs) spent so far by every local chain, warm-up included
@@ -515,6 +519,10 @@ class MCMC:
         self._states_flat = None
         self._last_state = _state_from_engine([r[1] for r in results], [r[2] for r in results], bound,
                                               self.num_chains == 1 and not self._dist, self.sampler._trajectory_length)
+        #: wall-clock split of this call (ms): H2D of the data + engine creation (tile images), chain init + sampling +
+        #: constrain + D2H of the samples, host-side assembly of the result dicts
+        self.timings = {"h2d_and_engine_create": 1e3 * (t_engines - t_begin), "init_sample_d2h": 1e3 * (t_work - t_engines),
+                        "assemble": 1e3 * (_time.perf_counter() - t_work)}
 
     def _all_gather(self, host):
         dist = torch.distributed

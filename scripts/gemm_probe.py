@@ -72,7 +72,7 @@ def main():
         print(f"run {rep}: {n} passes in {ms:.2f} ms = {ms / n:.3f} ms per pass; {l1 - l0} grad-evals "
               f"({(l1 - l0) / n:.0f} per pass) -> {(l1 - l0) / ms * 1e3:.0f} grad-evals/s, {flops / ms * 1e-9:.1f} algorithmic TFLOP/s; "
               f"CTA0: {(c1[0] - c0[0]) / n:.0f} cycles per pass in the kernel, {(c1[1] - c0[1]) / n:.1f} units, MMA thread waiting for the epilogue "
-              f"{(c1[2] - c0[2]) / n:.0f} cycles", flush=True)
+              f"{(c1[2] - c0[2]) / n:.0f} cycles, for tile copies {(c1[3] - c0[3]) / n:.0f}, for its own MMAs {(c1[4] - c0[4]) / n:.0f}", flush=True)
     st, _ = e.state()
     print("iterations reached:", min(s.i for s in st), max(s.i for s in st), "step sizes:", np.percentile([s.step_size for s in st], [0, 50, 100]))
 
