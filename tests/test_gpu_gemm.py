@@ -183,12 +183,22 @@ def test_config3_full_shape_gemm(lik):
         return                                   # (the whole-run comparison below is likelihood independent)
     keys = prng.split(prng.key(5), C)
     e.init(keys, 6)
-    out = e.run(10, 6, fields=("z", "num_steps", "diverging", "accept_prob", "potential_energy", "energy", "step_size", "mean_accept_prob"))
+    out = e.run(10, 6, fields=FIELDS)
     for c in (7, C - 1):
         kern = chain.Kernel(device_potential(e, c), max_tree_depth=(5, 5))
         res, _ = chain.run_chain(kern, fam, keys[c], 6, 4, fields=FIELDS)
         assert_run_equal(out, res, c)
     assert torch.isfinite(out["z"]).all() and int(out["num_steps"].sum().item()) >= 4 * C
+    # deeper trees (fixed small step, up to 31 leapfrogs per transition), all 16384 chains asynchronous
+    d = glm_engine(C, X, y, global_scale=_capi.SCALE_HALFCAUCHY, group_col_begin=192, group_col_end=256, tau_scale=1.0,
+                   max_tree_depth_warmup=5, max_tree_depth=5, step_size=0.02, adapt_step_size=0)
+    d.init(keys, 2)
+    outd = d.run(5, 2, fields=FIELDS)
+    assert outd["num_steps"].float().mean().item() > 8
+    for c in (1, 9000):
+        kern = chain.Kernel(device_potential(d, c), max_tree_depth=(5, 5), step_size=0.02, adapt_step_size=False)
+        res, _ = chain.run_chain(kern, fam, keys[c], 2, 3, fields=FIELDS)
+        assert_run_equal(outd, res, c)
 
 
 @pytest.mark.parametrize("lik", ["normal", "bernoulli"])
