@@ -175,6 +175,14 @@ int b200nuts_leapfrog(B200Nuts* h, const float* eps, const float* inv_mass, floa
 int b200nuts_constrain(B200Nuts* h, const float* z, int64_t n, float* out, void* stream);
 int b200nuts_constrained_dim(const B200Nuts* h);
 
+/* The consumers of the collected samples (numpyro/infer/util.py log_likelihood :1133-1188,
+ * Predictive :927-1131) for the registered families.  z: device [n][D] unconstrained samples; out: device
+ * [n][b200nuts_obs_count] -- the observed site's log_prob per observation, or a draw from it with the per-sample key
+ * keys[n][2] (device) that numpyro's seed handler would hand to that site.  Enqueue only. */
+int b200nuts_log_likelihood(B200Nuts* h, const float* z, int64_t n, float* out, void* stream);
+int b200nuts_predict(B200Nuts* h, const float* z, const uint32_t* keys, int64_t n, float* out, void* stream);
+int64_t b200nuts_obs_count(const B200Nuts* h);
+
 /* PRNG parity hooks: host in / host out, computed on the device, synchronising. */
 int b200nuts_prng_split(const uint32_t* keys, int64_t n_keys, int32_t num, uint32_t* out);      /* out [n_keys][num][2] */
 int b200nuts_prng_bits(const uint32_t* key, int64_t n, uint32_t* out);

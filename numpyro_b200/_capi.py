@@ -106,6 +106,9 @@ EXPORTS = {
     "b200nuts_leapfrog": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i32, vp]),
     "b200nuts_constrain": (C.c_int, [vp, vp, i64, vp, vp]),
     "b200nuts_constrained_dim": (C.c_int, [vp]),
+    "b200nuts_log_likelihood": (C.c_int, [vp, vp, i64, vp, vp]),
+    "b200nuts_predict": (C.c_int, [vp, vp, vp, i64, vp, vp]),
+    "b200nuts_obs_count": (i64, [vp]),
     "b200nuts_prng_split": (C.c_int, [vp, i64, i32, vp]),
     "b200nuts_prng_bits": (C.c_int, [vp, i64, vp]),
     "b200nuts_prng_uniform": (C.c_int, [vp, i64, f32, f32, vp]),

@@ -18,6 +18,7 @@
 #include "engine.cuh"
 #include "stream_engine.cuh"
 #include "gemm_engine.h"
+#include "predict.cuh"
 
 using namespace b2;
 
@@ -255,6 +256,7 @@ static int stream_launch(B200Nuts* h, int mode, const OutBufs& out, const float*
     p.vecs_in_smem = h->vecs_in_smem; p.spin_limit = 2000000000LL;      // ~1 s: every wait in the engine is bounded
     { const char* e = getenv("B200NUTS_SPIN_LIMIT"); if (e) p.spin_limit = atoll(e); }
     { const char* e = getenv("B200NUTS_NO_PREFETCH"); p.no_prefetch = e ? atoi(e) : 0; }
+    { const char* e = getenv("B200NUTS_NO_PEEK"); p.no_peek = e ? atoi(e) : 0; }
     if (getenv("B200NUTS_TRACE") && !h->trace_host) {
         if (cudaHostAlloc((void**)&h->trace_host, sizeof(unsigned int) * 32 * h->grid, cudaHostAllocMapped) == cudaSuccess)
             cudaHostGetDevicePointer((void**)&h->trace_dev, h->trace_host, 0);
@@ -342,6 +344,9 @@ static int check_stream_abort(B200Nuts* h, cudaStream_t st) {
     CK(cudaStreamSynchronize(st));
     h->passes += (long long)s.passes;
     for (int i = 0; i < 16; ++i) h->dbg[i] = s.dbg[i];
+    // [11..13]: positions published ahead of the tick (Tick::peek_next), fall-backs, mismatches -- summed over the chains
+    h->dbg[11] = h->dbg[12] = h->dbg[13] = 0ull;
+    for (int c = 0; c < h->C && c < kMaxStreamChains; ++c) { h->dbg[11] += s.peek_hit[c]; h->dbg[12] += s.peek_fallback[c]; h->dbg[13] += s.peek_mismatch[c]; }
     if (getenv("B200NUTS_DEBUG_TICK")) {
         for (int c = 0; c < h->C; ++c)
             fprintf(stderr, "[b200nuts] owner %d: passes %llu tick avg %.0f max %llu | per pass: finish %.0f advance %.0f publish %.0f gredsum %.0f | look-ahead hit/miss: leaf %u/%u doubling %u/%u transition %u/%u\n",
@@ -777,6 +782,37 @@ int b200nuts_constrain(B200Nuts* h, const float* z, int64_t n, float* out, void*
     CK(cudaGetLastError());
     h->launches += 1;
     return 0;
+}
+
+// ---- after the path: log-likelihoods and posterior-predictive draws over collected samples (predict.cuh) -------------
+static int rows_launch(B200Nuts* h, int mode, const float* z, const uint32_t* keys, int64_t n, float* out, cudaStream_t st) {
+    if (!h || !z || !out || n < 0 || (mode == 1 && !keys)) return B200NUTS_EINVAL;
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->fam.family == FAM_EIGHT_SCHOOLS) {
+        const long long tot = n * (h->D - 2);
+        if (mode == 0) k_eight_rows<0><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->fam, z, keys, n, out);
+        else k_eight_rows<1><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->fam, z, keys, n, out);
+    } else if (h->fam.family == FAM_GLM) {
+        if (mode == 1 && h->fam.likelihood == LIK_POISSON) { h->err = "predictive draws for the Poisson likelihood are not implemented"; return B200NUTS_EINVAL; }
+        const dim3 grid((unsigned)((h->fam.N + kPrRows - 1) / kPrRows), (unsigned)((n + kPrSamples - 1) / kPrSamples));
+        if (grid.y > 65535u) { h->err = "too many samples in one call (<= 524280)"; return B200NUTS_EINVAL; }
+        if (mode == 0) k_glm_rows<0><<<grid, kPrRows, 0, st>>>(h->fam, z, keys, n, out);
+        else k_glm_rows<1><<<grid, kPrRows, 0, st>>>(h->fam, z, keys, n, out);
+    } else { h->err = "log_likelihood / predictive: unsupported family"; return B200NUTS_EINVAL; }
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+int b200nuts_log_likelihood(B200Nuts* h, const float* z, int64_t n, float* out, void* stream) {
+    return rows_launch(h, 0, z, nullptr, n, out, (cudaStream_t)stream);
+}
+int b200nuts_predict(B200Nuts* h, const float* z, const uint32_t* keys, int64_t n, float* out, void* stream) {
+    return rows_launch(h, 1, z, keys, n, out, (cudaStream_t)stream);
+}
+int64_t b200nuts_obs_count(const B200Nuts* h) {
+    if (!h) return B200NUTS_EINVAL;
+    return h->fam.family == FAM_EIGHT_SCHOOLS ? (int64_t)(h->D - 2) : (h->fam.family == FAM_GLM ? (int64_t)h->fam.N : 0);
 }
 
 // ---- PRNG / det-math parity hooks: host in, host out -------------------------------------------

@@ -95,7 +95,8 @@ B2_HD constexpr int stream_ks_for(int D) { return D <= 8 ? 1 : D <= 16 ? 2 : D <
 struct StreamSync { unsigned int abort_flag, pad_[3]; unsigned long long passes; unsigned long long dbg[16];
                     unsigned long long tick_sum[kMaxStreamChains], tick_max[kMaxStreamChains], tick_lap[kMaxStreamChains][4];
                     unsigned int pre_hit[kMaxStreamChains][4], pre_miss[kMaxStreamChains][4];
-                    unsigned long long laps[32]; };     // -DB2_TICK_LAPS builds only: [i] cycles, [16 + i] occurrences   // per owner CTA: tick cycles, look-ahead hits
+                    unsigned long long laps[32];
+                    unsigned int peek_hit[kMaxStreamChains], peek_fallback[kMaxStreamChains], peek_mismatch[kMaxStreamChains]; };     // -DB2_TICK_LAPS builds only: [i] cycles, [16 + i] occurrences   // per owner CTA: tick cycles, look-ahead hits
 
 struct StreamParams {
     TickCfg cfg; FamilySpec fam; OutBufs out;
@@ -122,6 +123,7 @@ struct StreamParams {
     float nll_local_const;               // added to this rank's nll before the exchange (poisson: local sum lgamma(y+1))
     unsigned int* trace;                 // debug only (B200NUTS_TRACE): host-mapped [grid][8] progress words, see B2_TRACE
     int no_prefetch;                     // debug only: skip the PRNG look-ahead
+    int no_peek;                         // debug only: never publish the next position ahead of the tick (Tick::peek_next)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -298,32 +300,54 @@ B2_D void stream_publish_beta(const StreamParams& p, int chain, const float* zsr
     __syncwarp();
 }
 
-// The tick warp's work between two sweeps, for the chain owned by this CTA: finish the potential from the
-// reduced likelihood sums and advance the NUTS state machine.  Returns true when the chain needs no further gradient.
-__device__ __forceinline__ bool stream_tick_step(const StreamParams& p, Tick& tk, const float* gred, float* gz, float nll,
-                                                 int cta, unsigned long long* tdbg, unsigned int pass) {
+// The tick warp's work between two sweeps, for the chain owned by this CTA, in two parts.
+// stream_tick_critical: finish the potential from the reduced likelihood sums and -- when Tick::peek_next can tell where the
+// chain goes next without the full bookkeeping -- publish the next beta right away (returns true; `u` and gz keep what the
+// deferred part needs).  stream_tick_deferred: advance the NUTS state machine; with a single chain group the caller runs it
+// AFTER it has staged the next pass for its own consumers, i.e. while the grid already sweeps X again.
+__device__ __forceinline__ bool stream_tick_critical(const StreamParams& p, Tick& tk, const float* gred, float* gz, float* zpeek, float nll,
+                                                     int cta, unsigned long long* tdbg, uint32_t next_tag, float& u, unsigned int (&peek_stat)[3]) {
     const int lane = threadIdx.x & 31;
-    const bool dbg = (lane == 0);
-    long long t0 = dbg ? clock64() : 0ll;
-#define B2_TICK_LAP(k) do { warp_sync_hard(); if (dbg) { const long long t1 = clock64(); tdbg[k] += (unsigned long long)(t1 - t0); t0 = t1; } } while (0)
-    float u;
+    const long long t0 = (lane == 0) ? clock64() : 0ll;
     if (p.mode == 1) {
         const float* zin = p.z_in + (size_t)cta * p.cfg.D;
         glm_finish(p.fam, zin, nll, gred, u, gz);
         warp_sync_hard();
         if (lane == 0) p.u_out[cta] = u;
         for (int d = lane; d < p.cfg.D; d += 32) p.g_out[(size_t)cta * p.cfg.D + d] = gz[d];
-        return true;
+        return false;
     }
-    B2_TRACE_LANES(41);
     glm_finish(p.fam, tk.v(V_ZS), nll, gred, u, gz);
-    B2_TRACE_LANES(42);
-    B2_TICK_LAP(8);
+    warp_sync_hard();                    // gz is read across lanes below
+#if defined(__CUDA_ARCH__)
+    const bool early = !p.no_peek && tk.peek_next(u, gz, zpeek);
+#else
+    const bool early = false;            // (host compilation pass only: peek_next is device code)
+#endif
+    if (early) {
+        warp_sync_hard();                // the betas are gathered across lanes from zpeek
+        stream_publish_beta(p, cta, zpeek, true, next_tag);
+        peek_stat[0] += 1u;
+    } else if (tk.c.phase == PH_LEAF) peek_stat[1] += 1u;
+    warp_sync_hard();
+    if (lane == 0) tdbg[8] += (unsigned long long)(clock64() - t0);
+    return early;
+}
+
+// Returns true when the chain needs no further gradient.
+__device__ __forceinline__ bool stream_tick_deferred(const StreamParams& p, Tick& tk, const float* gz, const float* zpeek, float u, bool early,
+                                                     unsigned long long* tdbg, unsigned int (&peek_stat)[3]) {
+    const int lane = threadIdx.x & 31;
+    const long long t0 = (lane == 0) ? clock64() : 0ll;
     tk.advance(u, gz);
-    B2_TRACE_LANES(43);
     warp_sync_hard();                    // the next beta is gathered across lanes from V_ZS
-    B2_TICK_LAP(9);
-#undef B2_TICK_LAP
+    if (early) {                         // the position published ahead must be the one the state machine arrived at
+        const float* zs = tk.v(V_ZS);
+        bool same = tk.c.phase != PH_DONE;
+        for (int d = lane; d < p.cfg.D; d += 32) same = same && (__float_as_uint(zs[d]) == __float_as_uint(zpeek[d]));
+        if (!__all_sync(0xFFFFFFFFu, same)) peek_stat[2] += 1u;
+    }
+    if (lane == 0) tdbg[9] += (unsigned long long)(clock64() - t0);
     return tk.c.phase == PH_DONE;
 }
 
@@ -393,6 +417,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
     if (warp == kConsWarps) {
         const bool dbg = (cta == 0 && lane == 0);
         unsigned long long tk_sum = 0ull, tk_max = 0ull;
+        unsigned int peek_stat[3] = {0u, 0u, 0u};      // early publishes, fall-backs, mismatches (must stay 0)
+        bool deferred = false; float def_u = 0.0f;     // a tick whose next position is published but whose bookkeeping is pending
         unsigned long long* tlap = tdbg + 8;          // [0..1] finish / advance, [2] publish, [3] gred sum
         float loss0, dl0;
         link_fn<LIK>(0.0f, 0.0f, loss0, dl0);        // what every zero pad row adds to a chain's nll
@@ -591,11 +617,18 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                 const float nll = __shfl_sync(0xFFFFFFFFu, a64, 0) - (p.shard_count > 1 ? 0.0f : pad_nll);
                 if (lane == 0) tlap[3] += (unsigned long long)(clock64() - t_a);
                 B2_LAPQ(6);
-                float* gz = xred + kXSeg * kGStride; // scratch for the gradient wrt z (<= Dp floats)
-                if (!chain_done) chain_done = stream_tick_step(p, tk, gred, gz, nll, cta, tdbg, pass);
+                float* gz = xred + kXSeg * kGStride; // scratch for the gradient wrt z (<= 64 floats when the early publish applies)
+                float* zpeek = gz + 64;              // ... and for the position published ahead of the tick (<= 64 floats)
+                bool early = false;
+                if (!chain_done) {
+                    early = stream_tick_critical(p, tk, gred, gz, zpeek, nll, cta, tdbg, seq + 1u, def_u, peek_stat);
+                    if (p.mode == 1) chain_done = true;
+                    else if (early && !MG) deferred = true;       // single group: advance() runs after the next pass has been staged
+                    else chain_done = stream_tick_deferred(p, tk, gz, zpeek, def_u, early, tdbg, peek_stat);
+                }
                 B2_TRACE_LANES(5);
                 const long long t_p = clock64();
-                stream_publish_beta(p, cta, cv.v(V_ZS), !chain_done, (seq + 1u) | (chain_done ? 0x80000000u : 0u));
+                if (!early) stream_publish_beta(p, cta, cv.v(V_ZS), !chain_done, (seq + 1u) | (chain_done ? 0x80000000u : 0u));
                 B2_LAPQ(7);
                 if (lane == 0) {
                     const long long t_e = clock64();
@@ -606,11 +639,14 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                 }
                 pending = false;
             }
-            if (tick_first) {
-                staged = stage();
-                if (staged == 1) continue;
-                if (staged == 2) break;
+            if (tick_first) staged = stage();
+            if (deferred) {                          // the bookkeeping of the tick whose next position already went out (also
+                                                     // when the launch stops here: the chain must sit in front of that position)
+                chain_done = stream_tick_deferred(p, tk, xred + kXSeg * kGStride, xred + kXSeg * kGStride + 64, def_u, true, tdbg, peek_stat);
+                deferred = false;
             }
+            if (tick_first && staged == 2) break;
+            if (tick_first && staged == 1) continue;
             if (is_tick && grp == my_group) {
                 pending = true; my_round = need; pending_pass = qpass;
                 if (p.mode == 0 && !chain_done && !p.no_prefetch) tk.prefetch();     // off the critical path: PRNG look-ahead
@@ -624,6 +660,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         if (is_tick && lane == 0) {
             if (p.mode == 0) p.ctl[cta] = c;
             sy->tick_sum[cta] = tk_sum; sy->tick_max[cta] = tk_max;
+            sy->peek_hit[cta] = peek_stat[0]; sy->peek_fallback[cta] = peek_stat[1]; sy->peek_mismatch[cta] = peek_stat[2];
             for (int k = 0; k < 4; ++k) { sy->tick_lap[cta][k] = tlap[k]; sy->pre_hit[cta][k] = c.pre_hit[k]; sy->pre_miss[cta][k] = c.pre_miss[k]; }
         }
         __syncthreads();                             // pairs with the consumers' shutdown barrier: chain vectors are final

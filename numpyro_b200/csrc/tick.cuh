@@ -441,6 +441,151 @@ struct Tick {
     }
 #endif
 
+#if defined(__CUDA_ARCH__)
+    // "Where does this chain want its next gradient?" -- answered WITHOUT touching the chain state (streaming regime, D <= 64).
+    // After a gradient arrives, the only thing the rest of the grid waits for is the chain's next position; everything
+    // else a tick does (proposal bookkeeping, tree edges, root of the next tree, sample collection, ...) can run while the
+    // grid already sweeps X again.  peek_next() evaluates just the decisions that select the next position -- the same
+    // expressions, in the same order per element and per reduction, as on_leaf_fused / finish_doubling /
+    // finish_transition_common / begin_transition / begin_doubling -- and writes that position to `zout`.  The caller
+    // publishes it, then runs advance() as before, which recomputes the identical position into V_ZS (the streaming engine
+    // counts mismatches in debug builds of the tests; there must be none).  Returns false when the case is not covered
+    // (warm-up adaptation at a transition end, a PRNG look-ahead miss, the chain's last transition, HMC, D > 64): the
+    // caller then falls back to "advance first, publish afterwards".
+    __device__ __forceinline__ bool peek_next(float u, const float* g, float* zout) const {
+        const int Dn = cfg.D;
+        if (cfg.algo != 0 || c.phase != PH_LEAF || Dn > 64) return false;
+        const int lane = (int)(threadIdx.x & 31u);
+        const int d0 = lane, d1 = lane + 32;
+        const bool a0 = d0 < Dn, a1 = d1 < Dn;
+        const float e = c.going_right ? c.eps : -c.eps;
+        const float half = 0.5f * e;
+        const float* imm = v(V_IMM);
+        const float *zs = v(V_ZS), *rs = v(V_RS), *rsum_s = v(V_RSUMS);
+        float g0 = 0.0f, g1 = 0.0f, r0 = 0.0f, r1 = 0.0f, i0 = 0.0f, i1 = 0.0f, z0 = 0.0f, z1 = 0.0f, q0 = 0.0f, q1 = 0.0f;
+        if (a0) { g0 = g[d0]; r0 = rs[d0]; i0 = imm[d0]; z0 = zs[d0]; q0 = rsum_s[d0]; }
+        if (a1) { g1 = g[d1]; r1 = rs[d1]; i1 = imm[d1]; z1 = zs[d1]; q1 = rsum_s[d1]; }
+        r0 = r0 - half * g0; r1 = r1 - half * g1;
+        float pk = 0.0f;
+        if (a0) pk = pk + (i0 * r0) * r0;
+        if (a1) pk = pk + (i1 * r1) * r1;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) pk = pk + __shfl_xor_sync(0xFFFFFFFFu, pk, off);
+        const float energy_new = u + 0.5f * pk;
+        float delta = energy_new - c.energy0;
+        if (is_nan(delta)) delta = f_inf();
+        const float leaf_w = -delta;
+        const bool leaf_div = delta > 1000.0f;
+        const int leaf_idx = c.n_sub;
+        if (leaf_idx == 0) { q0 = r0; q1 = r1; } else { q0 = q0 + r0; q1 = q1 + r1; }
+        const uint32_t n = (uint32_t)leaf_idx;
+        const int idx_max = popc32(n >> 1);
+        const int idx_min = idx_max - popc32((~n & (n + 1u)) - 1u) + 1;
+        bool sub_turning = false;
+        for (int i = idx_max; i >= idx_min && !sub_turning; --i) {
+            const float* cr = v(V_CKPT_R + i); const float* cs = v(V_CKPT_RSUM + i);
+            float pl = 0.0f, pr = 0.0f;
+            if (a0) {
+                const float c_r = cr[d0], c_s = cs[d0];
+                const float sub = (q0 - c_s) + c_r;
+                const float sm = sub - (c_r + r0) / 2.0f;
+                pl = pl + (i0 * c_r) * sm; pr = pr + (i0 * r0) * sm;
+            }
+            if (a1) {
+                const float c_r = cr[d1], c_s = cs[d1];
+                const float sub = (q1 - c_s) + c_r;
+                const float sm = sub - (c_r + r1) / 2.0f;
+                pl = pl + (i1 * c_r) * sm; pr = pr + (i1 * r1) * sm;
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                pl = pl + __shfl_xor_sync(0xFFFFFFFFu, pl, off);
+                pr = pr + __shfl_xor_sync(0xFFFFFFFFu, pr, off);
+            }
+            sub_turning = (pl <= 0.0f) || (pr <= 0.0f);
+        }
+        if (leaf_idx + 1 < (1 << c.depth) && !sub_turning && !leaf_div) {          // ---- next leaf of this subtree
+            const float h0 = r0 - half * g0, h1 = r1 - half * g1;
+            if (a0) zout[d0] = z0 + e * (i0 * h0);
+            if (a1) zout[d1] = z1 + e * (i1 * h1);
+            return true;
+        }
+        // ---- the subtree is complete: tree-level U-turn test of finish_doubling
+        bool turning = sub_turning;
+        if (!sub_turning) {
+            const float* other = v(c.going_right ? V_RL : V_RR);
+            const float* rsum = v(V_RSUM);
+            float pl = 0.0f, pr = 0.0f;
+            if (a0) {
+                const float o0 = other[d0], t0 = rsum[d0] + q0;
+                const float rl_ = c.going_right ? o0 : r0, rr_ = c.going_right ? r0 : o0;
+                const float sm = t0 - (rl_ + rr_) / 2.0f;
+                pl = pl + (i0 * rl_) * sm; pr = pr + (i0 * rr_) * sm;
+            }
+            if (a1) {
+                const float o1 = other[d1], t1 = rsum[d1] + q1;
+                const float rl_ = c.going_right ? o1 : r1, rr_ = c.going_right ? r1 : o1;
+                const float sm = t1 - (rl_ + rr_) / 2.0f;
+                pl = pl + (i1 * rl_) * sm; pr = pr + (i1 * rr_) * sm;
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                pl = pl + __shfl_xor_sync(0xFFFFFFFFu, pl, off);
+                pr = pr + __shfl_xor_sync(0xFFFFFFFFu, pr, off);
+            }
+            turning = (pl <= 0.0f) || (pr <= 0.0f);
+        }
+        if (c.depth + 1 < c.max_depth && !turning && !leaf_div) {                   // ---- next doubling of this tree
+            if (!((c.pre_mask & 4u) && key_is(c.pd_from[0], mk(c.k_loop)))) return false;
+            const bool right = c.pd_right[0] != 0;
+            const float e2 = right ? c.eps : -c.eps;
+            const float half2 = 0.5f * e2;
+            float ez0 = z0, ez1 = z1, er0 = r0, er1 = r1, eg0 = g0, eg1 = g1;           // same direction: the leaf just built is the edge
+            if (right != (c.going_right != 0)) {
+                const float *ze = v(right ? V_ZR : V_ZL), *re = v(right ? V_RR : V_RL), *ge = v(right ? V_GR : V_GL);
+                if (a0) { ez0 = ze[d0]; er0 = re[d0]; eg0 = ge[d0]; }
+                if (a1) { ez1 = ze[d1]; er1 = re[d1]; eg1 = ge[d1]; }
+            }
+            const float h0 = er0 - half2 * eg0, h1 = er1 - half2 * eg1;
+            if (a0) zout[d0] = ez0 + e2 * (i0 * h0);
+            if (a1) zout[d1] = ez1 + e2 * (i1 * h1);
+            return true;
+        }
+        // ---- the transition ends: which proposal becomes the new state, then the first leapfrog of the next transition
+        if (c.i < cfg.num_warmup || c.i + 1 >= cfg.total_iters) return false;         // adaptation / the chain's last transition
+        if (!((c.pre_mask & 2u) && key_is(c.pf_from, mk(c.k_fin)))) return false;
+        if (!((c.pre_mask & 16u) && key_is(c.pt_from, mk(c.key_next)))) return false;
+        if (!((c.pre_mask & 8u) && key_is(c.pd_from[1], mk(c.pt_ktr)))) return false;
+        bool store_prop = true;
+        float sw = leaf_w;                                                           // sub_weight after this leaf
+        if (leaf_idx != 0) {
+            if (!((c.pre_mask & 1u) && key_is(c.pl_from, mk(c.k_sub)))) return false;
+            const float x_mix = leaf_w - c.sub_weight, d_mix = c.sub_weight - leaf_w;
+            const float e_mine = d_exp((lane & 1) ? -fabsf(d_mix) : -x_mix);          // two exponentials on two lanes
+            const float e_x = __shfl_sync(0xFFFFFFFFu, e_mine, 0), e_abs = __shfl_sync(0xFFFFFFFFu, e_mine, 1);
+            const float pp = 1.0f / (1.0f + e_x);
+            store_prop = c.pl_u < pp;
+            const float a_ = c.sub_weight, b_ = leaf_w;
+            sw = is_nan(d_mix) ? (a_ + b_) : (((a_ >= b_) ? a_ : b_) + d_log1p(e_abs));
+        }
+        float p2 = clip_max1(d_exp(sw - c.weight));
+        if (sub_turning || leaf_div) p2 = 0.0f;
+        const bool take = c.pf_u < p2;
+        float zn0 = z0, zn1 = z1, gn0 = g0, gn1 = g1;                                 // take && store_prop: this leaf
+        if (!(take && store_prop)) {
+            const float *zq = v(take ? V_ZPS : V_ZP), *gq = v(take ? V_GPS : V_GP);
+            if (a0) { zn0 = zq[d0]; gn0 = gq[d0]; }
+            if (a1) { zn1 = zq[d1]; gn1 = gq[d1]; }
+        }
+        const float *sm = v(V_SQRTM), *en = v(V_EPS);
+        const float e3 = c.pd_right[1] ? c.step_size : -c.step_size;
+        const float half3 = 0.5f * e3;
+        if (a0) { const float rr = sm[d0] * en[d0]; const float h = rr - half3 * gn0; zout[d0] = zn0 + e3 * (i0 * h); }
+        if (a1) { const float rr = sm[d1] * en[d1]; const float h = rr - half3 * gn1; zout[d1] = zn1 + e3 * (i1 * h); }
+        return true;
+    }
+#endif
+
     // one iteration of _iterative_build_subtree's loop body, after the gradient arrived
     B2_HD void on_leaf(float u, const float* g) {
 #if defined(__CUDA_ARCH__)
@@ -636,8 +781,11 @@ struct Tick {
         c.mean_accept_prob = c.mean_accept_prob + (accept_prob - c.mean_accept_prob) / (float)n;   // :511-513
         c.i = itr; st(c.key, mk(c.key_next));
         c.heur_t = t;
+        B2_LAPQ(8);
         if (in_warmup && adapt_update(t, accept_prob)) return;     // heuristic pending: heur_done() collects
+        B2_LAPQ(9);
         collect(t);
+        B2_LAPQ(10);
         begin_transition();
     }
 

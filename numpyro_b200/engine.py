@@ -243,6 +243,25 @@ class Engine:
         self._check(self.lib.b200nuts_constrain(self.h, _ptr(z), z.shape[0], _ptr(out), self._stream()), "b200nuts_constrain")
         return out
 
+    @_on_device
+    def log_likelihood(self, z) -> torch.Tensor:
+        """[n, D] unconstrained samples -> [n, n_obs] log_prob of the observed site per observation (b200nuts_log_likelihood)."""
+        z = torch.as_tensor(z, dtype=torch.float32).to(self.device).contiguous().view(-1, self.D)
+        out = torch.empty((z.shape[0], int(self.lib.b200nuts_obs_count(self.h))), dtype=torch.float32, device=self.device)
+        self._check(self.lib.b200nuts_log_likelihood(self.h, _ptr(z), z.shape[0], _ptr(out), self._stream()), "b200nuts_log_likelihood")
+        return out
+
+    @_on_device
+    def predict(self, z, keys) -> torch.Tensor:
+        """[n, D] unconstrained samples + [n, 2] uint32 keys of the observed site -> [n, n_obs] draws (b200nuts_predict)."""
+        z = torch.as_tensor(z, dtype=torch.float32).to(self.device).contiguous().view(-1, self.D)
+        k = torch.from_numpy(np.ascontiguousarray(keys, np.uint32).reshape(-1, 2).view(np.int32)).to(self.device)
+        if k.shape[0] != z.shape[0]:
+            raise ValueError("one key per sample")
+        out = torch.empty((z.shape[0], int(self.lib.b200nuts_obs_count(self.h))), dtype=torch.float32, device=self.device)
+        self._check(self.lib.b200nuts_predict(self.h, _ptr(z), _ptr(k), z.shape[0], _ptr(out), self._stream()), "b200nuts_predict")
+        return out
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.b200nuts_launch_count(self.h))

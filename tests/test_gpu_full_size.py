@@ -53,6 +53,7 @@ def test_whole_run_bit_exact_at_full_size(data):
         assert_run_equal(out, res, c)
         total += int(np.sum(res["num_steps"]))
     assert total >= 8 * 12
+    assert int(e.debug_clocks()[13]) == 0        # positions published ahead of the tick (Tick::peek_next) == the state machine's
     e.close(); hook.close()
 
 
@@ -72,6 +73,8 @@ def test_posterior_against_independent_laplace_reference(data):
     out = e.run(900, 400, fields=("z", "diverging"))
     z = out["z"].cpu().numpy().astype(np.float64)                   # [8, 500, 54]
     assert int(out["diverging"].sum().item()) == 0
+    dbg = e.debug_clocks()
+    assert int(dbg[11]) > 10 * int(dbg[12]) and int(dbg[13]) == 0   # early publishes dominate post warm-up, and never disagree
     ess = diag.effective_sample_size(z)
     sd = z.std(axis=(0, 1))
     mcse = sd / np.sqrt(ess)

@@ -194,8 +194,8 @@ def test_config3_full_shape_gemm(lik):
                    max_tree_depth_warmup=5, max_tree_depth=5, step_size=0.02, adapt_step_size=0)
     d.init(keys, 2)
     outd = d.run(5, 2, fields=FIELDS)
-    assert outd["num_steps"].float().mean().item() > 8
-    for c in (1, 9000):
+    assert outd["num_steps"].float().mean().item() > 4 and int(outd["num_steps"].max().item()) == 31
+    for c in (1, int(outd["num_steps"].sum(dim=1).argmax().item())):
         kern = chain.Kernel(device_potential(d, c), max_tree_depth=(5, 5), step_size=0.02, adapt_step_size=False)
         res, _ = chain.run_chain(kern, fam, keys[c], 2, 3, fields=FIELDS)
         assert_run_equal(outd, res, c)
