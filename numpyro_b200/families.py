@@ -63,8 +63,11 @@ def _f32(a):
 
 
 class Model:
-    """Base class of declared families; ``bind`` receives the model's call arguments."""
+    """Base class of declared families; ``bind`` receives the model's call arguments.  ``obs_name`` is the observed site
+    (what ``log_likelihood`` / ``Predictive`` return); ``bind(..., _predict=True)`` accepts ``y=None`` (the reference's
+    convention for predictive calls, infer/util.py:985-998) and binds a placeholder response."""
     name = "model"
+    obs_name = "obs"
 
     def bind(self, *args, **kwargs) -> BoundModel:
         raise NotImplementedError
@@ -101,9 +104,11 @@ class EightSchoolsNonCentered(Model):
     def __init__(self, mu_scale: float = 5.0, tau_scale: float = 5.0):
         self.mu_scale, self.tau_scale = float(mu_scale), float(tau_scale)
 
-    def bind(self, J, sigma, y=None) -> BoundModel:
+    def bind(self, J, sigma, y=None, _predict=False) -> BoundModel:
         if y is None:
-            raise ValueError("the engine samples posteriors: `y` must be observed")
+            if not _predict:
+                raise ValueError("the engine samples posteriors: `y` must be observed")
+            y = np.zeros(int(J), np.float32)
         sigma, y = _f32(sigma).ravel(), _f32(y).ravel()
         if sigma.shape[0] != J or y.shape[0] != J:
             raise ValueError("sigma and y must have length J")
@@ -123,7 +128,11 @@ class _GLM(Model):
     def _sites(self, D) -> Tuple[List[Site], List[Site]]:
         return [Site(self.coef_name, (D,))], []
 
-    def bind(self, X, y) -> BoundModel:
+    def bind(self, X, y=None, _predict=False) -> BoundModel:
+        if y is None:
+            if not _predict:
+                raise ValueError("the engine samples posteriors: `y` must be observed")
+            y = np.zeros(np.shape(X)[0], np.float32)
         X, y = _f32(X), _f32(y).ravel()
         if X.ndim != 2 or y.shape[0] != X.shape[0]:
             raise ValueError("X must be [N, D] and y [N]")
@@ -146,6 +155,7 @@ class HorseshoeRegression(_GLM):
     """examples/horseshoe_regression.py:37-78 (``model_normal_likelihood`` / ``model_bernoulli_likelihood``)."""
     name = "horseshoe_regression"
     coef_name = "unscaled_betas"
+    obs_name = "Y"
 
     def __init__(self, likelihood: str = "normal"):
         if likelihood not in ("normal", "bernoulli"):

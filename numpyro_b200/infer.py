@@ -227,6 +227,13 @@ class HMC(_KernelBase):
             z[0, s.z_offset:s.z_offset + s.size] = v
         return np.repeat(z, n_chains, axis=0)
 
+    def __getstate__(self):
+        """hmc.py:818-822: the compiled closures (here: the engine handle and its device state) are not pickled."""
+        state = self.__dict__.copy()
+        state["_engine"] = None
+        state["_engine_state"] = None
+        return state
+
     # ------------------------------------------------------------------ MCMCKernel (mcmc.py:79-124)
     def init(self, rng_key, num_warmup, init_params=None, model_args=(), model_kwargs=None):
         """``MCMCKernel.init`` (mcmc.py:90-108; hmc.py:740-799): bind the model, find valid initial parameters and
@@ -535,6 +542,14 @@ class MCMC:
             dist.all_gather(parts, t)                 # the only communication of the chain-sharded mode
             out[k] = torch.cat(parts, dim=0).cpu().numpy()
         return out
+
+    def __getstate__(self):
+        """mcmc.py:806-809 (test_pickle.py:88-95): samples, states and settings travel; engine handles and device buffers
+        are rebuilt by the next ``run``."""
+        state = self.__dict__.copy()
+        state["_shards"] = []
+        state["_args"], state["_kwargs"] = (), {}
+        return state
 
     # ------------------------------------------------------------------ results
     @property

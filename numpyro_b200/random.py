@@ -21,6 +21,11 @@ def split(key, num: int = 2) -> np.ndarray:
     return _engine.prng_split(np.asarray(key, np.uint32).reshape(1, 2), int(num))[0]
 
 
+def split_each(keys, num: int = 2) -> np.ndarray:
+    """``vmap(lambda k: jax.random.split(k, num))(keys)``: ``[n, 2]`` keys -> ``[n, num, 2]``, one device call."""
+    return _engine.prng_split(np.asarray(keys, np.uint32).reshape(-1, 2), int(num))
+
+
 def is_prng_key(k) -> bool:
     """numpyro.util.is_prng_key (util.py:176-182) for raw uint32[2] key data."""
     k = np.asarray(k)
