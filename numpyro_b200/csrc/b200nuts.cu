@@ -461,8 +461,13 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
         g_create_err = "gemm regime needs a GLM family with <= 1024 columns"; delete h; return B200NUTS_EINVAL;
     }
     if (cfg->shard_count > 1) {
-        if (!stream_ok) { g_create_err = "row-sharded handles need the streaming regime (GLM, <= 64 columns, one SM per chain)"; delete h; return B200NUTS_EINVAL; }
-        regime = B200NUTS_REGIME_STREAM;
+        // rows split over ranks: the streaming regime when it applies (a handful of chains, <= 64 columns), else the GEMM regime
+        if (cfg->regime == B200NUTS_REGIME_GEMM || !stream_ok || (cfg->regime == B200NUTS_REGIME_AUTO && gemm_ok && h->C > 32)) {
+            if (!gemm_ok || cfg->regime == B200NUTS_REGIME_STREAM || cfg->regime == B200NUTS_REGIME_WARP) {
+                g_create_err = "row-sharded handles need the streaming regime (GLM, <= 64 columns, one SM per chain) or the gemm regime (GLM, <= 1024 columns)"; delete h; return B200NUTS_EINVAL;
+            }
+            regime = B200NUTS_REGIME_GEMM;
+        } else regime = B200NUTS_REGIME_STREAM;
         h->shard_rank = cfg->shard_rank; h->shard_count = cfg->shard_count;
         h->n_rows_global = cfg->n_rows_global > 0 ? cfg->n_rows_global : cfg->n_rows;
     }
@@ -534,6 +539,12 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
     if (regime == B200NUTS_REGIME_GEMM) {
         const std::string ge = gemm_create(&h->gemm, h->fam, h->C, h->Dp, h->num_sms, h->ctl, h->vecs, &h->launches);
         if (!ge.empty()) { g_create_err = ge; b200nuts_destroy(h); return B200NUTS_ECUDA; }
+        if (h->shard_count > 1) {
+            const size_t mb = gemm_mail_bytes(h->gemm);
+            if ((ce = cudaMalloc(&h->mail, mb)) != cudaSuccess) return fail("cudaMalloc mailbox", ce);
+            cudaMemset(h->mail, 0, mb);
+            h->nll_local_const = h->fam.nll_const;
+        }
     }
     {   // Load every kernel this handle can launch NOW.  With lazy module loading the first launch of a function may need
         // a context-wide synchronisation; a persistent kernel of another (row-sharded) handle that is waiting for this
@@ -595,6 +606,7 @@ static int run_locked(B200Nuts* h, const B200NutsRun* run, cudaStream_t st) {
         CK(cudaGetLastError());
         h->launches += 1;
     } else if (h->regime == B200NUTS_REGIME_GEMM) {
+        if (h->shard_count > 1 && !h->shards_connected) { h->err = "row-sharded handle: call b200nuts_shard_connect first"; return B200NUTS_ESTATE; }
         const std::string e = gemm_run(h->gemm, h->tick, out, run->max_passes, st);
         if (!e.empty()) { h->err = e; return B200NUTS_ECUDA; }
         h->launches += 2;
@@ -731,6 +743,12 @@ int b200nuts_shard_connect(B200Nuts* h, const void* blobs) {
             h->mail_peer[q] = (float2*)ptr; h->mail_ipc[q] = true;
         }
     }
+    if (h->regime == B200NUTS_REGIME_GEMM) {
+        void* mail[kMaxShards];
+        for (int q = 0; q < h->shard_count; ++q) mail[q] = h->mail_peer[q];
+        const std::string e = gemm_set_shards(h->gemm, h->shard_rank, h->shard_count, mail, h->n_rows_global, h->nll_local_const);
+        if (!e.empty()) { h->err = e; return B200NUTS_ECUDA; }
+    }
     h->shards_connected = true;
     return 0;
 }
@@ -747,6 +765,7 @@ int b200nuts_potential_and_grad(B200Nuts* h, const float* z, float* U, float* g,
         return 0;
     }
     if (h->regime == B200NUTS_REGIME_GEMM) {
+        if (h->shard_count > 1 && !h->shards_connected) { h->err = "row-sharded handle: call b200nuts_shard_connect first"; return B200NUTS_ESTATE; }
         const std::string e = gemm_potential(h->gemm, z, U, g, st, &h->launches);
         if (!e.empty()) { h->err = e; return B200NUTS_ECUDA; }
         h->pending = true; h->pending_stream = st;

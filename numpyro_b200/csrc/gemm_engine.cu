@@ -22,6 +22,8 @@ struct GemmRegime {
     cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; cudaGraphConditionalHandle cond = 0;
     unsigned long long passes_seen = 0ull;
     size_t smem = 0;
+    GemmShardDev shard;                        // count == 1: not row-sharded
+    unsigned int epoch = 0;                    // launches of a row-sharded handle so far (every rank makes the same sequence)
 };
 
 #define GCK(call)                                                                              \
@@ -45,7 +47,7 @@ static std::string launch_pass(GemmRegime* g, cudaStream_t st) {
 static std::string launch_tick(GemmRegime* g, int first, cudaStream_t st) {
     const int blocks = (g->C + 3) / 4;
     k_gemm_tick<<<blocks, 128, 0, st>>>(g->gp, g->ctx, g->sched, g->fam, g->ctl, g->vecs, g->gtmp, g->gbeta, g->bimg, g->tile_count,
-                                        g->C, g->Dp, first);
+                                        g->C, g->Dp, first, g->shard);
     GCK(cudaGetLastError());
     k_gemm_sched<<<1, 32, 0, st>>>(g->ctx, g->sched, g->tile_count, g->active_tiles, g->CT, first, g->cond, 0);
     GCK(cudaGetLastError());
@@ -71,7 +73,7 @@ static std::string build_graph(GemmRegime* g) {
     }
     {
         int first = 0;
-        void* args[] = {&g->gp, &g->ctx, &g->sched, &g->fam, &g->ctl, &g->vecs, &g->gtmp, &g->gbeta, &g->bimg, &g->tile_count, &g->C, &g->Dp, &first};
+        void* args[] = {&g->gp, &g->ctx, &g->sched, &g->fam, &g->ctl, &g->vecs, &g->gtmp, &g->gbeta, &g->bimg, &g->tile_count, &g->C, &g->Dp, &first, &g->shard};
         cudaKernelNodeParams kp; memset(&kp, 0, sizeof(kp));
         kp.func = (void*)k_gemm_tick; kp.gridDim = dim3((g->C + 3) / 4); kp.blockDim = dim3(128); kp.kernelParams = args;
         GCK(cudaGraphAddKernelNode(&n_tick, body, &n_pass, 1, &kp));
@@ -98,7 +100,10 @@ std::string gemm_create(GemmRegime** out, const FamilySpec& fam, int C, int Dp, 
     const long long RC = (fam.N + kGtRows - 1) / kGtRows;
     const int KB = (fam.Dx + 31) / 32, Dxp = KB * 32, NDB = (Dxp + kGtNB - 1) / kGtNB;
     if (RC > 0x7FFFFFFFll / 8) { delete g; return "gemm regime: too many rows for one handle"; }
+    // units (chain tile x segment) per CTA: ~16 when there are many chain tiles; with a handful of tiles fewer, longer units keep
+    // the number of partial sums a tick has to add per chain small (config 5: one tile, 2 units per CTA)
     long long S = (16ll * num_sms + CT - 1) / CT;
+    if (S > 2ll * num_sms) S = 2ll * num_sms;
     if (const char* e = getenv("B200NUTS_GEMM_SEGMENTS")) S = atoll(e);
     if (S < 1) S = 1;
     if (S > RC) S = RC;
@@ -150,7 +155,9 @@ std::string gemm_create(GemmRegime** out, const FamilySpec& fam, int C, int Dp, 
         for (const void* f : fns)
             if ((ce = cudaFuncGetAttributes(&fa, f)) != cudaSuccess) return fail(std::string("cudaFuncGetAttributes: ") + cudaGetErrorString(ce));
     }
-    if (g->use_graph) {
+    memset(&g->shard, 0, sizeof(g->shard));
+    g->shard.count = 1;
+    if (g->use_graph) {                        // (gemm_set_shards rebuilds it: the graph bakes the kernel arguments)
         std::string e = build_graph(g);
         if (!e.empty()) return fail("gemm regime: " + e);
     }
@@ -173,9 +180,27 @@ void gemm_describe(const GemmRegime* g, int* info8) {
     info8[6] = g->gp.Dxp; info8[7] = g->use_graph ? 1 : 0;
 }
 
+size_t gemm_mail_bytes(const GemmRegime* g) { return gemm_mail_words(g->C, g->gp.Dxp) * sizeof(float2); }
+
+std::string gemm_set_shards(GemmRegime* g, int rank, int count, void* const* mail, long long n_rows_global, float nll_local_const) {
+    if (count < 1 || count > kGemmMaxShards || rank < 0 || rank >= count) return "gemm regime: shard rank / count out of range";
+    if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
+    if (g->graph) { cudaGraphDestroy(g->graph); g->graph = nullptr; }
+    memset(&g->shard, 0, sizeof(g->shard));
+    g->shard.rank = rank; g->shard.count = count; g->shard.stride = g->gp.Dxp + 32; g->shard.nll_local_const = nll_local_const;
+    for (int q = 0; q < count; ++q) g->shard.mail[q] = (float2*)mail[q];
+    if (count > 1) { g->fam.N = n_rows_global; g->fam.nll_const = 0.0f; }     // priors / Normal-likelihood constants see the whole dataset
+    if (g->use_graph) {
+        std::string e = build_graph(g);
+        if (!e.empty()) return "gemm regime: " + e;
+    }
+    GCK(cudaDeviceSynchronize());
+    return "";
+}
+
 std::string gemm_run(GemmRegime* g, const TickCfg& cfg, const OutBufs& out, int max_passes, cudaStream_t st) {
     GemmCtx h; memset(&h, 0, sizeof(h));
-    h.cfg = cfg; h.out = out; h.max_passes = max_passes;
+    h.cfg = cfg; h.out = out; h.max_passes = max_passes; h.epoch = ++g->epoch;
     GCK(cudaMemcpyAsync(g->ctx, &h, sizeof(h), cudaMemcpyHostToDevice, st));        // (pageable source: staged before the call returns)
     GCK(cudaMemsetAsync(g->tile_count, 0, (size_t)2 * g->CT * 4, st));
     std::string e = launch_tick(g, 1, st);                                            // betas of the chains that wait for a gradient
@@ -199,7 +224,7 @@ std::string gemm_potential(GemmRegime* g, const float* z, float* U, float* grad,
     GCK(cudaGetLastError());
     std::string e = launch_pass(g, st);
     if (!e.empty()) return e;
-    k_gemm_hook_finish<<<blocks, 128, 0, st>>>(g->gp, g->fam, z, U, grad, g->gbeta, g->C);
+    k_gemm_hook_finish<<<blocks, 128, 0, st>>>(g->gp, g->fam, z, U, grad, g->gbeta, g->C, g->shard, ++g->epoch);
     GCK(cudaGetLastError());
     *launches += 3;
     return "";
@@ -217,7 +242,8 @@ std::string gemm_sync(GemmRegime* g, cudaStream_t st, GemmStatus* status, long l
     }
     if (s.abort_flag) {
         char buf[160];
-        snprintf(buf, sizeof(buf), "gemm regime aborted: wait %u inside gemm_pass_kernel timed out (11-12 producer, 13-17 MMA issuer, 18-20 epilogue)", s.abort_flag);
+        if (s.abort_flag == 4u) snprintf(buf, sizeof(buf), "gemm regime aborted: a peer rank's likelihood sums never arrived (row-sharded exchange timed out)");
+        else snprintf(buf, sizeof(buf), "gemm regime aborted: wait %u inside gemm_pass_kernel timed out (11-12 producer, 13-17 MMA issuer, 18-20 epilogue)", s.abort_flag);
         cudaMemsetAsync(&g->sched->abort_flag, 0, 4, st);
         return buf;
     }

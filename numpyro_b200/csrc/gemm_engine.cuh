@@ -362,7 +362,20 @@ static __global__ void k_gemm_pack_y(const float* __restrict__ y, long long N, l
 struct GemmCtx {                               // device memory, rewritten by b200nuts_run before every launch
     TickCfg cfg; OutBufs out;
     int max_passes;                            // 0 = run until every chain has finished
+    unsigned int epoch;                        // launch number of a row-sharded handle (part of the exchange tags)
 };
+// Row sharding (BASELINE config 5): every rank runs the GEMM pass over its own rows with all chains replicated; the
+// per-chain likelihood sums [Dx gradient columns + loss] are all-reduced inside the tick kernel: each rank stores its sums as
+// {value, tag} 8-byte words into EVERY rank's mailbox (peer memory over NVLink) and adds the `count` contributions in rank
+// order, so all ranks hold bit-identical (U, grad) and their replicated chains stay in lock-step.
+constexpr int kGemmMaxShards = 16;
+struct GemmShardDev {
+    int rank, count;
+    int stride;                                // float2 words per (parity, source rank, chain): Dxp + 32 (loss at index Dxp)
+    float nll_local_const;                     // this rank's share of the likelihood constant (poisson: sum lgamma(y+1) over its rows)
+    float2* mail[kGemmMaxShards];              // [2 parities][kGemmMaxShards source ranks][C][stride] of every rank
+};
+B2_HD size_t gemm_mail_words(int C, int Dxp) { return (size_t)2 * kGemmMaxShards * C * (Dxp + 32); }
 struct GemmSched {                             // device memory
     int n_active; int pass; int pass_in_run; unsigned int abort_flag;
     unsigned long long passes_total; unsigned long long dbg[8];
@@ -399,11 +412,53 @@ B2_D float gemm_gather(const GemmParams& gp, int chain, float* gbeta, int Dx) {
     return nll;
 }
 
+B2_D void g_st_sys_v2(float2* p, float2 v) { asm volatile("st.volatile.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory"); }
+B2_D float2 g_ld_volatile_v2(const float2* p) { float2 v; asm volatile("ld.volatile.global.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory"); return v; }
+B2_HD uint32_t gemm_xtag(uint32_t epoch, uint32_t seq) { const uint32_t t = epoch * 0x9E3779B1u + seq; return t ? t : 1u; }
+
+// All-reduce of one chain's likelihood sums over the row shards (one warp; see GemmShardDev).  gbeta[0..Dx) and the returned
+// loss are replaced by the sums over all ranks, added in rank order.  Every wait is bounded (abort code 4).
+B2_D float gemm_shard_allreduce(const GemmShardDev& sh, int C, int chain, float* gbeta, float nll, int Dx, int Dxp, uint32_t tag, int parity,
+                                unsigned int* abort_flag, long long spin_limit) {
+    const int lane = threadIdx.x & 31;
+    const size_t per_rank = (size_t)C * sh.stride;
+    const size_t base = ((size_t)parity * kGemmMaxShards) * per_rank + (size_t)chain * sh.stride;
+    const float tagf = __uint_as_float(tag);
+    for (int d = lane; d <= Dxp; d += 32) {
+        if (d >= Dx && d != Dxp) continue;
+        const float mine = (d == Dxp) ? (nll + sh.nll_local_const) : gbeta[d];
+        for (int q = 0; q < sh.count; ++q) g_st_sys_v2(sh.mail[q] + base + (size_t)sh.rank * per_rank + d, make_float2(mine, tagf));
+    }
+    const long long t0 = clock64();
+    float nll_tot = 0.0f;
+    for (int d = lane; d <= Dxp; d += 32) {
+        if (d >= Dx && d != Dxp) continue;
+        const float2* box = sh.mail[sh.rank] + base + d;
+        float tot = 0.0f;
+        for (int sr = 0; sr < sh.count; ++sr) {
+            float2 v;
+            unsigned int it = 0;
+            while (true) {
+                v = g_ld_volatile_v2(box + (size_t)sr * per_rank);
+                if (__float_as_uint(v.y) == tag) break;
+                if ((++it & 63u) == 0u) {
+                    if (*(volatile unsigned int*)abort_flag) break;
+                    if (clock64() - t0 > spin_limit) { atomicCAS(abort_flag, 0u, 4u); break; }
+                }
+            }
+            tot += v.x;
+        }
+        if (d == Dxp) nll_tot = tot; else gbeta[d] = tot;
+    }
+    // the loss lives in the lane that owns index Dxp
+    return __shfl_sync(0xFFFFFFFFu, nll_tot, Dxp & 31);
+}
+
 // Tick of every chain after a pass (one warp per chain): likelihood sums -> potential -> NUTS state machine -> next betas.
 // first != 0: start of a run -- no gradient yet, only publish the betas of the chains that wait for one.
 static __global__ void __launch_bounds__(128) k_gemm_tick(GemmParams gp, const GemmCtx* ctx, GemmSched* sched, FamilySpec fam, ChainCtl* ctl,
                                                            float* vecs, float* gtmp, float* gbeta, float* bimg, int* tile_count,
-                                                           int C, int Dp, int first) {
+                                                           int C, int Dp, int first, GemmShardDev sh) {
     __shared__ TickCfg s_cfg; __shared__ OutBufs s_out;
     {
         const int* src = (const int*)&ctx->cfg; int* dst = (int*)&s_cfg;
@@ -420,8 +475,13 @@ static __global__ void __launch_bounds__(128) k_gemm_tick(GemmParams gp, const G
     if (!first) {
         Tick t{s_cfg, c, cv, s_out, chain, C};
         float* gb = gbeta + (size_t)chain * gp.Dxp; float* g = gtmp + (size_t)chain * Dp;
-        const float nll = gemm_gather(gp, chain, gb, fam.Dx);
+        float nll = gemm_gather(gp, chain, gb, fam.Dx);
         __syncwarp(); lane_sync();
+        if (sh.count > 1) {
+            nll = gemm_shard_allreduce(sh, C, chain, gb, nll, fam.Dx, gp.Dxp, gemm_xtag(ctx->epoch, (uint32_t)sched->pass_in_run + 1u),
+                                       sched->pass_in_run & 1, gp.abort_flag, 8 * gp.spin_limit);
+            __syncwarp(); lane_sync();
+        }
         float u;
         glm_finish(fam, cv.v(V_ZS), nll, gb, u, g);
         __syncwarp(); lane_sync();
@@ -463,12 +523,16 @@ static __global__ void __launch_bounds__(128) k_gemm_hook_begin(FamilySpec fam, 
     gemm_write_betas(fam, z_in + (size_t)chain * fam.D, bimg, KB, chain);
 }
 static __global__ void __launch_bounds__(128) k_gemm_hook_finish(GemmParams gp, FamilySpec fam, const float* z_in, float* U, float* g_out,
-                                                                  float* gbeta, int C) {
+                                                                  float* gbeta, int C, GemmShardDev sh, unsigned int epoch) {
     const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (chain >= C) return;
     float* gb = gbeta + (size_t)chain * gp.Dxp;
-    const float nll = gemm_gather(gp, chain, gb, fam.Dx);
+    float nll = gemm_gather(gp, chain, gb, fam.Dx);
     __syncwarp(); lane_sync();
+    if (sh.count > 1) {
+        nll = gemm_shard_allreduce(sh, C, chain, gb, nll, fam.Dx, gp.Dxp, gemm_xtag(epoch, 0x7FFFFFu), 0, gp.abort_flag, 8 * gp.spin_limit);
+        __syncwarp(); lane_sync();
+    }
     float u;
     glm_finish(fam, z_in + (size_t)chain * fam.D, nll, gb, u, g_out + (size_t)chain * fam.D);
     if ((threadIdx.x & 31) == 0) U[chain] = u;

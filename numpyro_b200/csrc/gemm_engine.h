@@ -24,6 +24,10 @@ void gemm_destroy(GemmRegime* g);
 std::string gemm_run(GemmRegime* g, const TickCfg& cfg, const OutBufs& out, int max_passes, cudaStream_t st);
 std::string gemm_potential(GemmRegime* g, const float* z, float* U, float* grad, cudaStream_t st, long long* launches);
 std::string gemm_sync(GemmRegime* g, cudaStream_t st, GemmStatus* status, long long* launches);
+// Row sharding (config 5): bytes of this handle's mailbox (allocated by the caller, exported to the peers), and the wiring:
+// mail[q] = rank q's mailbox as seen from this device, q < count.
+size_t gemm_mail_bytes(const GemmRegime* g);
+std::string gemm_set_shards(GemmRegime* g, int rank, int count, void* const* mail, long long n_rows_global, float nll_local_const);
 void gemm_describe(const GemmRegime* g, int* info8);    // CT, RC, KB, S, cps, NDB, Dxp, graph mode
 
 }  // namespace b2

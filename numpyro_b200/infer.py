@@ -393,7 +393,7 @@ class MCMC:
             cfg.update(bound.cfg)
             cfg["num_chains"] = s.hi - s.lo
             if G > 1:
-                cfg.update(shard_rank=k, shard_count=G, n_rows_global=N, regime=_capi.REGIME_STREAM)
+                cfg.update(shard_rank=k, shard_count=G, n_rows_global=N)      # (the engine picks the streaming or the GEMM regime)
                 s.engine = Engine(device=s.device, X=bound.X[cuts[k]:cuts[k + 1]], y=bound.y[cuts[k]:cuts[k + 1]], aux=bound.aux, **cfg)
                 s.stream = torch.cuda.Stream(device=s.device)     # the ranks' persistent kernels must run concurrently
             else:

@@ -17,19 +17,21 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 os.environ.setdefault("B200NUTS_WATCHDOG_S", "120")
-N, D, C = 200003, 54, 8
+GEMM = len(sys.argv) > 1 and sys.argv[1] == "gemm"          # config-5 shape of the chain state: 64 chains x 128 columns
+N, D, C = (100003, 128, 64) if GEMM else (200003, 54, 8)
 rng = np.random.default_rng(5)
 X = rng.normal(size=(N, D)).astype(F)
 y = (rng.uniform(size=N) < 1 / (1 + np.exp(-X @ (rng.normal(size=D) * 0.3)))).astype(F)
 cuts = [N * r // world for r in range(world + 1)]
 e = eng.Engine(device=f"cuda:{local}", family=_capi.FAMILY_GLM, num_chains=C, X=X[cuts[rank]:cuts[rank + 1]],
-               y=y[cuts[rank]:cuts[rank + 1]], regime=_capi.REGIME_STREAM, shard_rank=rank, shard_count=world,
+               y=y[cuts[rank]:cuts[rank + 1]], regime=_capi.REGIME_GEMM if GEMM else _capi.REGIME_STREAM, shard_rank=rank, shard_count=world,
                n_rows_global=N, max_tree_depth=6, max_tree_depth_warmup=6)
 e.connect_shards()
 z = (rng.normal(size=(C, D)) * 0.2).astype(F)
 U, g = e.potential_and_grad(z)
-e.init(prng.split(prng.key(3), C), 30)
-out = e.run(50, 30, fields=("z", "num_steps"))
+W0, S0 = (10, 6) if GEMM else (30, 20)
+e.init(prng.split(prng.key(3), C), W0)
+out = e.run(W0 + S0, W0, fields=("z", "num_steps"))
 torch.cuda.synchronize()
 mine = torch.cat([U.flatten(), g.flatten(), out["z"].flatten(), out["num_steps"].flatten().float()])
 allr = [torch.empty_like(mine) for _ in range(world)]

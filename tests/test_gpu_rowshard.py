@@ -40,14 +40,14 @@ def _data(N, D, seed, lik="bernoulli"):
 class Ranks:
     """W row-sharded handles driven by W threads of this process."""
 
-    def __init__(self, X, y, C, cuts, devices, **cfg):
+    def __init__(self, X, y, C, cuts, devices, regime=_capi.REGIME_STREAM, **cfg):
         self.W = len(cuts) - 1
         self.streams, self.engines = [], []
         for r in range(self.W):
             dev = torch.device("cuda", devices[r])
             torch.cuda.set_device(dev)
             e = eng.Engine(device=dev, family=_capi.FAMILY_GLM, num_chains=C, X=X[cuts[r]:cuts[r + 1]], y=y[cuts[r]:cuts[r + 1]],
-                           regime=_capi.REGIME_STREAM, shard_rank=r, shard_count=self.W, n_rows_global=X.shape[0], **cfg)
+                           regime=regime, shard_rank=r, shard_count=self.W, n_rows_global=X.shape[0], **cfg)
             self.engines.append(e)
             self.streams.append(torch.cuda.Stream(device=dev))
         blobs = [e.shard_blob() for e in self.engines]
@@ -146,11 +146,66 @@ def test_sharded_run_bit_identical_across_ranks_and_bit_exact_against_oracle(dev
     rk.close()
 
 
+# ---- the many-chain GEMM regime with the rows split over ranks (BASELINE config 5: 64 chains x 128 columns): the all-reduce
+#      of the per-chain sums happens in the tick kernel that follows every GEMM pass (gemm_shard_allreduce)
+@pytest.mark.parametrize("devices", _layouts())
+@pytest.mark.parametrize("lik", ["bernoulli", "poisson"])
+def test_gemm_sharded_potential_identical_on_all_ranks_and_equal_to_fp64(devices, lik, half_grid):
+    N, D, C = 20011, 100, 40
+    X, y = _data(N, D, 13, lik)
+    kw = dict(likelihood=_capi.LIK_POISSON_LOG) if lik == "poisson" else {}
+    rk = Ranks(X, y, C, [0, 11003, N], devices, regime=_capi.REGIME_GEMM, **kw)
+    assert all(e.regime == _capi.REGIME_GEMM for e in rk.engines)
+    rng = np.random.default_rng(0)
+    z = (rng.normal(size=(C, D)) * 0.2).astype(F)
+    (U0, g0), (U1, g1) = rk.each(lambda e: tuple(t.cpu().numpy() for t in e.potential_and_grad(z)))
+    assert np.array_equal(U0, U1) and np.array_equal(g0, g1), "ranks disagree: replicated chains would diverge"
+    fam = families.GLM(X, y, likelihood="poisson") if lik == "poisson" else families.logistic_regression(X, y)
+    for c in (0, 17, C - 1):
+        u64, g64 = fam.potential64(z[c].astype(np.float64))
+        np.testing.assert_allclose(U0[c], u64, rtol=1e-5)
+        np.testing.assert_allclose(g0[c], g64, rtol=1e-5, atol=1e-5 * np.abs(g64).max())
+    res2 = rk.each(lambda e: tuple(t.cpu().numpy() for t in e.potential_and_grad(z)))      # tags carry the launch number
+    assert np.array_equal(res2[0][0], U0) and np.array_equal(res2[1][1], g0)
+    rk.close()
+
+
+@pytest.mark.parametrize("devices", _layouts())
+def test_gemm_sharded_run_bit_identical_across_ranks_and_bit_exact_against_oracle(devices, half_grid):
+    N, D, C = 9000, 70, 24
+    X, y = _data(N, D, 14)
+    rk = Ranks(X, y, C, [0, 5000, N], devices, regime=_capi.REGIME_GEMM, max_tree_depth_warmup=4, max_tree_depth=4)
+    keys = prng.split(prng.key(9), C)
+    rk.each(lambda e: e.init(keys, 12))
+    # two launches (12 warm-up transitions collected away, then 8 samples; the second is pass-bounded and resumed)
+    rk.each(lambda e: e.run(12, 12, fields=()))
+    outs = rk.each(lambda e: e.run(20, 12, fields=FIELDS, max_passes=25))
+    outs = rk.each(lambda e: {k: v.cpu().numpy() for k, v in e.run(20, 12, fields=FIELDS, out=outs[rk.engines.index(e)]).items()})
+    for f in FIELDS:
+        assert np.array_equal(outs[0][f], outs[1][f]), f
+    fam = families.logistic_regression(X, y)
+
+    def device_potential(c):
+        def pot(zc):
+            zz = np.zeros((C, D), F)
+            zz[c] = zc
+            U, g = rk.each(lambda e: tuple(t.cpu().numpy() for t in e.potential_and_grad(zz)))[0]
+            return F(U[c]), g[c]
+        return pot
+    cc = 5
+    kern = chain.Kernel(device_potential(cc), max_tree_depth=(4, 4))
+    res, _ = chain.run_chain(kern, fam, keys[cc], 12, 8, fields=FIELDS)
+    for f in FIELDS:
+        assert np.array_equal(outs[0][f][cc], res[f]), f
+    rk.close()
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (ranks = processes, CUDA IPC)")
-def test_sharded_processes_over_cuda_ipc():
+@pytest.mark.parametrize("regime", ["stream", "gemm"])
+def test_sharded_processes_over_cuda_ipc(regime):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(root, "tests", "rowshard_worker.py")]
+           "--master-port", "29533", os.path.join(root, "tests", "rowshard_worker.py"), regime]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert "ROWSHARD_OK" in p.stdout
