@@ -9,6 +9,8 @@ Configs (BASELINE.json `configs`); the default and the headline 
   c2  covtype-shaped Bayesian logistic regression NUTS, N = 581012, D = 54 fp32, 8 chains per GPU  -- streaming regime, HBM roofline
   c3  hierarchical GLM, N = 100k, D = 256, 16384 chains per GPU                                    -- tcgen05 GEMM regime, tensor roofline
   c4  horseshoe regression, N = 10k, D = 1000, 1024 chains per GPU                                 -- tcgen05 GEMM regime
+  c5  row-sharded logistic regression, 25M rows x 128 columns PER GPU (200M over 8), 64 replicated chains, the per-chain
+      (log-density, gradient) sums all-reduced over the ranks after every pass                     -- GEMM regime + peer mailboxes
 
 c2.  A *step* is TRANSITIONS_PER_STEP NUTS transitions of every chain (fixed samples per chain, what a user of
 ``MCMC.run`` experiences), post warm-up; adaptation runs before the timed region as setup.  A GPU needs as many sweeps of X as
@@ -40,12 +42,14 @@ WORKLOADS = {
     "c2": "configs[1]: covtype-shaped Bayesian logistic regression NUTS (N=581012, D=54 fp32, synthetic, 8 chains per GPU, max_tree_depth=10)",
     "c3": "configs[2]: vectorized-chain hierarchical GLM NUTS (N=100000, D=256 with a 64-column group block sharing a HalfCauchy scale, Bernoulli-logit, synthetic, 16384 chains per GPU)",
     "c4": "configs[3]: horseshoe regression NUTS (examples/horseshoe_regression.py recipe scaled to N=10000, D=1000, Normal likelihood, synthetic, 1024 chains per GPU)",
+    "c5": "configs[4]: row-sharded logistic regression NUTS (N=25M rows per GPU = 200M over 8 GPUs, D=128 fp32, generated on the device, 64 chains replicated on every GPU, all-reduce of grad+logp per leapfrog)",
 }
 C2_ROWS, C2_COLS, C2_CHAINS = 581012, 54, 8
 C2_BYTES_PER_PASS = C2_ROWS * C2_COLS * 4 + C2_ROWS * 4          # one sweep of X and y serves every chain
 C2_TRANSITIONS_PER_STEP = 400
 C2_PASSES_PER_STEP = 3000           # pass-bounded secondary measurement
 C2_ADAPT_ITERS = 600
+C5 = dict(rows_per_gpu=25_000_000, D=128, C=64, warm_passes=12, passes_per_step=4, num_warmup=100)
 GEMM = {"c3": dict(N=100_000, D=256, C=16384, warm_passes=120, passes_per_step=12),
         "c4": dict(N=10_000, D=1000, C=1024, warm_passes=300, passes_per_step=60)}
 
@@ -73,6 +77,11 @@ def make_data(config):
         X = rng.standard_normal(size=(g["N"], g["D"]), dtype=np.float32)
         X -= X.mean(0)
         return X, (2 * X[:, 0] - X[:, 1] + 0.5 * X[:, 2] + 0.05 * rng.normal(size=g["N"])).astype(F)
+    if config == "c5":                                            # CPU legs only: a 200k-row sample of one GPU's shard
+        rng = np.random.default_rng(5)
+        X = rng.standard_normal(size=(200_000, C5["D"]), dtype=np.float32)
+        beta = (rng.normal(size=C5["D"]) * 0.1).astype(F)
+        return X, (rng.uniform(size=X.shape[0]) < 1 / (1 + np.exp(-(X @ beta)))).astype(F)
     raise ValueError(config)
 
 
@@ -143,6 +152,9 @@ def _cpu_family(config):
         if config == "c2":
             fam = families.logistic_regression(X, y)
             _CPU["pot"] = fam.potential_and_grad_f32          # fp32 BLAS matvecs: the arithmetic a CPU run of the reference performs
+        elif config == "c5":
+            fam = families.logistic_regression(X, y)
+            _CPU["pot"] = fam.potential_and_grad_f32
         elif config == "c3":
             fam = families.GLM(X, y, global_scale="halfcauchy", group_cols=(192, 256), tau_scale=1.0)
             _CPU["pot"] = fam.potential_and_grad
@@ -181,7 +193,7 @@ def cpu_start(config, X, y, chains=8):
         var = np.diag(np.linalg.inv(H))
         z = (b[None] + rng.normal(size=(chains, X.shape[1])) * np.sqrt(var)[None]).astype(F)
         return z, np.full(chains, 0.33, F), np.tile(var.astype(F), (chains, 1))
-    D = X.shape[1] + 1 if config == "c3" else 2 * X.shape[1] + 2
+    D = X.shape[1] + 1 if config == "c3" else X.shape[1] if config == "c5" else 2 * X.shape[1] + 2
     z = (rng.normal(size=(chains, D)) * 0.05).astype(F)
     return z, np.full(chains, 0.01, F), np.full((chains, D), 1.0, F)
 
@@ -233,6 +245,11 @@ def run_reference(args):
     value = float(np.median(rates))
     sample = (f"{len(rates)} steps, each {cores} single-threaded processes x 1 oracle NUTS transition from the same start "
               f"(tree depth capped, {sum(leaps)} leapfrogs in total); median; spread {(max(rates) - min(rates)) / value:.2f}")
+    if config == "c5":
+        scale = X.shape[0] / float(C5["rows_per_gpu"] * max(args.gpus, 1))
+        sample += f"; run on {X.shape[0]} rows and scaled linearly to the {C5['rows_per_gpu'] * max(args.gpus, 1)} rows of the config (x {scale:.3g})"
+        rates = [r * scale for r in rates]
+        value *= scale
     line = {"impl": "reference", "metric": "grad_evals_per_sec", "value": value, "unit": "grad-evals/s",
             "n_gpus": args.gpus, "steps": len(rates), "warmup": 1, "ms_per_step": 1e3 * float(np.median(leaps)) / value,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -569,6 +586,124 @@ def run_gemm(args):
     d.close()
 
 
+# ------------------------------------------------------------------------------------------ c5 (row-sharded)
+def run_c5(args):
+    """Every rank generates ITS rows on the device (102 GB never exist on the host), all ranks replicate the 64
+    chains (same keys) and exchange the per-chain sums after every GEMM pass.  A step = passes_per_step passes of all chains."""
+    import torch
+    from numpyro_b200 import _capi, engine as eng, random as b2random
+    d = Dist()
+    world, rank, dev = d.world, d.rank, d.dev
+    g = dict(C5)
+    g["rows_per_gpu"] = int(os.environ.get("B200NUTS_C5_ROWS", g["rows_per_gpu"]))        # (smaller shards for smoke runs)
+    rows, D, C = g["rows_per_gpu"], g["D"], g["C"]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5000 + rank)
+    X = torch.empty((rows, D), dtype=torch.float32, device=dev)
+    blk = 1 << 20
+    for lo in range(0, rows, blk):                                     # (blockwise: no second 12.8 GB temporary)
+        X[lo:lo + blk].normal_(generator=gen)
+    beta_true = torch.from_numpy((np.random.default_rng(5).normal(size=D) * 0.1).astype(F)).to(dev)
+    y = torch.empty(rows, dtype=torch.float32, device=dev)
+    for lo in range(0, rows, blk):
+        y[lo:lo + blk] = (torch.rand(min(blk, rows - lo), generator=gen, device=dev) < torch.sigmoid(X[lo:lo + blk] @ beta_true)).float()
+    keys = b2random.split(b2random.PRNGKey(1), C)                     # replicated chains: the same keys on every rank
+    kw = dict(shard_rank=rank, shard_count=world, n_rows_global=rows * world) if world > 1 else {}
+    e = eng.Engine(device=dev, family=_capi.FAMILY_GLM, num_chains=C, X=X, y=y, regime=_capi.REGIME_GEMM,
+                   max_tree_depth_warmup=6, max_tree_depth=6, **kw)
+    if world > 1:
+        e.connect_shards()                                             # mailboxes opened through CUDA IPC
+    info = e.gemm_info()
+    NW = g["num_warmup"]
+    e.init(keys, NW)
+    lf = lambda: sum(int(s.total_leapfrogs) for s in e.state()[0])
+    e.run(NW, NW, fields=(), max_passes=g["warm_passes"])
+    P, W = g["passes_per_step"], max(args.warmup, 3)
+    step = lambda: e.run(NW, NW, fields=(), max_passes=P)
+    for _ in range(W):
+        step()
+    clocks = ClockSampler(d.local)
+    if rank == 0:
+        clocks.start()
+    lf0, p0, l0 = lf(), e.pass_count, e.launch_count
+    c0 = e.debug_clocks().astype(np.float64)
+    d.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    d.barrier()
+    ms = ev0.elapsed_time(ev1)
+    leap, passes, launches = lf() - lf0, e.pass_count - p0, e.launch_count - l0
+    c1 = e.debug_clocks().astype(np.float64)
+    st, vec = e.state()
+    iters = [int(s.i) for s in st]
+    # every rank must hold the same chains, bit for bit (the replicas would diverge otherwise)
+    sig = torch.from_numpy(np.ascontiguousarray(vec["z"])).to(dev)
+    same = True
+    if world > 1:
+        sigs = [torch.empty_like(sig) for _ in range(world)]
+        d.dist.all_gather(sigs, sig)
+        same = all(torch.equal(sigs[0].view(torch.int32), s_.view(torch.int32)) for s_ in sigs)
+    mx = d.reduce([ms], "MAX")
+    per_rank = d.gather_obj({"rank": rank, "ms": ms, "passes": int(passes), "grad_evals": int(leap)})
+    if rank != 0:
+        e.close()
+        d.close()
+        return
+    clk = clocks.stop()
+    ms = mx[0]
+    peaks = measured_peaks()
+    bytes_per_pass = rows * D * 4 + rows * 4                            # per GPU: its rows of X and y once per pass (all 64 chains)
+    achieved = passes * bytes_per_pass / (ms * 1e-3) / 1e9
+    tf32_peak = 0.5 * peaks["bf16_tflops_sustained"]
+    tflops = 4.0 * rows * D * leap / (ms * 1e-3) / 1e12                # per GPU, algorithmic
+    cyc = c1 - c0
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        n_cpu = 200_000
+        Xc, yc = X[:n_cpu].cpu().numpy(), y[:n_cpu].cpu().numpy()
+        cpu = cpu_baseline("c5", Xc, yc, depth=3, rounds=3)
+        cpu["sample"] += f"; run on the first {n_cpu} rows and scaled linearly to {rows} rows (x {n_cpu / rows:.4g})"
+        cpu["value_at_sample_size"] = cpu["value"]
+        cpu["value"] = cpu["value"] * n_cpu / rows
+    line = {
+        "metric": "grad_evals_per_sec", "value": leap / (ms * 1e-3), "unit": "grad-evals/s", "n_gpus": world,
+        "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tf32 tensor cores, 3-term split, fp32 accumulate)", "data": "synthetic (generated on the device)",
+        "config": {"workload": WORKLOADS["c5"], "chains_total": C, "rows_per_gpu": rows, "rows_total": rows * world, "passes_per_step": P,
+                   "step": "a fixed number of gradient passes of the 64 replicated chains; every GPU sweeps its own rows in every pass",
+                   "scaling_note": "weak in the data: rows per GPU are fixed, the dataset grows with the number of GPUs; grad-evals/s of the "
+                                   "64 chains stays flat when the exchange is hidden (value(N) / value(1), not / N, is the efficiency)",
+                   "phase": f"early warm-up (after {g['warm_passes']} untimed passes; chains at iterations {min(iters)}..{max(iters)} of {NW})",
+                   "l2": "inputs_larger_than_l2 (tile images of X: 2 x %.1f GB per GPU)" % (rows * D * 8 / 1e9),
+                   "gemm": info, "parallelism": f"rows sharded over {world} GPU(s); all-reduce of [64 chains x (128 + 1)] fp32 per pass through peer "
+                                                "mailboxes (CUDA IPC over NVLink), sums in rank order, no NCCL on the data path"},
+        "grad_evals": int(leap), "grad_evals_per_pass": leap / max(passes, 1), "ms_per_pass": ms / max(passes, 1),
+        "row_grad_evals_per_sec": leap * float(rows) * world / (ms * 1e-3),
+        "replicas_bit_identical": bool(same),
+        "gpu_launches": int(launches) * world,
+        "e2e": {"value": None, "unit": "grad-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "what": "not measured: SURVEY.md 8(d) generates every rank's shard on the device (the 102 GB dataset never exists on the host)"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                     "traffic": None, "peak_source": peaks["source"], "kernel": "gemm_pass_kernel",
+                     "algorithmic_bytes_per_pass_per_gpu": bytes_per_pass,
+                     "image_bytes_read_per_pass_per_gpu": rows * D * 16 + rows * 4,
+                     "tensor": {"achieved_tflops": tflops, "peak_tf32": tf32_peak, "frac": tflops / tf32_peak,
+                                "executed_frac": tflops * 3 * 2 / tf32_peak,
+                                "note": "3-term split x 128-lane chain tile half filled by 64 chains: executed tensor work = 6x algorithmic"},
+                     "side": "SURVEY 8(d) ridge: the config needs 419 algorithmic TFLOP/s per GPU to stay HBM-bound; with the fp32-parity split the "
+                             "pass is tensor- and image-traffic-bound (the pre-split X / X^T tile images are 4x the algorithmic bytes)",
+                     "cta0_cycles_per_pass": cyc[0] / max(passes, 1), "cta0_wait_epilogue": cyc[2] / max(cyc[0], 1),
+                     "cta0_wait_tile_copies": cyc[3] / max(cyc[0], 1), "cta0_wait_own_mma": cyc[4] / max(cyc[0], 1)},
+        "cpu_baseline": cpu, "clocks": clk, "per_rank": per_rank,
+    }
+    print(json.dumps(line))
+    e.close()
+    d.close()
+
+
 # ------------------------------------------------------------------------------------------ c1
 Y8 = np.array([28.0, 8.0, -3.0, 7.0, -1.0, 1.0, 18.0, 12.0], F)
 S8 = np.array([15.0, 10.0, 16.0, 11.0, 9.0, 11.0, 10.0, 18.0], F)
@@ -660,14 +795,14 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-many-chains", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     else:
-        {"c1": run_c1, "c2": run_c2, "c3": run_gemm, "c4": run_gemm}[args.config](args)
+        {"c1": run_c1, "c2": run_c2, "c3": run_gemm, "c4": run_gemm, "c5": run_c5}[args.config](args)
 
 
 if __name__ == "__main__":
