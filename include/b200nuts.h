@@ -86,6 +86,9 @@ typedef struct B200NutsConfig {
     void* nccl_comm;           /* reserved (NULL): the per-gradient all-reduce runs inside the kernel over NVLink peer
                                   stores in fixed rank order (see b200nuts_shard_connect), not through NCCL */
     int64_t n_rows_global;     /* row-sharded handles: rows of the whole dataset (0 => n_rows) */
+    /* --- mass matrix structure (hmc.py:916-951 dense_mass; hmc_util.py:439-515) --- */
+    int32_t dense_mass;        /* 1: one dense [D, D] inverse mass matrix over all latent sites (dense_mass=True); 0: diagonal */
+    int32_t reserved0;
 } B200NutsConfig;
 
 /* Collection window of one run = fori_collect(lower, upper, thinning) (numpyro/util.py:321-454). */
@@ -182,6 +185,17 @@ int b200nuts_constrained_dim(const B200Nuts* h);
 int b200nuts_log_likelihood(B200Nuts* h, const float* z, int64_t n, float* out, void* stream);
 int b200nuts_predict(B200Nuts* h, const float* z, const uint32_t* keys, int64_t n, float* out, void* stream);
 int64_t b200nuts_obs_count(const B200Nuts* h);
+
+/* Mass matrix (numpyro/infer/hmc_util.py:439-515, hmc.py:759-769).
+ * b200nuts_set_inverse_mass_matrix: the kernel's `inverse_mass_matrix=` argument, the same for every chain: host fp32,
+ * ndim 1 => [D] (a dense handle puts it on the diagonal), ndim 2 => [D][D] row-major (a diagonal handle keeps its diagonal);
+ * call before b200nuts_init.  b200nuts_get/set_dense_state: HMCAdaptState.inverse_mass_matrix / mass_matrix_sqrt /
+ * mass_matrix_sqrt_inv / the Welford m2 of a dense handle, host fp32 [num_chains][D][D] each (NULL = skip); set ignores the
+ * two roots and recomputes them from inverse_mass_matrix. */
+int b200nuts_set_inverse_mass_matrix(B200Nuts* h, const float* imm, int32_t ndim, void* stream);
+int b200nuts_get_dense_state(B200Nuts* h, float* inverse_mass_matrix, float* mass_matrix_sqrt, float* mass_matrix_sqrt_inv,
+                             float* wf_m2, void* stream);
+int b200nuts_set_dense_state(B200Nuts* h, const float* inverse_mass_matrix, const float* wf_m2, void* stream);
 
 /* PRNG parity hooks: host in / host out, computed on the device, synchronising. */
 int b200nuts_prng_split(const uint32_t* keys, int64_t n_keys, int32_t num, uint32_t* out);      /* out [n_keys][num][2] */

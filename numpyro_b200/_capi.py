@@ -39,6 +39,7 @@ class Config(C.Structure):
         ("model_built", i32), ("regime", i32),
         ("shard_rank", i32), ("shard_count", i32), ("nccl_comm", vp),
         ("n_rows_global", i64),
+        ("dense_mass", i32), ("reserved0", i32),
     ]
 
 
@@ -109,6 +110,9 @@ EXPORTS = {
     "b200nuts_log_likelihood": (C.c_int, [vp, vp, i64, vp, vp]),
     "b200nuts_predict": (C.c_int, [vp, vp, vp, i64, vp, vp]),
     "b200nuts_obs_count": (i64, [vp]),
+    "b200nuts_set_inverse_mass_matrix": (C.c_int, [vp, vp, i32, vp]),
+    "b200nuts_get_dense_state": (C.c_int, [vp, vp, vp, vp, vp, vp]),
+    "b200nuts_set_dense_state": (C.c_int, [vp, vp, vp, vp]),
     "b200nuts_prng_split": (C.c_int, [vp, i64, i32, vp]),
     "b200nuts_prng_bits": (C.c_int, [vp, i64, vp]),
     "b200nuts_prng_uniform": (C.c_int, [vp, i64, f32, f32, vp]),
@@ -132,6 +136,8 @@ def load() -> C.CDLL:
                 "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in EXPORTS.items():
+            if os.environ.get("B200NUTS_LIB") and not hasattr(lib, name):
+                continue                 # (A/B runs against an older build: entry points added since are simply absent)
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args

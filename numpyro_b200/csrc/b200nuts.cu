@@ -29,6 +29,8 @@ struct B200Nuts {
     bool inited = false;
     ChainCtl* ctl = nullptr; float* vecs = nullptr; float* gtmp = nullptr; float* scratch = nullptr;
     uint32_t* keys = nullptr;
+    float* dense = nullptr;                    // dense_mass: [C][4][D][D] (ChainVecs::dense)
+    bool imm_given = false;                    // b200nuts_set_inverse_mass_matrix was called
     // R2
     float2* partial = nullptr; uint4* beta = nullptr; StreamSync* sync = nullptr;
     float* img = nullptr; long long n_tiles = 0; int pad_rows = 0, ks = 0;   // engine-owned tile image of (X, y)
@@ -62,12 +64,14 @@ static std::string g_create_err;
 
 // ------------------------------------------------------------------------------------------------
 // small kernels
-__global__ void k_chain_begin(TickCfg cfg, ChainCtl* ctl, float* vecs, int C, int Dp, const uint32_t* keys,
+B2_D float* dense_of(float* dense, int chain, int D) { return dense ? dense + (size_t)chain * 4 * D * D : nullptr; }
+
+__global__ void k_chain_begin(TickCfg cfg, ChainCtl* ctl, float* vecs, float* dense, int C, int Dp, const uint32_t* keys,
                               const float* z0) {
     const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (chain >= C) return;
     ChainCtl c; memset(&c, 0, sizeof(c));
-    ChainVecs cv; cv.base = vecs + (size_t)chain * Dp; cv.field_stride = C * Dp;
+    ChainVecs cv; cv.base = vecs + (size_t)chain * Dp; cv.field_stride = C * Dp; cv.dense = dense_of(dense, chain, cfg.D);
     OutBufs none; memset(&none, 0, sizeof(none));
     Tick t{cfg, c, cv, none, chain, C};
     Key k; k.a = keys[2 * chain]; k.b = keys[2 * chain + 1];
@@ -76,13 +80,13 @@ __global__ void k_chain_begin(TickCfg cfg, ChainCtl* ctl, float* vecs, int C, in
     if ((threadIdx.x & 31) == 0) ctl[chain] = c;
 }
 
-__global__ void k_chain_resume(TickCfg cfg, ChainCtl* ctl, float* vecs, int C, int Dp) {
+__global__ void k_chain_resume(TickCfg cfg, ChainCtl* ctl, float* vecs, float* dense, int C, int Dp) {
     const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (chain >= C) return;
     ChainCtl c = ctl[chain];
     __syncwarp();
     if (c.phase != PH_DONE || c.init_failed || c.i >= cfg.total_iters) return;
-    ChainVecs cv; cv.base = vecs + (size_t)chain * Dp; cv.field_stride = C * Dp;
+    ChainVecs cv; cv.base = vecs + (size_t)chain * Dp; cv.field_stride = C * Dp; cv.dense = dense_of(dense, chain, cfg.D);
     OutBufs none; memset(&none, 0, sizeof(none));
     Tick t{cfg, c, cv, none, chain, C};
     t.begin_transition();
@@ -91,12 +95,12 @@ __global__ void k_chain_resume(TickCfg cfg, ChainCtl* ctl, float* vecs, int C, i
 }
 
 // Regime R1: each warp runs its chain to completion; the potential is evaluated inside the warp.
-__global__ void __launch_bounds__(128) k_warp_run(TickCfg cfg, FamilySpec fam, OutBufs out, ChainCtl* ctl, float* vecs,
+__global__ void __launch_bounds__(128) k_warp_run(TickCfg cfg, FamilySpec fam, OutBufs out, ChainCtl* ctl, float* vecs, float* dense,
                                                   float* gtmp, float* scratch, long long scratch_stride, int C, int Dp) {
     const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (chain >= C) return;
     ChainCtl c = ctl[chain];
-    ChainVecs cv; cv.base = vecs + (size_t)chain * Dp; cv.field_stride = C * Dp;
+    ChainVecs cv; cv.base = vecs + (size_t)chain * Dp; cv.field_stride = C * Dp; cv.dense = dense_of(dense, chain, cfg.D);
     Tick t{cfg, c, cv, out, chain, C};
     float* g = gtmp + (size_t)chain * Dp;
     float* scr = scratch ? scratch + (size_t)chain * scratch_stride : nullptr;
@@ -119,6 +123,17 @@ __global__ void k_potential_warp(FamilySpec fam, const float* z, float* U, float
     potential_inwarp(fam, z + (size_t)chain * fam.D, scratch ? scratch + (size_t)chain * scratch_stride : nullptr, u,
                      g + (size_t)chain * fam.D);
     if ((threadIdx.x & 31) == 0) U[chain] = u;
+}
+
+// dense handles: (re)derive M^1/2 and the Cholesky workspace from the M^-1 block of every chain (set_dense_state)
+__global__ void k_dense_roots(TickCfg cfg, ChainCtl* ctl, float* vecs, float* dense, int C, int Dp) {
+    const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (chain >= C) return;
+    ChainCtl c = ctl[chain];
+    ChainVecs cv; cv.base = vecs + (size_t)chain * Dp; cv.field_stride = C * Dp; cv.dense = dense_of(dense, chain, cfg.D);
+    OutBufs none; memset(&none, 0, sizeof(none));
+    Tick t{cfg, c, cv, none, chain, C};
+    t.dense_roots();
 }
 
 // velocity_verlet halves for the leapfrog parity hook (numpyro/infer/hmc_util.py:289-309)
@@ -416,7 +431,7 @@ int b200nuts_constrained_dim(const B200Nuts* h) {
 
 void b200nuts_destroy(B200Nuts* h) {
     if (!h) return;
-    cudaFree(h->ctl); cudaFree(h->vecs); cudaFree(h->gtmp); cudaFree(h->scratch); cudaFree(h->keys);
+    cudaFree(h->ctl); cudaFree(h->vecs); cudaFree(h->gtmp); cudaFree(h->scratch); cudaFree(h->keys); cudaFree(h->dense);
     cudaFree(h->partial); cudaFree(h->beta); cudaFree(h->sync); cudaFree(h->img);
     if (h->trace_host) cudaFreeHost(h->trace_host);
     for (int q = 0; q < kMaxShards; ++q) if (h->mail_ipc[q] && h->mail_peer[q]) cudaIpcCloseMemHandle(h->mail_peer[q]);
@@ -451,8 +466,11 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
     if (regime == B200NUTS_REGIME_AUTO) {
         // many chains: the gradient is a GEMM (tcgen05); tall data with a handful of chains: one HBM sweep per pass; else in-warp
         if (gemm_ok && h->C >= 128 && (long long)h->fam.N * h->fam.Dx >= (1LL << 17)) regime = B200NUTS_REGIME_GEMM;
-        else if (stream_ok && (long long)h->fam.N * h->fam.Dx >= (1LL << 20)) regime = B200NUTS_REGIME_STREAM;
+        else if (stream_ok && (long long)h->fam.N * h->fam.Dx >= (1LL << 20)) regime = cfg->dense_mass ? B200NUTS_REGIME_GEMM : B200NUTS_REGIME_STREAM;
         else regime = B200NUTS_REGIME_WARP;
+    }
+    if (regime == B200NUTS_REGIME_STREAM && cfg->dense_mass) {
+        g_create_err = "dense_mass is not available in the streaming regime (use the warp or the gemm regime)"; delete h; return B200NUTS_EINVAL;
     }
     if (regime == B200NUTS_REGIME_STREAM && !stream_ok) {
         g_create_err = "stream regime needs a GLM family with <= 64 columns and one SM per chain (<= 148 chains)"; delete h; return B200NUTS_EINVAL;
@@ -482,6 +500,12 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
     if ((ce = cudaMalloc(&h->keys, sizeof(uint32_t) * 2 * h->C)) != cudaSuccess) return fail("cudaMalloc keys", ce);
     cudaMemset(h->vecs, 0, sizeof(float) * (size_t)V_COUNT * h->C * h->Dp);
     cudaMemset(h->ctl, 0, sizeof(ChainCtl) * h->C);
+    if (cfg->dense_mass) {
+        const size_t bytes = sizeof(float) * (size_t)h->C * 4 * h->D * h->D;
+        if (bytes > ((size_t)8 << 30)) { g_create_err = "dense_mass: num_chains x 4 x D^2 floats exceed 8 GiB"; b200nuts_destroy(h); return B200NUTS_EINVAL; }
+        if ((ce = cudaMalloc(&h->dense, bytes)) != cudaSuccess) return fail("cudaMalloc dense mass matrices", ce);
+        cudaMemset(h->dense, 0, bytes);
+    }
     if (glm && regime == B200NUTS_REGIME_WARP) {
         const size_t stride = (size_t)h->fam.N + h->fam.Dx;
         if ((ce = cudaMalloc(&h->scratch, sizeof(float) * stride * h->C)) != cudaSuccess) return fail("cudaMalloc scratch", ce);
@@ -537,7 +561,7 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
         }
     }
     if (regime == B200NUTS_REGIME_GEMM) {
-        const std::string ge = gemm_create(&h->gemm, h->fam, h->C, h->Dp, h->num_sms, h->ctl, h->vecs, &h->launches);
+        const std::string ge = gemm_create(&h->gemm, h->fam, h->C, h->Dp, h->num_sms, h->ctl, h->vecs, h->dense, &h->launches);
         if (!ge.empty()) { g_create_err = ge; b200nuts_destroy(h); return B200NUTS_ECUDA; }
         if (h->shard_count > 1) {
             const size_t mb = gemm_mail_bytes(h->gemm);
@@ -550,7 +574,7 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
         // a context-wide synchronisation; a persistent kernel of another (row-sharded) handle that is waiting for this
         // handle's contribution would then never finish.
         cudaFuncAttributes fa;
-        const void* fns[] = {(const void*)k_chain_begin, (const void*)k_chain_resume, (const void*)k_warp_run, (const void*)k_potential_warp,
+        const void* fns[] = {(const void*)k_chain_begin, (const void*)k_chain_resume, (const void*)k_warp_run, (const void*)k_potential_warp, (const void*)k_dense_roots,
                              (const void*)k_leap_pre, (const void*)k_leap_post, (const void*)k_constrain,
                              regime == B200NUTS_REGIME_STREAM ? stream_kernel_for(h->ks, h->fam.likelihood, h->num_groups) : nullptr};
         for (const void* fn : fns)
@@ -575,7 +599,8 @@ int b200nuts_init(B200Nuts* h, const uint32_t* keys, const float* z0, int32_t nu
     if (!e.empty()) { h->err = e; return B200NUTS_EINVAL; }
     CK(cudaMemcpyAsync(h->keys, keys, sizeof(uint32_t) * 2 * h->C, cudaMemcpyHostToDevice, st));
     const int blocks = (h->C + 3) / 4;
-    k_chain_begin<<<blocks, 128, 0, st>>>(h->tick, h->ctl, h->vecs, h->C, h->Dp, h->keys, z0);
+    h->tick.imm_given = h->imm_given ? 1 : 0;
+    k_chain_begin<<<blocks, 128, 0, st>>>(h->tick, h->ctl, h->vecs, h->dense, h->C, h->Dp, h->keys, z0);
     CK(cudaGetLastError());
     h->launches += 1;
     h->inited = true;
@@ -597,11 +622,11 @@ static int run_locked(B200Nuts* h, const B200NutsRun* run, cudaStream_t st) {
         h->err = "max_passes needs the streaming regime with <= 8 chains or the gemm regime"; return B200NUTS_EINVAL;
     }
     const int blocks = (h->C + 3) / 4;
-    k_chain_resume<<<blocks, 128, 0, st>>>(h->tick, h->ctl, h->vecs, h->C, h->Dp);
+    k_chain_resume<<<blocks, 128, 0, st>>>(h->tick, h->ctl, h->vecs, h->dense, h->C, h->Dp);
     CK(cudaGetLastError());
     h->launches += 1;
     if (h->regime == B200NUTS_REGIME_WARP) {
-        k_warp_run<<<blocks, 128, 0, st>>>(h->tick, h->fam, out, h->ctl, h->vecs, h->gtmp, h->scratch,
+        k_warp_run<<<blocks, 128, 0, st>>>(h->tick, h->fam, out, h->ctl, h->vecs, h->dense, h->gtmp, h->scratch,
                                            (long long)h->fam.N + h->fam.Dx, h->C, h->Dp);
         CK(cudaGetLastError());
         h->launches += 1;
@@ -703,6 +728,75 @@ int b200nuts_set_state(B200Nuts* h, const B200NutsChainState* states, const floa
                                  sizeof(float) * h->D, h->C, cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
     h->inited = true;
+    return 0;
+}
+
+// ---- mass matrix structure -------------------------------------------------------------
+int b200nuts_set_inverse_mass_matrix(B200Nuts* h, const float* imm, int32_t ndim, void* stream) {
+    if (!h || !imm || (ndim != 1 && ndim != 2)) return B200NUTS_EINVAL;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (int rc0 = sync_locked(h)) return rc0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = h->D;
+    if (h->dense) {
+        std::vector<float> blk((size_t)h->C * 4 * D * D, 0.0f);
+        for (int c = 0; c < h->C; ++c)
+            for (int i = 0; i < D; ++i)
+                for (int j = 0; j < D; ++j)
+                    blk[((size_t)c * 4) * D * D + (size_t)i * D + j] = ndim == 2 ? imm[(size_t)i * D + j] : (i == j ? imm[i] : 0.0f);
+        CK(cudaMemcpyAsync(h->dense, blk.data(), sizeof(float) * blk.size(), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    } else {
+        std::vector<float> v((size_t)h->C * D);
+        for (int c = 0; c < h->C; ++c)
+            for (int d = 0; d < D; ++d) v[(size_t)c * D + d] = ndim == 2 ? imm[(size_t)d * D + d] : imm[d];
+        CK(cudaMemcpy2DAsync(h->vecs + (size_t)V_IMM * h->C * h->Dp, sizeof(float) * h->Dp, v.data(), sizeof(float) * D,
+                             sizeof(float) * D, h->C, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    h->imm_given = true;
+    return 0;
+}
+
+int b200nuts_get_dense_state(B200Nuts* h, float* inverse_mass_matrix, float* mass_matrix_sqrt, float* mass_matrix_sqrt_inv,
+                             float* wf_m2, void* stream) {
+    if (!h) return B200NUTS_EINVAL;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->dense) { h->err = "not a dense_mass handle"; return B200NUTS_ESTATE; }
+    if (int rc0 = sync_locked(h)) return rc0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = h->D; const size_t DD = (size_t)D * D;
+    std::vector<float> blk((size_t)h->C * 4 * DD);
+    CK(cudaMemcpyAsync(blk.data(), h->dense, sizeof(float) * blk.size(), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int c = 0; c < h->C; ++c) {
+        const float* b = blk.data() + (size_t)c * 4 * DD;
+        if (inverse_mass_matrix) memcpy(inverse_mass_matrix + c * DD, b, sizeof(float) * DD);
+        if (mass_matrix_sqrt) memcpy(mass_matrix_sqrt + c * DD, b + DD, sizeof(float) * DD);
+        if (wf_m2) memcpy(wf_m2 + c * DD, b + 2 * DD, sizeof(float) * DD);
+        if (mass_matrix_sqrt_inv)                           // tril_inv[i][j] = Lc[D-1-j][D-1-i] (hmc_util.py:229-231)
+            for (int i = 0; i < D; ++i)
+                for (int j = 0; j < D; ++j) mass_matrix_sqrt_inv[c * DD + (size_t)i * D + j] = b[3 * DD + (size_t)(D - 1 - j) * D + (D - 1 - i)];
+    }
+    return 0;
+}
+
+int b200nuts_set_dense_state(B200Nuts* h, const float* inverse_mass_matrix, const float* wf_m2, void* stream) {
+    if (!h || !inverse_mass_matrix) return B200NUTS_EINVAL;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->dense) { h->err = "not a dense_mass handle"; return B200NUTS_ESTATE; }
+    if (int rc0 = sync_locked(h)) return rc0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = h->D; const size_t DD = (size_t)D * D;
+    for (int c = 0; c < h->C; ++c) {
+        float* b = h->dense + (size_t)c * 4 * DD;
+        CK(cudaMemcpyAsync(b, inverse_mass_matrix + c * DD, sizeof(float) * DD, cudaMemcpyHostToDevice, st));
+        if (wf_m2) CK(cudaMemcpyAsync(b + 2 * DD, wf_m2 + c * DD, sizeof(float) * DD, cudaMemcpyHostToDevice, st));
+    }
+    k_dense_roots<<<(h->C + 3) / 4, 128, 0, st>>>(h->tick, h->ctl, h->vecs, h->dense, h->C, h->Dp);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    h->launches += 1;
     return 0;
 }
 

@@ -14,9 +14,11 @@
 #if defined(__CUDACC__)
 #define B2_HD __host__ __device__ __forceinline__
 #define B2_D __device__ __forceinline__
+#define B2_HD_COLD static __host__ __device__ __noinline__      // rarely taken paths: kept out of line (code size, build time)
 #else
 #define B2_HD inline
 #define B2_D inline
+#define B2_HD_COLD inline
 #endif
 
 namespace b2 {
@@ -58,6 +60,15 @@ inline int lane_step() { return 1; }
 #endif
 
 #define B2_FOR_D(d, D) for (int d = b2::lane_first(); d < (D); d += b2::lane_step())
+
+// Warp barrier between lanes that hand vector elements to each other through memory.
+#if defined(__CUDA_ARCH__)
+// A shuffle whose result is consumed, not __syncwarp(): ptxas 12.9 was seen to turn a __syncwarp() that follows a
+// lane-strided loop into a NOP (stream_engine.cuh, gred reduction); a shuffle cannot be dropped.
+B2_D void lane_sync() { unsigned int x = __shfl_sync(0xFFFFFFFFu, threadIdx.x, 0); asm volatile("" ::"r"(x) : "memory"); }
+#else
+inline void lane_sync() {}
+#endif
 
 // Canonical reduction of f(d), d in [0, D): lane partials p[l] = sum_k f(l + 32k) (k ascending,
 // starting from +0), then p[l] += p[l ^ off] for off = 16, 8, 4, 2, 1.  All lanes get the result.

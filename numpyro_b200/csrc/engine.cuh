@@ -126,6 +126,7 @@ inline std::string make_tick_cfg(const B200NutsConfig& c, const FamilySpec& f, c
     t.collect_start = 0; t.thinning = 1; t.S = 0;
     t.init_given = init_given ? 1 : 0;
     t.init_radius = c.init_radius > 0 ? c.init_radius : 2.0f;
+    t.dense = c.dense_mass ? 1 : 0; t.imm_given = 0;        // (imm_given: set by the caller that pre-loaded the matrix)
     t.n_sites = sites.n_sites;
     for (int i = 0; i < sites.n_sites; ++i) { t.site_off[i] = sites.off[i]; t.site_size[i] = sites.size[i]; }
     return "";

@@ -42,13 +42,7 @@ constexpr float kLogSqrt2Pi = 0.918938533204672742f;
 constexpr float kLog2 = 0.693147180559945309f;
 constexpr float kLogPi = 1.144729885849400174f;
 
-#if defined(__CUDA_ARCH__)
-// A shuffle whose result is consumed, not __syncwarp(): ptxas 12.9 was seen to turn a __syncwarp() that follows a
-// lane-strided loop into a NOP (stream_engine.cuh, gred reduction); a shuffle cannot be dropped.
-B2_D void lane_sync() { unsigned int x = __shfl_sync(0xFFFFFFFFu, threadIdx.x, 0); asm volatile("" ::"r"(x) : "memory"); }
-#else
-inline void lane_sync() {}
-#endif
+// (lane_sync(): common.cuh)
 
 // ---- per-observation loss: value and d/d eta of the negative log-likelihood ------------------
 B2_HD void glm_loss(int lik, float eta, float y, float& loss, float& dl) {

@@ -17,7 +17,7 @@ struct GemmRegime {
     float *gtmp = nullptr, *gbeta = nullptr;
     int *tile_count = nullptr, *active_tiles = nullptr;
     GemmSched* sched = nullptr; GemmCtx* ctx = nullptr;
-    ChainCtl* ctl = nullptr; float* vecs = nullptr;
+    ChainCtl* ctl = nullptr; float* vecs = nullptr; float* dense = nullptr;
     bool use_graph = true;
     cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; cudaGraphConditionalHandle cond = 0;
     unsigned long long passes_seen = 0ull;
@@ -47,7 +47,7 @@ static std::string launch_pass(GemmRegime* g, cudaStream_t st) {
 static std::string launch_tick(GemmRegime* g, int first, cudaStream_t st) {
     const int blocks = (g->C + 3) / 4;
     k_gemm_tick<<<blocks, 128, 0, st>>>(g->gp, g->ctx, g->sched, g->fam, g->ctl, g->vecs, g->gtmp, g->gbeta, g->bimg, g->tile_count,
-                                        g->C, g->Dp, first, g->shard);
+                                        g->C, g->Dp, first, g->shard, g->dense);
     GCK(cudaGetLastError());
     k_gemm_sched<<<1, 32, 0, st>>>(g->ctx, g->sched, g->tile_count, g->active_tiles, g->CT, first, g->cond, 0);
     GCK(cudaGetLastError());
@@ -73,7 +73,7 @@ static std::string build_graph(GemmRegime* g) {
     }
     {
         int first = 0;
-        void* args[] = {&g->gp, &g->ctx, &g->sched, &g->fam, &g->ctl, &g->vecs, &g->gtmp, &g->gbeta, &g->bimg, &g->tile_count, &g->C, &g->Dp, &first, &g->shard};
+        void* args[] = {&g->gp, &g->ctx, &g->sched, &g->fam, &g->ctl, &g->vecs, &g->gtmp, &g->gbeta, &g->bimg, &g->tile_count, &g->C, &g->Dp, &first, &g->shard, &g->dense};
         cudaKernelNodeParams kp; memset(&kp, 0, sizeof(kp));
         kp.func = (void*)k_gemm_tick; kp.gridDim = dim3((g->C + 3) / 4); kp.blockDim = dim3(128); kp.kernelParams = args;
         GCK(cudaGraphAddKernelNode(&n_tick, body, &n_pass, 1, &kp));
@@ -89,10 +89,11 @@ static std::string build_graph(GemmRegime* g) {
     return "";
 }
 
-std::string gemm_create(GemmRegime** out, const FamilySpec& fam, int C, int Dp, int num_sms, ChainCtl* ctl, float* vecs, long long* launches) {
+std::string gemm_create(GemmRegime** out, const FamilySpec& fam, int C, int Dp, int num_sms, ChainCtl* ctl, float* vecs, float* dense,
+                        long long* launches) {
     *out = nullptr;
     GemmRegime* g = new GemmRegime();
-    g->fam = fam; g->C = C; g->Dp = Dp; g->num_sms = num_sms; g->ctl = ctl; g->vecs = vecs;
+    g->fam = fam; g->C = C; g->Dp = Dp; g->num_sms = num_sms; g->ctl = ctl; g->vecs = vecs; g->dense = dense;
     g->grid = num_sms;
     if (const char* e = getenv("B200NUTS_GRID")) { const int v = atoi(e); if (v >= 1 && v < g->grid) g->grid = v; }
     g->use_graph = !getenv("B200NUTS_GEMM_HOSTLOOP");

@@ -458,7 +458,7 @@ B2_D float gemm_shard_allreduce(const GemmShardDev& sh, int C, int chain, float*
 // first != 0: start of a run -- no gradient yet, only publish the betas of the chains that wait for one.
 static __global__ void __launch_bounds__(128) k_gemm_tick(GemmParams gp, const GemmCtx* ctx, GemmSched* sched, FamilySpec fam, ChainCtl* ctl,
                                                            float* vecs, float* gtmp, float* gbeta, float* bimg, int* tile_count,
-                                                           int C, int Dp, int first, GemmShardDev sh) {
+                                                           int C, int Dp, int first, GemmShardDev sh, float* dense) {
     __shared__ TickCfg s_cfg; __shared__ OutBufs s_out;
     {
         const int* src = (const int*)&ctx->cfg; int* dst = (int*)&s_cfg;
@@ -472,6 +472,7 @@ static __global__ void __launch_bounds__(128) k_gemm_tick(GemmParams gp, const G
     if (c.phase == PH_DONE) return;
     const int par = first ? 0 : ((sched->pass + 1) & 1);          // the tile counts this tick fills (k_gemm_sched flips `pass`)
     ChainVecs cv; cv.base = vecs + (size_t)chain * Dp; cv.field_stride = C * Dp;
+    if (dense) cv.dense = dense + (size_t)chain * 4 * s_cfg.D * s_cfg.D;
     if (!first) {
         Tick t{s_cfg, c, cv, s_out, chain, C};
         float* gb = gbeta + (size_t)chain * gp.Dxp; float* g = gtmp + (size_t)chain * Dp;

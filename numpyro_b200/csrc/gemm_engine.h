@@ -17,7 +17,7 @@ struct GemmStatus {
 };
 
 // All functions return "" or an error message.  ctl / vecs are the handle's chain state (engine-owned, see b200nuts.cu).
-std::string gemm_create(GemmRegime** out, const FamilySpec& fam, int C, int Dp, int num_sms, ChainCtl* ctl, float* vecs, long long* launches);
+std::string gemm_create(GemmRegime** out, const FamilySpec& fam, int C, int Dp, int num_sms, ChainCtl* ctl, float* vecs, float* dense, long long* launches);
 void gemm_destroy(GemmRegime* g);
 // Enqueue a whole run: every chain that waits for a gradient is advanced until it reaches cfg.total_iters (or for
 // max_passes passes).  Only enqueues; gemm_sync reports the outcome.

@@ -57,6 +57,8 @@
 
 namespace b2 {
 
+using StreamTick = TickT<false>;         // no dense mass matrices in this regime (see TickT)
+
 constexpr int kStreamCT = 8;             // chains per pass (= one chain group = the N of the MMAs)
 constexpr int kMaxGroups = 20;           // chain groups per handle: passes rotate over the groups, so one group's exchange
 constexpr int kMaxStreamChains = kMaxGroups * kStreamCT;   // ... hides behind the other groups' sweeps (every chain needs its own owner CTA)
@@ -305,7 +307,7 @@ B2_D void stream_publish_beta(const StreamParams& p, int chain, const float* zsr
 // chain goes next without the full bookkeeping -- publish the next beta right away (returns true; `u` and gz keep what the
 // deferred part needs).  stream_tick_deferred: advance the NUTS state machine; with a single chain group the caller runs it
 // AFTER it has staged the next pass for its own consumers, i.e. while the grid already sweeps X again.
-__device__ __forceinline__ bool stream_tick_critical(const StreamParams& p, Tick& tk, const float* gred, float* gz, float* zpeek, float nll,
+__device__ __forceinline__ bool stream_tick_critical(const StreamParams& p, StreamTick& tk, const float* gred, float* gz, float* zpeek, float nll,
                                                      int cta, unsigned long long* tdbg, uint32_t next_tag, float& u, unsigned int (&peek_stat)[3]) {
     const int lane = threadIdx.x & 31;
     const long long t0 = (lane == 0) ? clock64() : 0ll;
@@ -335,7 +337,7 @@ __device__ __forceinline__ bool stream_tick_critical(const StreamParams& p, Tick
 }
 
 // Returns true when the chain needs no further gradient.
-__device__ __forceinline__ bool stream_tick_deferred(const StreamParams& p, Tick& tk, const float* gz, const float* zpeek, float u, bool early,
+__device__ __forceinline__ bool stream_tick_deferred(const StreamParams& p, StreamTick& tk, const float* gz, const float* zpeek, float u, bool early,
                                                      unsigned long long* tdbg, unsigned int (&peek_stat)[3]) {
     const int lane = threadIdx.x & 31;
     const long long t0 = (lane == 0) ? clock64() : 0ll;
@@ -426,7 +428,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         // the chain's control block lives in this warp's registers for the whole launch (every lane holds a copy)
         ChainCtl c;
         if (is_tick && p.mode == 0) c = p.ctl[cta]; else memset(&c, 0, sizeof(c));
-        Tick tk{p.cfg, c, cv, p.out, cta, p.C};
+        StreamTick tk{p.cfg, c, cv, p.out, cta, p.C};
         bool chain_done = !is_tick || (p.mode == 0 && c.phase == PH_DONE);
         // Passes rotate over the chain groups (8 chains each) that still have work; group g's r-th sweep uses the betas its
         // owners published with tag r.  With several groups the owners' ticks overlap with the other groups' sweeps.

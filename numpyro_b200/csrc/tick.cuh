@@ -41,7 +41,8 @@ enum VecField {
     V_EPS,                              // look-ahead: unit normal draws of the next transition's momentum (prefetch())
     V_CKPT_R,                           // kMaxDepthAlloc rows
     V_CKPT_RSUM = V_CKPT_R + kMaxDepthAlloc,
-    V_COUNT = V_CKPT_RSUM + kMaxDepthAlloc
+    V_TMP0 = V_CKPT_RSUM + kMaxDepthAlloc, V_TMP1,   // dense mass matrix: M^-1 r products, Welford deltas
+    V_COUNT
 };
 
 enum Phase { PH_DONE = 0, PH_INIT = 1, PH_LEAF = 2, PH_HMC = 3, PH_HEUR = 4 };
@@ -95,6 +96,8 @@ struct TickCfg {
     int32_t num_windows; int32_t window_end[16];
     int32_t collect_start, thinning, S;     // fori_collect: start_idx, thinning, collection size
     int32_t init_given; float init_radius;
+    int32_t dense;                          // dense_mass=True: one [D, D] block over all sites (hmc.py:759-769)
+    int32_t imm_given;                      // inverse_mass_matrix= was supplied (pre-loaded into V_IMM / the dense block)
     int32_t n_sites; int32_t site_off[kMaxSites], site_size[kMaxSites];   // latent sites, trace order
 };
 
@@ -105,6 +108,8 @@ struct OutBufs {                            // all [C][S] except z [C][S][D]; nu
 
 struct ChainVecs {
     float* base; int field_stride;
+    // dense_mass=True: this chain's [4][D][D] block -- M^-1 | M^1/2 (lower triangular) | Welford m2 | Cholesky workspace
+    float* dense = nullptr;
     B2_HD float* v(int f) const { return base + (size_t)f * field_stride; }
 };
 
@@ -158,7 +163,58 @@ __host__ __device__ inline void b2_lapq(int i) {
 #define B2_LAPQ(i) do {} while (0)
 #endif
 
-struct Tick {
+// ---- dense mass matrix kernels (out of line: rarely taken, and they must not take the Tick object -- its ChainCtl lives in
+//      registers in the streaming engine) -----------------------------------------------------------------------------------
+// out = A r for a row-major [D][D] matrix: row i (lane i mod 32) accumulates left to right from +0, one rounding per operation
+B2_HD_COLD void dense_matvec(int Dn, const float* A, const float* r, float* out) {
+    lane_sync();
+    B2_FOR_D(i, Dn) {
+        const float* row = A + (size_t)i * Dn;
+        float a = 0.0f;
+        for (int j = 0; j < Dn; ++j) a = a + row[j] * r[j];
+        out[i] = a;
+    }
+    lane_sync();
+}
+// (mass_matrix_sqrt, mass_matrix_sqrt_inv) of the dense M^-1 in block 0 of `dense` (hmc_util.py:228-233, 499-509):
+//   Lc = cholesky(sym(M^-1[::-1, ::-1])) -> block 3;  tril_inv[i][j] = Lc[D-1-j][D-1-i];  M^1/2 = tril_inv^-1 -> block 1.
+// Element order as oracle/adapt.py cholesky_lower / solve_lower_identity (k ascending, one rounding per operation).
+B2_HD_COLD void dense_roots_of(int Dn, float* dense, float* tmp) {
+    const size_t DD = (size_t)Dn * Dn;
+    const float* A = dense; float* W = dense + 3 * DD; float* X = dense + DD;
+    for (int j = 0; j < Dn; ++j) {
+        lane_sync();
+        B2_FOR_D(ii, Dn - j) {
+            const int i = j + ii;
+            const int ri = Dn - 1 - i, rj = Dn - 1 - j;
+            float s = (A[(size_t)ri * Dn + rj] + A[(size_t)rj * Dn + ri]) / 2.0f;
+            for (int k = 0; k < j; ++k) s = s - W[(size_t)i * Dn + k] * W[(size_t)j * Dn + k];
+            tmp[i] = s;
+        }
+        lane_sync();
+        const float sj = tmp[j];
+        const float piv = (sj > 0.0f) ? sqrtf(sj) : f_nan();
+        B2_FOR_D(ii, Dn - j) {
+            const int i = j + ii;
+            W[(size_t)i * Dn + j] = (i == j) ? piv : tmp[i] / piv;
+        }
+        B2_FOR_D(ii, j) W[(size_t)ii * Dn + j] = 0.0f;           // (strict upper part: zero)
+    }
+    lane_sync();
+    B2_FOR_D(cidx, Dn) {                                         // forward substitution, one column per lane
+        for (int i = 0; i < Dn; ++i) {
+            float s = (i == cidx) ? 1.0f : 0.0f;
+            for (int k = 0; k < i; ++k) s = s - W[(size_t)(Dn - 1 - k) * Dn + (Dn - 1 - i)] * X[(size_t)k * Dn + cidx];
+            X[(size_t)i * Dn + cidx] = s / W[(size_t)(Dn - 1 - i) * Dn + (Dn - 1 - i)];
+        }
+    }
+    lane_sync();
+}
+
+// DENSE_OK = false compiles the dense-mass branches away (the streaming engine: its tick shares one register allocation with the
+// sweep, and the out-of-line dense kernels cost the sweep ~4 % through spills around the call sites).
+template <bool DENSE_OK>
+struct TickT {
     const TickCfg& cfg;
     ChainCtl& c;
     ChainVecs vs;
@@ -166,6 +222,7 @@ struct Tick {
     int chain, C;
 
     B2_HD float* v(int f) const { return vs.v(f); }
+    B2_HD bool dense_on() const { return DENSE_OK && cfg.dense != 0; }
     B2_HD int D() const { return cfg.D; }
 
     B2_HD void copy(int dst, int src) const {
@@ -173,9 +230,57 @@ struct Tick {
         B2_FOR_D(d, cfg.D) a[d] = b[d];
     }
 
+    // ---------------------------------------------------------------- mass matrix (diagonal vector or dense block)
+    // Dense (hmc_util.py:192-237, 439-515, 726-728, 1193-1194): every product with M^-1 / M^1/2 is a
+    // [D, D] x [D] product in which row i (lane i mod 32) accumulates its terms left to right from +0, one rounding per
+    // multiplication and per addition -- the order oracle/tree.py imm_apply restates.
+    B2_HD float* dmat(int k) const { return vs.dense + (size_t)k * cfg.D * cfg.D; }
+    B2_HD void matvec(const float* A, const float* r, float* out) const { dense_matvec(cfg.D, A, r, out); }
+    B2_HD float kin(const float* r) const {                                   // euclidean_kinetic_energy
+        if (!dense_on()) return kinetic(cfg.D, v(V_IMM), r);
+        float* t = v(V_TMP0);
+        matvec(dmat(0), r, t);
+        return 0.5f * lane_sum(cfg.D, [&](int d) { return t[d] * r[d]; });
+    }
+    B2_HD bool turning_between(const float* r_left, const float* r_right, const float* r_sum) const {   // _is_turning
+        if (!dense_on()) return is_turning(cfg.D, v(V_IMM), r_left, r_right, r_sum);
+        float *vl = v(V_TMP0), *vr = v(V_TMP1);
+        matvec(dmat(0), r_left, vl); matvec(dmat(0), r_right, vr);
+        float l, r;
+        lane_sum2(cfg.D, [&](int d, float& a, float& b) {
+            const float s = r_sum[d] - (r_left[d] + r_right[d]) / 2.0f;
+            a = vl[d] * s; b = vr[d] * s;
+        }, l, r);
+        return (l <= 0.0f) || (r <= 0.0f);
+    }
+    B2_HD void leap(float eps, const float* z, const float* r, const float* g, float* z_out, float* r_half_out) const {
+        if (!dense_on()) { leap_begin(cfg.D, eps, v(V_IMM), z, r, g, z_out, r_half_out); return; }
+        const float half = 0.5f * eps;
+        B2_FOR_D(d, cfg.D) r_half_out[d] = r[d] - half * g[d];
+        float* t = v(V_TMP0);
+        matvec(dmat(0), r_half_out, t);
+        B2_FOR_D(d, cfg.D) z_out[d] = z[d] + eps * t[d];
+    }
+    // r = S eps with S = M^1/2 (momentum_generator) or, for the step-size heuristic, S = M^-1 (the reference's quirk)
+    B2_HD void scale_normals(int which, const float* eps, float* r) const {
+        if (dense_on()) { matvec(dmat(which), eps, r); return; }
+        const float* sc = v(which ? V_SQRTM : V_IMM);
+        B2_FOR_D(d, cfg.D) r[d] = sc[d] * eps[d];
+    }
+    // (mass_matrix_sqrt, mass_matrix_sqrt_inv) of the dense M^-1 in dmat(0) (hmc_util.py:228-233, 499-509):
+    //   Lc = cholesky(sym(M^-1[::-1, ::-1])) -> workspace dmat(3);  tril_inv[i][j] = Lc[D-1-j][D-1-i];  M^1/2 = tril_inv^-1
+    // Element order as oracle/adapt.py cholesky_lower / solve_lower_identity (k ascending, one rounding per operation).
+    B2_HD void dense_roots() const { dense_roots_of(cfg.D, vs.dense, v(V_TMP0)); }
+
     // ---------------------------------------------------------------- momentum (hmc.py:92-110)
     B2_HD void draw_momentum(Key k, float* r) const {
         if (cfg.model_built) k = split_at(k, 0);           // one-block dict -> split(key, 1)[0]
+        if (dense_on()) {
+            float* en = v(V_TMP1);
+            B2_FOR_D(d, cfg.D) en[d] = normal_at(k, (uint32_t)d);
+            scale_normals(1, en, r);
+            return;
+        }
         const float* sm = v(V_SQRTM);
         B2_FOR_D(d, cfg.D) r[d] = sm[d] * normal_at(k, (uint32_t)d);
     }
@@ -216,13 +321,33 @@ struct Tick {
         const Key wk = split_at(k_wa, 0), k_ss = split_at(k_wa, 1);                           // hmc_util.py:565
         st(c.key, k_hmc); st(c.wa_key, wk);
         float* imm = v(V_IMM); float* sm = v(V_SQRTM); float* mean = v(V_WF_MEAN); float* m2 = v(V_WF_M2);
-        B2_FOR_D(d, cfg.D) { imm[d] = 1.0f; sm[d] = 1.0f; mean[d] = 0.0f; m2[d] = 0.0f; }
+        // _initialize_mass_matrix (hmc_util.py:439-515): identity, or the supplied matrix and its roots
+        if (dense_on()) {
+            const int Dn = cfg.D;
+            float *A = dmat(0), *S = dmat(1), *M2 = dmat(2), *W = dmat(3);
+            B2_FOR_D(i, Dn) {
+                for (int j = 0; j < Dn; ++j) {
+                    const float id = (i == j) ? 1.0f : 0.0f;
+                    const size_t o = (size_t)i * Dn + j;
+                    if (!cfg.imm_given) A[o] = id;
+                    S[o] = id; W[o] = id; M2[o] = 0.0f;
+                }
+                mean[i] = 0.0f;
+            }
+            if (cfg.imm_given) dense_roots();
+        } else {
+            B2_FOR_D(d, cfg.D) {
+                if (!cfg.imm_given) { imm[d] = 1.0f; sm[d] = 1.0f; }
+                else sm[d] = 1.0f / sqrtf(imm[d]);
+                mean[d] = 0.0f; m2[d] = 0.0f;
+            }
+        }
         c.mm_n = 0; c.window_idx = 0;
         c.step_size = cfg.init_step_size;
         // initial energy uses a throw-away momentum (hmc.py:340-343)
         float* r = v(V_R0);
         draw_momentum(k_mom, r);
-        c.energy = c.pe + kinetic(cfg.D, imm, r);
+        c.energy = c.pe + kin(r);
         if (cfg.adapt_step && cfg.find_heuristic) { heur_begin(k_ss, 1); return; }
         da_reinit(d_log(10.0f * c.step_size));                                               // :576
         begin_transition();
@@ -249,17 +374,18 @@ struct Tick {
         // NB: the reference hands *inverse_mass_matrix* to momentum_generator here
         // (hmc_util.py:355 vs hmc.py:92), so r = M^-1 * eps, not M^1/2 * eps.
         float* r0 = v(V_R0);
-        { Key km = cfg.model_built ? split_at(k_mom, 0) : k_mom; const float* imm = v(V_IMM);
-          B2_FOR_D(d, cfg.D) r0[d] = imm[d] * normal_at(km, (uint32_t)d); }
-        leap_begin(cfg.D, c.heur_step, v(V_IMM), v(V_Z), r0, v(V_G), v(V_ZS), v(V_RS));
+        { Key km = cfg.model_built ? split_at(k_mom, 0) : k_mom;
+          if (dense_on()) { float* en = v(V_TMP1); B2_FOR_D(d, cfg.D) en[d] = normal_at(km, (uint32_t)d); scale_normals(0, en, r0); }
+          else { const float* imm = v(V_IMM); B2_FOR_D(d, cfg.D) r0[d] = imm[d] * normal_at(km, (uint32_t)d); } }
+        leap(c.heur_step, v(V_Z), r0, v(V_G), v(V_ZS), v(V_RS));
         c.phase = PH_HEUR;
     }
     B2_HD void on_heur(float u, const float* g) {
         const float half = 0.5f * c.heur_step;
         float* rs = v(V_RS);
         B2_FOR_D(d, cfg.D) rs[d] = rs[d] - half * g[d];
-        const float e_cur = kinetic(cfg.D, v(V_IMM), v(V_R0)) + c.pe;
-        const float e_new = kinetic(cfg.D, v(V_IMM), rs) + u;
+        const float e_cur = kin(v(V_R0)) + c.pe;
+        const float e_new = kin(rs) + u;
         const float delta = e_new - e_cur;
         const int new_dir = (d_log(0.8f) < -delta) ? 1 : -1;
         c.heur_last = c.heur_dir; c.heur_dir = new_dir;
@@ -280,8 +406,7 @@ struct Tick {
         float* r = v(V_R0);
         if ((c.pre_mask & 16u) && key_is(c.pt_from, key)) {          // looked ahead: same splits, same normals
             st(c.key_next, mk(c.pt_keynext)); k_tr = mk(c.pt_ktr);
-            const float* sm = v(V_SQRTM); const float* en = v(V_EPS);
-            B2_FOR_D(d, cfg.D) r[d] = sm[d] * en[d]; c.pre_hit[2] += 1u;
+            scale_normals(1, v(V_EPS), r); c.pre_hit[2] += 1u;
         } else { c.pre_miss[2] += 1u;
             const Key k_mom = split_at(key, 1);
             k_tr = split_at(key, 2);
@@ -289,7 +414,7 @@ struct Tick {
             draw_momentum(k_mom, r);
         }
         c.eps = c.step_size;
-        c.energy0 = c.pe + kinetic(cfg.D, v(V_IMM), r);
+        c.energy0 = c.pe + kin(r);
         if (cfg.algo == 1) { hmc_begin(k_tr); return; }
         // build_tree root (hmc_util.py:1129-1153)
         const float* z = v(V_Z); const float* g = v(V_G);
@@ -323,8 +448,8 @@ struct Tick {
         }
         c.n_sub = 0; c.sub_div = 0; c.sub_weight = 0.0f; c.sub_sum_acc = 0.0f;
         const float e = c.going_right ? c.eps : -c.eps;
-        if (c.going_right) leap_begin(cfg.D, e, v(V_IMM), v(V_ZR), v(V_RR), v(V_GR), v(V_ZS), v(V_RS));
-        else leap_begin(cfg.D, e, v(V_IMM), v(V_ZL), v(V_RL), v(V_GL), v(V_ZS), v(V_RS));
+        if (c.going_right) leap(e, v(V_ZR), v(V_RR), v(V_GR), v(V_ZS), v(V_RS));
+        else leap(e, v(V_ZL), v(V_RL), v(V_GL), v(V_ZS), v(V_RS));
         c.phase = PH_LEAF;
     }
 
@@ -454,7 +579,7 @@ struct Tick {
     // caller then falls back to "advance first, publish afterwards".
     __device__ __forceinline__ bool peek_next(float u, const float* g, float* zout) const {
         const int Dn = cfg.D;
-        if (cfg.algo != 0 || c.phase != PH_LEAF || Dn > 64) return false;
+        if (cfg.algo != 0 || c.phase != PH_LEAF || Dn > 64 || dense_on()) return false;
         const int lane = (int)(threadIdx.x & 31u);
         const int d0 = lane, d1 = lane + 32;
         const bool a0 = d0 < Dn, a1 = d1 < Dn;
@@ -589,7 +714,7 @@ struct Tick {
     // one iteration of _iterative_build_subtree's loop body, after the gradient arrived
     B2_HD void on_leaf(float u, const float* g) {
 #if defined(__CUDA_ARCH__)
-        if (cfg.D <= 64) { on_leaf_fused(u, g); return; }
+        if (cfg.D <= 64 && !dense_on()) { on_leaf_fused(u, g); return; }
 #endif
         const int Dn = cfg.D;
         const float e = c.going_right ? c.eps : -c.eps;
@@ -600,7 +725,7 @@ struct Tick {
         B2_FOR_D(d, Dn) { const float gg = g[d]; gs[d] = gg; rs[d] = rs[d] - half * gg; }
         c.total_leapfrogs += 1ull;
         // _build_basetree (hmc_util.py:866-875)
-        const float energy_new = u + kinetic(Dn, imm, rs);
+        const float energy_new = u + kin(rs);
         B2_LAPQ(0);
         float delta = energy_new - c.energy0;
         if (is_nan(delta)) delta = f_inf();
@@ -641,9 +766,20 @@ struct Tick {
             B2_FOR_D(d, Dn) { cr[d] = rs[d]; cs[d] = rsum_s[d]; }
         }
         bool sub_turning = false;
+        if (dense_on() && idx_max >= idx_min) matvec(dmat(0), rs, v(V_TMP1));          // M^-1 r of the new leaf, once
         for (int i = idx_max; i >= idx_min && !sub_turning; --i) {
             const float* cr = v(V_CKPT_R + i); const float* cs = v(V_CKPT_RSUM + i);
             float l, r;
+            if (dense_on()) {
+                const float *vl = v(V_TMP0), *vr = v(V_TMP1);
+                matvec(dmat(0), cr, v(V_TMP0));
+                lane_sum2(Dn, [&](int d, float& a, float& b) {
+                    const float sub = (rsum_s[d] - cs[d]) + cr[d];
+                    const float s = sub - (cr[d] + rs[d]) / 2.0f;
+                    a = vl[d] * s;
+                    b = vr[d] * s;
+                }, l, r);
+            } else
             lane_sum2(Dn, [&](int d, float& a, float& b) {
                 const float sub = (rsum_s[d] - cs[d]) + cr[d];
                 const float s = sub - (cr[d] + rs[d]) / 2.0f;
@@ -654,7 +790,7 @@ struct Tick {
         }
         B2_LAPQ(3);
         if (c.n_sub < (1 << c.depth) && !sub_turning && !c.sub_div) {      // next leaf of this subtree
-            leap_begin(Dn, e, imm, zs, rs, gs, zs, rs);
+            leap(e, zs, rs, gs, zs, rs);
             B2_LAPQ(4);
             return;
         }
@@ -670,7 +806,7 @@ struct Tick {
         float* rsum = v(V_RSUM);
         bool turning;
 #if defined(__CUDA_ARCH__)
-        if (Dn <= 64) {
+        if (Dn <= 64 && !dense_on()) {
             // two elements per lane, loads first; the tree-level U-turn test (is_turning) runs on the registers
             const int lane = (int)(threadIdx.x & 31u);
             const int d0 = lane, d1 = lane + 32;
@@ -708,7 +844,8 @@ struct Tick {
 #endif
         {
             B2_FOR_D(d, Dn) { zo[d] = zs[d]; ro[d] = rs[d]; go[d] = gs[d]; rsum[d] = rsum[d] + rsum_s[d]; }
-            turning = sub_turning || is_turning(Dn, v(V_IMM), v(V_RL), v(V_RR), rsum);
+            lane_sync();
+            turning = sub_turning || turning_between(v(V_RL), v(V_RR), rsum);
         }
         B2_LAPQ(11);
         float p = clip_max1(d_exp(c.sub_weight - c.weight));
@@ -740,7 +877,7 @@ struct Tick {
         }
         if (!(n >= 1)) n = 1;         // keeps the call graph acyclic; ceil(L / eps) >= 1 for finite eps
         c.hmc_n = n; c.hmc_left = n;
-        leap_begin(cfg.D, c.eps, v(V_IMM), v(V_Z), v(V_R0), v(V_G), v(V_ZS), v(V_RS));
+        leap(c.eps, v(V_Z), v(V_R0), v(V_G), v(V_ZS), v(V_RS));
         c.phase = PH_HMC;
     }
     B2_HD void on_hmc(float u, const float* g) {
@@ -749,12 +886,12 @@ struct Tick {
         B2_FOR_D(d, cfg.D) { const float gg = g[d]; gs[d] = gg; rs[d] = rs[d] - half * gg; }
         c.total_leapfrogs += 1ull;
         c.hmc_left -= 1;
-        if (c.hmc_left > 0) { leap_begin(cfg.D, c.eps, v(V_IMM), v(V_ZS), rs, gs, v(V_ZS), rs); return; }
+        if (c.hmc_left > 0) { leap(c.eps, v(V_ZS), rs, gs, v(V_ZS), rs); return; }
         hmc_finish(u);
     }
     B2_HD void hmc_finish(float u_new) {
         const float e_old = c.energy0;
-        const float e_new = u_new + kinetic(cfg.D, v(V_IMM), v(V_RS));
+        const float e_new = u_new + kin(v(V_RS));
         float delta = e_new - e_old;
         if (is_nan(delta)) delta = f_inf();
         const float acc = clip_max1(d_exp(-delta));
@@ -841,6 +978,20 @@ struct Tick {
             const float* z = v(V_Z); float* mean = v(V_WF_MEAN); float* m2 = v(V_WF_M2);
             c.mm_n += 1;
             const float nf = (float)c.mm_n;
+            if (dense_on()) {                                         // m2 + outer(delta_post, delta_pre)  (:193-194)
+                float *pre = v(V_TMP0), *post = v(V_TMP1), *M2 = dmat(2);
+                B2_FOR_D(d, Dn) {
+                    const float p0 = z[d] - mean[d];
+                    const float mu = mean[d] + p0 / nf;
+                    pre[d] = p0; post[d] = z[d] - mu; mean[d] = mu;
+                }
+                lane_sync();
+                B2_FOR_D(i, Dn) {
+                    const float pi = post[i];
+                    for (int j = 0; j < Dn; ++j) M2[(size_t)i * Dn + j] = M2[(size_t)i * Dn + j] + pi * pre[j];
+                }
+                lane_sync();
+            } else
             B2_FOR_D(d, Dn) {
                 const float pre = z[d] - mean[d];
                 const float mu = mean[d] + pre / nf;
@@ -859,6 +1010,19 @@ struct Tick {
             const float n5 = (float)(c.mm_n + 5);
             const float scale = nf / n5;
             const float shrink = 1e-3f * (5.0f / n5);
+            if (dense_on()) {
+                float *A = dmat(0), *M2 = dmat(2);
+                B2_FOR_D(i, Dn) {
+                    for (int j = 0; j < Dn; ++j) {
+                        const size_t o = (size_t)i * Dn + j;
+                        float cov = M2[o] / nm1;
+                        if (cfg.regularize) cov = scale * cov + shrink * ((i == j) ? 1.0f : 0.0f);
+                        A[o] = cov; M2[o] = 0.0f;
+                    }
+                    mean[i] = 0.0f;
+                }
+                dense_roots();
+            } else
             B2_FOR_D(d, Dn) {
                 float cov = m2[d] / nm1;
                 if (cfg.regularize) cov = scale * cov + shrink;
@@ -935,5 +1099,6 @@ struct Tick {
         }
     }
 };
+using Tick = TickT<true>;
 
 }  // namespace b2

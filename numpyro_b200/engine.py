@@ -212,6 +212,33 @@ class Engine:
                                                 int(num_warmup), self._stream()), "b200nuts_set_state")
         self.num_warmup = int(num_warmup)
 
+    # ------------------------------------------------------------------ mass matrix structure
+    @_on_device
+    def set_inverse_mass_matrix(self, imm):
+        """The kernel's ``inverse_mass_matrix=`` argument ([D] or [D, D], the same for every chain); before :meth:`init`."""
+        imm = np.ascontiguousarray(imm, np.float32)
+        if imm.ndim not in (1, 2) or any(n != self.D for n in imm.shape):
+            raise ValueError(f"inverse_mass_matrix must be [{self.D}] or [{self.D}, {self.D}]")
+        self._check(self.lib.b200nuts_set_inverse_mass_matrix(self.h, imm.ctypes.data_as(C.c_void_p), imm.ndim, self._stream()),
+                    "b200nuts_set_inverse_mass_matrix")
+
+    @_on_device
+    def dense_state(self) -> Dict[str, np.ndarray]:
+        """dense_mass handles: HMCAdaptState's matrices, [C, D, D] each (b200nuts_get_dense_state)."""
+        names = ("inverse_mass_matrix", "mass_matrix_sqrt", "mass_matrix_sqrt_inv", "wf_m2")
+        out = {n: np.zeros((self.C, self.D, self.D), np.float32) for n in names}
+        self._check(self.lib.b200nuts_get_dense_state(self.h, *[out[n].ctypes.data_as(C.c_void_p) for n in names], self._stream()),
+                    "b200nuts_get_dense_state")
+        return out
+
+    @_on_device
+    def set_dense_state(self, inverse_mass_matrix, wf_m2=None):
+        imm = np.ascontiguousarray(inverse_mass_matrix, np.float32).reshape(self.C, self.D, self.D)
+        m2 = None if wf_m2 is None else np.ascontiguousarray(wf_m2, np.float32).reshape(self.C, self.D, self.D)
+        self._check(self.lib.b200nuts_set_dense_state(self.h, imm.ctypes.data_as(C.c_void_p),
+                                                      None if m2 is None else m2.ctypes.data_as(C.c_void_p), self._stream()),
+                    "b200nuts_set_dense_state")
+
     # ------------------------------------------------------------------ parity hooks
     @_on_device
     def potential_and_grad(self, z):

@@ -66,8 +66,9 @@ def init_to_value(values=None):
 
 
 # ---------------------------------------------------------------------- HMCState <-> engine
-def _state_from_engine(sts, vecs, bound, squeeze_one, trajectory_length):
-    """HMCState (hmc.py:31-48) of the chains behind one or more engine handles, field for field."""
+def _state_from_engine(sts, vecs, bound, squeeze_one, trajectory_length, dense=None):
+    """HMCState (hmc.py:31-48) of the chains behind one or more engine handles, field for field.  ``dense``: the handles'
+    :meth:`Engine.dense_state` dicts when the kernel uses ``dense_mass=True`` (matrices [C, D, D] instead of vectors)."""
     cat = lambda name: np.concatenate([v[name] for v in vecs], axis=0)
     st = [s[k] for s in sts for k in range(len(s))]
     arr = lambda f, dt: np.array([getattr(s, f) for s in st], dt)
@@ -75,13 +76,18 @@ def _state_from_engine(sts, vecs, bound, squeeze_one, trajectory_length):
                         for s in bound.latent_sites}
     squeeze = (lambda a: a[0]) if squeeze_one else (lambda a: a)
     tree = lambda d: {k: squeeze(v) for k, v in d.items()}
-    imm, msq = cat("inverse_mass_matrix"), cat("mass_matrix_sqrt")
     key = tuple(sorted(s.name for s in bound.latent_sites))        # one-block structured mass matrix (hmc.py:759-769)
+    if dense is not None:
+        dcat = lambda name: np.concatenate([d[name] for d in dense], axis=0)
+        imm, msq, msq_inv, m2 = (dcat(n) for n in ("inverse_mass_matrix", "mass_matrix_sqrt", "mass_matrix_sqrt_inv", "wf_m2"))
+    else:
+        imm, msq, m2 = cat("inverse_mass_matrix"), cat("mass_matrix_sqrt"), cat("wf_m2")
+        msq_inv = 1.0 / msq
     adapt = HMCAdaptState(
-        squeeze(arr("step_size", np.float32)), {key: squeeze(imm)}, {key: squeeze(msq)}, {key: squeeze(1.0 / msq)},
+        squeeze(arr("step_size", np.float32)), {key: squeeze(imm)}, {key: squeeze(msq)}, {key: squeeze(msq_inv)},
         (squeeze(arr("ss_x_t", np.float32)), squeeze(arr("ss_x_avg", np.float32)), squeeze(arr("ss_g_avg", np.float32)),
          squeeze(arr("ss_t", np.int32)), squeeze(arr("ss_prox", np.float32))),
-        {key: (squeeze(cat("wf_mean")), squeeze(cat("wf_m2")), squeeze(arr("mm_n", np.int32)))},
+        {key: (squeeze(cat("wf_mean")), squeeze(m2), squeeze(arr("mm_n", np.int32)))},
         squeeze(arr("window_idx", np.int32)),
         squeeze(np.array([[s.adapt_rng_key[0], s.adapt_rng_key[1]] for s in st], np.uint32)))
     return HMCState(squeeze(arr("i", np.int32)), tree(unflat(cat("z"))), tree(unflat(cat("z_grad"))),
@@ -108,6 +114,11 @@ def _state_to_engine(state: HMCState, bound, engine: Engine, n_total: int, lo: i
     one = lambda d: np.asarray(next(iter(d.values())) if isinstance(d, dict) else d, np.float32).reshape(C, -1)
     imm = one(a.inverse_mass_matrix)
     mm = next(iter(a.mm_state.values())) if isinstance(a.mm_state, dict) else a.mm_state
+    dense = imm.shape[1] == D * D and D > 1
+    imm_full, m2_full = imm, np.asarray(mm[1], np.float32).reshape(C, -1)
+    if dense:                       # the vector slots of the C ABI carry the diagonals; the matrices follow below
+        imm = imm_full.reshape(C, D, D)[:, np.arange(D), np.arange(D)]
+        mm = (mm[0], m2_full.reshape(C, D, D)[:, np.arange(D), np.arange(D)], mm[2])
     sc = lambda v, dt: np.asarray(v, dt).reshape(C)
     rk = np.asarray(state.rng_key if keys is None else keys, np.uint32).reshape(C, 2)
     akeys = np.asarray(a.rng_key, np.uint32).reshape(C, 2)
@@ -128,6 +139,8 @@ def _state_to_engine(state: HMCState, bound, engine: Engine, n_total: int, lo: i
            "wf_mean": np.asarray(mm[0], np.float32).reshape(C, -1)[lo:hi],
            "wf_m2": np.asarray(mm[1], np.float32).reshape(C, -1)[lo:hi]}
     engine.set_state(st, vec, num_warmup)
+    if dense:
+        engine.set_dense_state(imm_full.reshape(C, D, D)[lo:hi], m2_full.reshape(C, D, D)[lo:hi])
 
 
 def _flatten_init(init_params, bound, D):
@@ -157,8 +170,15 @@ class HMC(_KernelBase):
                                       "arbitrary potential_fn / kinetic_fn callables are not supported")
         if not isinstance(model, families.Model):
             raise TypeError("model must be a numpyro_b200.families.Model (a declared model family)")
-        if dense_mass or inverse_mass_matrix is not None:
-            raise NotImplementedError("dense / user-supplied mass matrices are not implemented yet (SURVEY.md 8(f) rank 1)")
+        if not isinstance(dense_mass, (bool, np.bool_)):
+            raise NotImplementedError("block-structured mass matrices (dense_mass as a list of site tuples) are not implemented; "
+                                      "dense_mass=True / False and inverse_mass_matrix= (vector or matrix) are")
+        if isinstance(inverse_mass_matrix, dict):
+            if len(inverse_mass_matrix) != 1:
+                raise NotImplementedError("inverse_mass_matrix: only one block over all latent sites is implemented")
+            inverse_mass_matrix = next(iter(inverse_mass_matrix.values()))
+        self._dense_mass = bool(dense_mass)
+        self._inverse_mass_matrix = None if inverse_mass_matrix is None else np.asarray(inverse_mass_matrix, np.float32)
         if forward_mode_differentiation:
             raise NotImplementedError("gradients are hand-derived; forward_mode_differentiation does not apply")
         if init_strategy is None:
@@ -174,7 +194,7 @@ class HMC(_KernelBase):
                          max_tree_depth_warmup=int(depth[0]), max_tree_depth=int(depth[1]),
                          hmc_num_steps=int(num_steps or 0),
                          trajectory_length=float(trajectory_length if num_steps is None else 0.0) or 2 * np.pi,
-                         regime={"auto": 0, "warp": 1, "stream": 2, "gemm": 3}[regime])
+                         regime={"auto": 0, "warp": 1, "stream": 2, "gemm": 3}[regime], dense_mass=int(self._dense_mass))
         if init_strategy.kind == "uniform":
             self._cfg["init_radius"] = init_strategy.radius
         self._trajectory_length = None if num_steps is not None else trajectory_length
@@ -249,12 +269,19 @@ class HMC(_KernelBase):
         cfg["num_chains"] = keys.shape[0]
         e = Engine(device=torch.device("cuda", torch.cuda.current_device()), X=bound.X, y=bound.y, aux=bound.aux, **cfg)
         z0 = _flatten_init(init_params, bound, e.D) if init_params is not None else self._strategy_z0(bound, e.D, keys.shape[0])
+        if self._inverse_mass_matrix is not None:
+            e.set_inverse_mass_matrix(self._inverse_mass_matrix)
         e.init(keys, int(num_warmup), z0)
         e.run(0, 0, fields=())                      # evaluates the potential at the start (retrying invalid draws): HMCState.i == 0
         self._engine, self._bound, self._num_warmup = e, bound, int(num_warmup)
-        st, vec = e.state()
-        self._engine_state = _state_from_engine([st], [vec], bound, self._single, self._trajectory_length)
+        self._engine_state = self._read_state()
         return self._engine_state
+
+    def _read_state(self):
+        e = self._engine
+        st, vec = e.state()
+        return _state_from_engine([st], [vec], self._bound, self._single, self._trajectory_length,
+                                  dense=[e.dense_state()] if self._dense_mass else None)
 
     def sample(self, state, model_args=(), model_kwargs=None):
         """``MCMCKernel.sample`` (mcmc.py:110-124; hmc.py:801-816): one transition from ``state``."""
@@ -264,8 +291,7 @@ class HMC(_KernelBase):
         if state is not self._engine_state:          # a state the engine does not hold (e.g. HMCGibbs edited z): load it
             _state_to_engine(state, self._bound, e, e.C, 0, e.C, self._num_warmup)
         e.transition(1)
-        st, vec = e.state()
-        self._engine_state = _state_from_engine([st], [vec], self._bound, self._single, self._trajectory_length)
+        self._engine_state = self._read_state()
         return self._engine_state
 
     def postprocess_fn(self, model_args=(), model_kwargs=None):
@@ -486,6 +512,8 @@ class MCMC:
             e = s.engine
             with torch.cuda.device(s.device), torch.cuda.stream(getattr(s, "stream", None)):
                 if fresh:
+                    if self.sampler._inverse_mass_matrix is not None:
+                        e.set_inverse_mass_matrix(self.sampler._inverse_mass_matrix)
                     e.init(keys[s.lo:s.hi], self.num_warmup, None if z0 is None else z0[s.lo:s.hi])
                 else:
                     _state_to_engine(resume, bound, e, n_local, s.lo - lo0, s.hi - lo0, self.num_warmup,
@@ -495,14 +523,14 @@ class MCMC:
                 st, vec = e.state()                                  # raises "Cannot find valid initial parameters" (EINIT)
                 host = {k: v.cpu().numpy() for k, v in out.items()}
                 host["_constrained"] = con.cpu().numpy()
-                return host, st, vec
+                return host, st, vec, (e.dense_state() if self.sampler._dense_mass else None)
 
         results = self._for_each_shard(work)
         t_work = _time.perf_counter()
         if self.row_shards > 1:
             results = results[:1]              # every rank holds the same (bit-identical) chains
         #: gradient evaluations (leapfrogs) spent so far by every local chain, warm-up included
-        self.total_grad_evals = int(sum(int(st[k].total_leapfrogs) for _, st, _ in results for k in range(len(st))))
+        self.total_grad_evals = int(sum(int(r[1][k].total_leapfrogs) for r in results for k in range(len(r[1]))))
         host = {k: np.concatenate([r[0][k] for r in results], axis=0) for k in results[0][0]}
         if self._dist:
             host = self._all_gather(host)
@@ -525,7 +553,8 @@ class MCMC:
         self._states = states
         self._states_flat = None
         self._last_state = _state_from_engine([r[1] for r in results], [r[2] for r in results], bound,
-                                              self.num_chains == 1 and not self._dist, self.sampler._trajectory_length)
+                                              self.num_chains == 1 and not self._dist, self.sampler._trajectory_length,
+                                              dense=[r[3] for r in results] if self.sampler._dense_mass else None)
         #: wall-clock split of this call (ms): H2D of the data + engine creation (tile images), chain init + sampling +
         #: constrain + D2H of the samples, host-side assembly of the result dicts
         self.timings = {"h2d_and_engine_create": 1e3 * (t_engines - t_begin), "init_sample_d2h": 1e3 * (t_work - t_engines),

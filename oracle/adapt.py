@@ -1,7 +1,7 @@
 """Oracle: warm-up adaptation (TEST INFRASTRUCTURE ONLY).
 
 NumPy/det-f32 restatement of numpyro/infer/hmc_util.py: dual_averaging :60-130,
-welford_covariance :133-239 (diagonal branch), find_reasonable_step_size :314-384,
+welford_covariance :133-239 (diagonal and dense), find_reasonable_step_size :314-384,
 build_adaptation_schedule :387-436, warmup_adapter :518-707.
 """
 from __future__ import annotations
@@ -13,7 +13,7 @@ import numpy as np
 
 from . import detmath as dm
 from . import prng
-from .tree import kinetic_energy, leapfrog
+from .tree import imm_apply, kinetic_energy, leapfrog
 
 F = np.float32
 TINY = np.finfo(np.float32).tiny
@@ -78,8 +78,8 @@ class WelfordState:
     n: int
 
 
-def welford_init(d: int) -> WelfordState:
-    return WelfordState(np.zeros(d, F), np.zeros(d, F), 0)
+def welford_init(d: int, dense: bool = False) -> WelfordState:
+    return WelfordState(np.zeros(d, F), np.zeros((d, d) if dense else d, F), 0)
 
 
 def welford_update(z, s: WelfordState) -> WelfordState:
@@ -87,8 +87,54 @@ def welford_update(z, s: WelfordState) -> WelfordState:
     delta_pre = (z - s.mean).astype(F)
     mean = (s.mean + (delta_pre / F(n)).astype(F)).astype(F)
     delta_post = (z - mean).astype(F)
-    m2 = (s.m2 + (delta_pre * delta_post).astype(F)).astype(F)
+    if s.m2.ndim == 1:
+        m2 = (s.m2 + (delta_pre * delta_post).astype(F)).astype(F)
+    else:                                                          # :193-194  m2 + outer(delta_post, delta_pre)
+        m2 = (s.m2 + np.outer(delta_post, delta_pre).astype(F)).astype(F)
     return WelfordState(mean, m2, n)
+
+
+def cholesky_lower(a) -> np.ndarray:
+    """``jnp.linalg.cholesky(a)`` (lower factor; jax symmetrises its input by default: (a + a^T) / 2) in det-f32: element
+    (i, j), j <= i:  s = a_sym[i, j] - sum_{k < j} L[i, k] * L[j, k]  (k ascending, one rounding per operation), then
+    sqrt(s) on the diagonal, s / L[j, j] below it.  A non-positive pivot gives NaN, as LAPACK / XLA do."""
+    a = np.asarray(a, F)
+    d = a.shape[0]
+    with np.errstate(all="ignore"):
+        sym = ((a + a.T).astype(F) / F(2.0)).astype(F)
+        L = np.zeros((d, d), F)
+        for j in range(d):
+            s = sym[j:, j].copy()
+            for k in range(j):
+                s = (s - (L[j:, k] * L[j, k]).astype(F)).astype(F)
+            piv = np.sqrt(s[0]).astype(F) if s[0] > 0 else F(np.nan)
+            L[j, j] = piv
+            L[j + 1:, j] = (s[1:] / piv).astype(F)
+    return L
+
+
+def solve_lower_identity(t) -> np.ndarray:
+    """``solve_triangular(t, identity, lower=True)`` = t^-1 by forward substitution, column by column:
+    x_i = (e_i - sum_{k < i} t[i, k] x_k) / t[i, i], k ascending, one rounding per operation."""
+    t = np.asarray(t, F)
+    d = t.shape[0]
+    x = np.zeros((d, d), F)
+    with np.errstate(all="ignore"):
+        for i in range(d):
+            s = np.zeros(d, F)
+            s[i] = F(1.0)
+            for k in range(i):
+                s = (s - (t[i, k] * x[k, :]).astype(F)).astype(F)
+            x[i, :] = (s / t[i, i]).astype(F)
+    return x
+
+
+def mass_matrix_roots(imm):
+    """hmc_util.py:228-233 / :499-509: (mass_matrix_sqrt, mass_matrix_sqrt_inv) of a dense inverse mass matrix:
+    tril_inv = swapaxes(cholesky(imm[::-1, ::-1])[::-1, ::-1]);  sqrt = solve_triangular(tril_inv, I, lower=True)."""
+    lc = cholesky_lower(np.asarray(imm, F)[::-1, ::-1])
+    tril_inv = np.ascontiguousarray(lc[::-1, ::-1].T)
+    return solve_lower_identity(tril_inv), tril_inv
 
 
 def welford_final(s: WelfordState, regularize: bool):
@@ -98,7 +144,13 @@ def welford_final(s: WelfordState, regularize: bool):
         if regularize:
             scaled = (F(F(s.n) / F(s.n + 5)) * cov).astype(F)
             shrink = F(F(1e-3) * F(F(5.0) / F(s.n + 5)))
-            cov = (scaled + shrink).astype(F)
+            if cov.ndim == 1:
+                cov = (scaled + shrink).astype(F)
+            else:                                   # :222  scaled_cov + shrinkage * identity
+                cov = (scaled + (shrink * np.identity(cov.shape[0], dtype=F)).astype(F)).astype(F)
+        if cov.ndim == 2:
+            sqrt_m, sqrt_inv = mass_matrix_roots(cov)
+            return cov, sqrt_m, sqrt_inv
         sqrt_inv = np.sqrt(cov).astype(F)          # mass_matrix_sqrt_inv  (tril_inv)
         sqrt_m = (F(1.0) / sqrt_inv).astype(F)     # mass_matrix_sqrt      (cov_inv_sqrt)
     return cov, sqrt_m, sqrt_inv
@@ -123,7 +175,7 @@ def find_reasonable_step_size(potential: Callable, imm, sqrt_m, z, pe, g, init_s
             step = F(F(2.0) ** direction * step)
             # NB: the reference passes inverse_mass_matrix as momentum_generator's mass_matrix_sqrt
             # argument here (hmc_util.py:355), so r = M^-1 * eps.
-            r = (imm * prng.normal(momentum_key_fn(k_mom), d)).astype(F)
+            r = imm_apply(imm, prng.normal(momentum_key_fn(k_mom), d))
             _, r_new, pe_new, _ = leapfrog(potential, step, imm, z, r, g)
             e_cur = F(kinetic_energy(imm, r) + pe)
             e_new = F(kinetic_energy(imm, r_new) + pe_new)
@@ -155,6 +207,7 @@ class WarmupAdapter:
     adapt_mass_matrix: bool = True
     target_accept_prob: float = 0.8
     regularize_mass_matrix: bool = True
+    dense_mass: bool = False
 
     def __post_init__(self):
         self.schedule = build_adaptation_schedule(self.num_adapt_steps)
@@ -163,11 +216,18 @@ class WarmupAdapter:
     def init(self, z, pe, g, key, step_size=1.0, inverse_mass_matrix=None) -> AdaptState:
         key, k_ss = prng.split(key)
         d = z.shape[0]
-        if inverse_mass_matrix is None:
-            imm = np.ones(d, F)
+        if inverse_mass_matrix is None:                       # _initialize_mass_matrix :487-493
+            imm = np.identity(d, dtype=F) if self.dense_mass else np.ones(d, F)
             sqrt_m = sqrt_inv = imm
+        elif self.dense_mass:                                 # :495-509
+            imm = np.asarray(inverse_mass_matrix, F)
+            if imm.ndim == 1:
+                imm = np.diag(imm).astype(F)
+            sqrt_m, sqrt_inv = mass_matrix_roots(imm)
         else:
             imm = np.asarray(inverse_mass_matrix, F)
+            if imm.ndim == 2:
+                imm = np.ascontiguousarray(np.diag(imm))
             sqrt_inv = np.sqrt(imm).astype(F)
             sqrt_m = (F(1.0) / sqrt_inv).astype(F)
         step = F(step_size)
@@ -175,7 +235,7 @@ class WarmupAdapter:
             step = self.find_step(step, imm, sqrt_m, z, pe, g, k_ss)
         with np.errstate(all="ignore"):
             ss = da_init(dm.log(F(F(10.0) * step)))
-        return AdaptState(step, imm, sqrt_m, sqrt_inv, ss, welford_init(d), 0, key)
+        return AdaptState(step, imm, sqrt_m, sqrt_inv, ss, welford_init(d, self.dense_mass), 0, key)
 
     def update(self, t: int, accept_prob, z, pe, g, s: AdaptState) -> AdaptState:
         key, k_ss = prng.split(s.rng_key)
@@ -200,7 +260,7 @@ class WarmupAdapter:
             imm, sqrt_m, sqrt_inv = out.inverse_mass_matrix, out.mass_matrix_sqrt, out.mass_matrix_sqrt_inv
             if self.adapt_mass_matrix:
                 imm, sqrt_m, sqrt_inv = welford_final(mm, self.regularize_mass_matrix)
-                mm = welford_init(z.shape[0])
+                mm = welford_init(z.shape[0], self.dense_mass)
             if self.adapt_step_size:
                 if self.find_step is not None:
                     step = self.find_step(step, imm, sqrt_m, z, pe, g, k_ss)

@@ -16,7 +16,7 @@ import numpy as np
 from . import adapt as ad
 from . import detmath as dm
 from . import prng
-from .tree import TreeTrace, build_tree, kinetic_energy, leapfrog, MAX_DELTA_ENERGY
+from .tree import TreeTrace, build_tree, imm_apply, kinetic_energy, leapfrog, MAX_DELTA_ENERGY
 
 F = np.float32
 
@@ -75,13 +75,14 @@ class Kernel:
     regularize_mass_matrix: bool = True
     num_steps: Optional[int] = None           # HMC only
     trajectory_length: float = 2 * np.pi      # HMC only
+    dense_mass: bool = False                  # hmc.py:759-769 with dense_mass=True: one dense block over all sites
 
     def momentum(self, sqrt_m, key):
-        """momentum_generator (hmc.py:92-110)."""
+        """momentum_generator (hmc.py:92-110): multiply (diagonal) or dot (dense) with the unit normals."""
         if self.model_built:
             key = prng.split(key, 1)[0]
         eps = prng.normal(key, sqrt_m.shape[0])
-        return (sqrt_m * eps).astype(F)
+        return imm_apply(sqrt_m, eps)
 
     def init(self, key, num_warmup: int, z, pe, g, inverse_mass_matrix=None) -> HMCState:
         """init_kernel (hmc.py:193-362)."""
@@ -93,7 +94,7 @@ class Kernel:
                 self.potential, imm, sm, z_, pe_, g_, step, k, mk)
         self.adapter = ad.WarmupAdapter(num_warmup, find, self.adapt_step_size,
                                         self.adapt_mass_matrix, self.target_accept_prob,
-                                        self.regularize_mass_matrix)
+                                        self.regularize_mass_matrix, self.dense_mass)
         k_hmc, k_wa, k_mom = prng.split(key, 3)
         wa = self.adapter.init(z, pe, g, k_wa, self.step_size, inverse_mass_matrix)
         r = self.momentum(wa.mass_matrix_sqrt, k_mom)
@@ -162,7 +163,7 @@ def run_chain(kernel: Kernel, family, chain_key, num_warmup: int, num_samples: i
               thinning: int = 1, init_z=None, collect_warmup=False,
               fields: Sequence[str] = ("z", "diverging", "num_steps", "accept_prob",
                                        "potential_energy", "energy", "step_size"),
-              traces: Optional[List[TreeTrace]] = None):
+              traces: Optional[List[TreeTrace]] = None, inverse_mass_matrix=None):
     """One chain of ``MCMC.run`` (mcmc.py:466-521) = HMC.init + fori_collect.
 
     Returns (dict of per-sample arrays, last HMCState).  Collection follows util.py:368-403:
@@ -177,7 +178,7 @@ def run_chain(kernel: Kernel, family, chain_key, num_warmup: int, num_samples: i
     else:
         z = np.asarray(init_z, F)
         pe, g = pot(z)
-    state = kernel.init(rng_key, num_warmup, z, pe, g)
+    state = kernel.init(rng_key, num_warmup, z, pe, g, inverse_mass_matrix)
     upper = num_warmup + num_samples
     lower = 0 if collect_warmup else num_warmup
     size = (upper - lower) // thinning

@@ -5,7 +5,7 @@ NumPy/det-f32 restatement of numpyro/infer/hmc_util.py:
   :710-746, transition kernels :749-764, _combine_tree :767-848, _build_basetree :851-894,
   _double_tree :907-938, _leaf_idx_to_ckpt_idxs :941-958, _is_iterative_turning :961-981,
   _iterative_build_subtree :984-1085, build_tree :1088-1180.
-One chain at a time, diagonal mass matrix, flat float32 vectors.  ``potential`` is any callable
+One chain at a time, flat float32 vectors; the inverse mass matrix is a vector (diagonal) or a [D, D] array (dense_mass=True).  ``potential`` is any callable
 ``z -> (U, grad)``; in tests it is either an oracle family (fp64 rounded once) or the CUDA engine's
 own potential hook (so the tree bookkeeping can be compared bit for bit).
 """
@@ -23,9 +23,23 @@ F = np.float32
 MAX_DELTA_ENERGY = F(1000.0)        # hmc.py:188
 
 
+def imm_apply(imm, r) -> np.ndarray:
+    """``M^-1 r``: ``jnp.multiply`` for a diagonal, ``jnp.matmul`` for a dense inverse mass matrix (hmc_util.py:1193-1196,
+    :726-731).  det-f32 order of the dense product: every row accumulates its terms left to right from +0, one rounding
+    per multiplication and per addition (the engine gives row i to lane i mod 32)."""
+    imm = np.asarray(imm, F)
+    if imm.ndim == 1:
+        return (imm * r).astype(F)
+    acc = np.zeros(imm.shape[0], F)
+    with np.errstate(all="ignore"):
+        for j in range(imm.shape[1]):
+            acc = (acc + (imm[:, j] * r[j]).astype(F)).astype(F)
+    return acc
+
+
 def kinetic_energy(imm, r) -> np.float32:
-    """0.5 * dot(M^-1 r, r)  (hmc_util.py:1183-1200, diagonal branch)."""
-    v = (imm * r).astype(F)
+    """0.5 * dot(M^-1 r, r)  (hmc_util.py:1183-1200)."""
+    v = imm_apply(imm, r)
     return F(F(0.5) * dm.lane_dot(v, r))
 
 
@@ -34,7 +48,7 @@ def leapfrog(potential, eps, imm, z, r, g):
     eps = F(eps)
     half = F(F(0.5) * eps)
     r_half = (r - (half * g).astype(F)).astype(F)
-    z_new = (z + (eps * (imm * r_half).astype(F)).astype(F)).astype(F)
+    z_new = (z + (eps * imm_apply(imm, r_half)).astype(F)).astype(F)
     u_new, g_new = potential(z_new)
     r_new = (r_half - (half * g_new).astype(F)).astype(F)
     return z_new, r_new, F(u_new), np.asarray(g_new, F)
@@ -42,8 +56,8 @@ def leapfrog(potential, eps, imm, z, r, g):
 
 def is_turning(imm, r_left, r_right, r_sum) -> bool:
     """hmc_util.py:710-746."""
-    v_left = (imm * r_left).astype(F)
-    v_right = (imm * r_right).astype(F)
+    v_left = imm_apply(imm, r_left)
+    v_right = imm_apply(imm, r_right)
     mid = ((r_left + r_right).astype(F) / F(2.0)).astype(F)
     s = (r_sum - mid).astype(F)
     return bool(dm.lane_dot(v_left, s) <= 0) or bool(dm.lane_dot(v_right, s) <= 0)

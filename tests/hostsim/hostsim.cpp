@@ -16,9 +16,13 @@ typedef void (*potential_cb)(void* user, int chain, const float* z, int D, float
 struct HostSim {
     B200NutsConfig cfg; FamilySpec fam; SiteLayout sites; TickCfg tick;
     int C, D;
-    std::vector<ChainCtl> ctl; std::vector<float> vecs, gtmp, scratch, ylgam;
-    std::string err; bool inited = false; bool lookahead = false;
-    ChainVecs cv(int chain) { ChainVecs v; v.base = vecs.data() + (size_t)chain * D; v.field_stride = C * D; return v; }
+    std::vector<ChainCtl> ctl; std::vector<float> vecs, gtmp, scratch, ylgam, dense;
+    std::string err; bool inited = false; bool lookahead = false; bool imm_given = false;
+    ChainVecs cv(int chain) {
+        ChainVecs v; v.base = vecs.data() + (size_t)chain * D; v.field_stride = C * D;
+        v.dense = dense.empty() ? nullptr : dense.data() + (size_t)chain * 4 * D * D;
+        return v;
+    }
 };
 
 extern "C" {
@@ -32,6 +36,7 @@ int hostsim_create(const B200NutsConfig* cfg, HostSim** out) {
     h->ctl.assign(h->C, ChainCtl());
     h->vecs.assign((size_t)V_COUNT * h->C * h->D, 0.0f);
     h->gtmp.assign((size_t)h->C * h->D, 0.0f);
+    if (cfg->dense_mass) h->dense.assign((size_t)h->C * 4 * h->D * h->D, 0.0f);
     if (h->fam.family == FAM_GLM) {
         h->scratch.assign((size_t)(h->fam.N + h->fam.Dx), 0.0f);
         if (h->fam.likelihood == LIK_POISSON) {
@@ -59,6 +64,7 @@ static void eval(HostSim* h, int chain, potential_cb cb, void* user, float& u) {
 int hostsim_init(HostSim* h, const uint32_t* keys, const float* z0, int num_warmup) {
     std::string e = make_tick_cfg(h->cfg, h->fam, h->sites, num_warmup, z0 != nullptr, h->tick);
     if (!e.empty()) { fprintf(stderr, "hostsim: %s\n", e.c_str()); return B200NUTS_EINVAL; }
+    h->tick.imm_given = h->imm_given ? 1 : 0;
     OutBufs none; memset(&none, 0, sizeof(none));
     for (int c = 0; c < h->C; ++c) {
         memset(&h->ctl[c], 0, sizeof(ChainCtl));
@@ -101,6 +107,39 @@ int hostsim_get_state(HostSim* h, B200NutsChainState* st, float* z, float* g, fl
             if (imm) imm[(size_t)c * h->D + d] = v.v(V_IMM)[d];
             if (sqrtm) sqrtm[(size_t)c * h->D + d] = v.v(V_SQRTM)[d];
         }
+    }
+    return 0;
+}
+
+// the kernel's inverse_mass_matrix= argument: [D] or [D][D], the same for every chain (call before hostsim_init)
+int hostsim_set_inverse_mass_matrix(HostSim* h, const float* imm, int ndim) {
+    const int D = h->D;
+    for (int c = 0; c < h->C; ++c) {
+        ChainVecs v = h->cv(c);
+        if (h->cfg.dense_mass) {
+            float* A = v.dense;
+            for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j)
+                A[(size_t)i * D + j] = ndim == 2 ? imm[(size_t)i * D + j] : (i == j ? imm[i] : 0.0f);
+        } else {
+            for (int d = 0; d < D; ++d) v.v(V_IMM)[d] = ndim == 2 ? imm[(size_t)d * D + d] : imm[d];
+        }
+    }
+    h->imm_given = true;
+    return 0;
+}
+// dense handles: [C][D][D] each (NULL = skip)
+int hostsim_get_dense_state(HostSim* h, float* imm, float* sqrtm, float* sqrt_inv, float* m2) {
+    if (h->dense.empty()) return B200NUTS_ESTATE;
+    const int D = h->D; const size_t DD = (size_t)D * D;
+    for (int c = 0; c < h->C; ++c) {
+        const float* blk = h->dense.data() + (size_t)c * 4 * DD;
+        for (size_t o = 0; o < DD; ++o) {
+            if (imm) imm[c * DD + o] = blk[o];
+            if (sqrtm) sqrtm[c * DD + o] = blk[DD + o];
+            if (m2) m2[c * DD + o] = blk[2 * DD + o];
+        }
+        if (sqrt_inv) for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j)
+            sqrt_inv[c * DD + (size_t)i * D + j] = blk[3 * DD + (size_t)(D - 1 - j) * D + (D - 1 - i)];     // tril_inv[i][j] = Lc[D-1-j][D-1-i]
     }
     return 0;
 }

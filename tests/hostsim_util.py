@@ -38,6 +38,8 @@ def lib():
         _lib.hostsim_run.argtypes = [C.c_void_p, C.POINTER(_capi.Run), CB, C.c_void_p]
         _lib.hostsim_get_state.argtypes = [C.c_void_p] * 6
         _lib.hostsim_potential.argtypes = [C.c_void_p] * 4
+        _lib.hostsim_set_inverse_mass_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        _lib.hostsim_get_dense_state.argtypes = [C.c_void_p] * 5
         _lib.hostsim_prng_split.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _lib.hostsim_prng_uniform.argtypes = [C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_void_p]
         _lib.hostsim_prng_normal.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p]
@@ -105,6 +107,15 @@ class HostSim:
         z, g, imm, sm = (np.zeros((self.C, self.D), np.float32) for _ in range(4))
         lib().hostsim_get_state(self.h, C.cast(st, C.c_void_p), _p(z), _p(g), _p(imm), _p(sm))
         return st, z, g, imm, sm
+
+    def set_inverse_mass_matrix(self, imm):
+        imm = np.ascontiguousarray(imm, np.float32)
+        assert lib().hostsim_set_inverse_mass_matrix(self.h, _p(imm), imm.ndim) == 0
+
+    def dense_state(self):
+        a = [np.zeros((self.C, self.D, self.D), np.float32) for _ in range(4)]
+        assert lib().hostsim_get_dense_state(self.h, *[_p(x) for x in a]) == 0
+        return dict(zip(("inverse_mass_matrix", "mass_matrix_sqrt", "mass_matrix_sqrt_inv", "wf_m2"), a))
 
     def potential(self, z):
         z = np.ascontiguousarray(z, np.float32).reshape(self.C, self.D)
