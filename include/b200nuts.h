@@ -88,6 +88,9 @@ typedef struct B200NutsConfig {
     int64_t n_rows_global;     /* row-sharded handles: rows of the whole dataset (0 => n_rows) */
     /* --- mass matrix structure (hmc.py:916-951 dense_mass; hmc_util.py:439-515) --- */
     int32_t dense_mass;        /* 1: one dense [D, D] inverse mass matrix over all latent sites (dense_mass=True); 0: diagonal */
+    /* --- energy-conserving subsampling, the inner potential of HMCECS (hmc_gibbs.py:502-690); plain GLM, warp regime --- */
+    int32_t ecs_subsample_size;  /* m > 0: the likelihood is estimated from m of the n_rows rows (b200nuts_ecs_set_indices) */
+    int32_t ecs_proxy_degree;    /* Taylor proxy degree 1 / 2 (b200nuts_ecs_set_proxy), 0 = no proxy (plate-scaled estimate) */
     int32_t reserved0;
 } B200NutsConfig;
 
@@ -196,6 +199,14 @@ int b200nuts_set_inverse_mass_matrix(B200Nuts* h, const float* imm, int32_t ndim
 int b200nuts_get_dense_state(B200Nuts* h, float* inverse_mass_matrix, float* mass_matrix_sqrt, float* mass_matrix_sqrt_inv,
                              float* wf_m2, void* stream);
 int b200nuts_set_dense_state(B200Nuts* h, const float* inverse_mass_matrix, const float* wf_m2, void* stream);
+
+/* HMCECS inner potential (numpyro/infer/hmc_gibbs.py:577-682, contrib/ecs_proxies.py:23-300).
+ * set_proxy: the Taylor proxy's reference point and the full-data terms at it -- device fp32: ref [n_cols], eta_ref [n_rows]
+ * (= X ref), G [n_cols] and H [n_cols][n_cols] (gradient / Hessian of the full-data log-likelihood at ref; H may be NULL for
+ * degree 1), L0 = the full-data log-likelihood at ref; the pointers are borrowed.  set_indices: the current subsample of every
+ * chain, host int32 [num_chains][m] (the Gibbs site of HMCECS); every later potential / transition uses it. */
+int b200nuts_ecs_set_proxy(B200Nuts* h, const float* ref, const float* eta_ref, const float* G, const float* H, float L0);
+int b200nuts_ecs_set_indices(B200Nuts* h, const int32_t* idx, void* stream);
 
 /* PRNG parity hooks: host in / host out, computed on the device, synchronising. */
 int b200nuts_prng_split(const uint32_t* keys, int64_t n_keys, int32_t num, uint32_t* out);      /* out [n_keys][num][2] */

@@ -30,6 +30,7 @@ struct B200Nuts {
     ChainCtl* ctl = nullptr; float* vecs = nullptr; float* gtmp = nullptr; float* scratch = nullptr;
     uint32_t* keys = nullptr;
     float* dense = nullptr;                    // dense_mass: [C][4][D][D] (ChainVecs::dense)
+    int32_t* ecs_idx = nullptr; bool ecs_proxy_set = false, ecs_idx_set = false;     // HMCECS: [C][m] subsample rows
     bool imm_given = false;                    // b200nuts_set_inverse_mass_matrix was called
     // R2
     float2* partial = nullptr; uint4* beta = nullptr; StreamSync* sync = nullptr;
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(128) k_warp_run(TickCfg cfg, FamilySpec fam, O
     Tick t{cfg, c, cv, out, chain, C};
     float* g = gtmp + (size_t)chain * Dp;
     float* scr = scratch ? scratch + (size_t)chain * scratch_stride : nullptr;
+    if (fam.ecs_m > 0) fam.ecs_idx += (size_t)chain * fam.ecs_m;
     while (c.phase != PH_DONE) {
         __syncwarp();
         float u;
@@ -119,6 +121,7 @@ __global__ void k_potential_warp(FamilySpec fam, const float* z, float* U, float
                                  long long scratch_stride, int C) {
     const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (chain >= C) return;
+    if (fam.ecs_m > 0) fam.ecs_idx += (size_t)chain * fam.ecs_m;
     float u;
     potential_inwarp(fam, z + (size_t)chain * fam.D, scratch ? scratch + (size_t)chain * scratch_stride : nullptr, u,
                      g + (size_t)chain * fam.D);
@@ -385,6 +388,10 @@ static int check_stream_abort(B200Nuts* h, cudaStream_t st) {
     return 0;
 }
 
+static long long scratch_stride(const B200Nuts* h) {
+    return h->fam.ecs_m > 0 ? 2ll * h->fam.ecs_m + h->fam.Dx : (long long)h->fam.N + h->fam.Dx;
+}
+
 // Collect the outcome of the last enqueued launch (caller holds h->mu).
 static int sync_locked(B200Nuts* h) {
     if (!h->pending) return 0;
@@ -431,7 +438,7 @@ int b200nuts_constrained_dim(const B200Nuts* h) {
 
 void b200nuts_destroy(B200Nuts* h) {
     if (!h) return;
-    cudaFree(h->ctl); cudaFree(h->vecs); cudaFree(h->gtmp); cudaFree(h->scratch); cudaFree(h->keys); cudaFree(h->dense);
+    cudaFree(h->ctl); cudaFree(h->vecs); cudaFree(h->gtmp); cudaFree(h->scratch); cudaFree(h->keys); cudaFree(h->dense); cudaFree(h->ecs_idx);
     cudaFree(h->partial); cudaFree(h->beta); cudaFree(h->sync); cudaFree(h->img);
     if (h->trace_host) cudaFreeHost(h->trace_host);
     for (int q = 0; q < kMaxShards; ++q) if (h->mail_ipc[q] && h->mail_peer[q]) cudaIpcCloseMemHandle(h->mail_peer[q]);
@@ -468,6 +475,13 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
         if (gemm_ok && h->C >= 128 && (long long)h->fam.N * h->fam.Dx >= (1LL << 17)) regime = B200NUTS_REGIME_GEMM;
         else if (stream_ok && (long long)h->fam.N * h->fam.Dx >= (1LL << 20)) regime = cfg->dense_mass ? B200NUTS_REGIME_GEMM : B200NUTS_REGIME_STREAM;
         else regime = B200NUTS_REGIME_WARP;
+    }
+    if (h->fam.ecs_m > 0) {                       // HMCECS inner potential: O(m) rows per gradient, evaluated inside the chain's warp
+        if (regime != B200NUTS_REGIME_WARP && cfg->regime != B200NUTS_REGIME_AUTO) {
+            g_create_err = "energy-conserving subsampling runs in the warp regime"; delete h; return B200NUTS_EINVAL;
+        }
+        if (cfg->shard_count > 1) { g_create_err = "energy-conserving subsampling does not combine with row sharding"; delete h; return B200NUTS_EINVAL; }
+        regime = B200NUTS_REGIME_WARP;
     }
     if (regime == B200NUTS_REGIME_STREAM && cfg->dense_mass) {
         g_create_err = "dense_mass is not available in the streaming regime (use the warp or the gemm regime)"; delete h; return B200NUTS_EINVAL;
@@ -506,7 +520,15 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
         if ((ce = cudaMalloc(&h->dense, bytes)) != cudaSuccess) return fail("cudaMalloc dense mass matrices", ce);
         cudaMemset(h->dense, 0, bytes);
     }
-    if (glm && regime == B200NUTS_REGIME_WARP) {
+    if (h->fam.ecs_m > 0) {
+        const size_t stride = (size_t)h->fam.N + h->fam.Dx;      // (>= 2 m + Dx whenever m <= N / 2; checked here)
+        if ((size_t)2 * h->fam.ecs_m > (size_t)h->fam.N) { g_create_err = "ecs_subsample_size must be <= n_rows / 2"; b200nuts_destroy(h); return B200NUTS_EINVAL; }
+        if ((ce = cudaMalloc(&h->scratch, sizeof(float) * (2 * (size_t)h->fam.ecs_m + h->fam.Dx) * h->C)) != cudaSuccess) return fail("cudaMalloc scratch", ce);
+        if ((ce = cudaMalloc(&h->ecs_idx, sizeof(int32_t) * (size_t)h->fam.ecs_m * h->C)) != cudaSuccess) return fail("cudaMalloc subsample indices", ce);
+        cudaMemset(h->ecs_idx, 0, sizeof(int32_t) * (size_t)h->fam.ecs_m * h->C);
+        h->fam.ecs_idx = h->ecs_idx;
+        (void)stride;
+    } else if (glm && regime == B200NUTS_REGIME_WARP) {
         const size_t stride = (size_t)h->fam.N + h->fam.Dx;
         if ((ce = cudaMalloc(&h->scratch, sizeof(float) * stride * h->C)) != cudaSuccess) return fail("cudaMalloc scratch", ce);
     }
@@ -626,8 +648,11 @@ static int run_locked(B200Nuts* h, const B200NutsRun* run, cudaStream_t st) {
     CK(cudaGetLastError());
     h->launches += 1;
     if (h->regime == B200NUTS_REGIME_WARP) {
+        if (h->fam.ecs_m > 0 && !(h->ecs_idx_set && (h->ecs_proxy_set || h->fam.ecs_degree == 0))) {
+            h->err = "HMCECS handle: call b200nuts_ecs_set_proxy / b200nuts_ecs_set_indices first"; return B200NUTS_ESTATE;
+        }
         k_warp_run<<<blocks, 128, 0, st>>>(h->tick, h->fam, out, h->ctl, h->vecs, h->dense, h->gtmp, h->scratch,
-                                           (long long)h->fam.N + h->fam.Dx, h->C, h->Dp);
+                                           scratch_stride(h), h->C, h->Dp);
         CK(cudaGetLastError());
         h->launches += 1;
     } else if (h->regime == B200NUTS_REGIME_GEMM) {
@@ -728,6 +753,33 @@ int b200nuts_set_state(B200Nuts* h, const B200NutsChainState* states, const floa
                                  sizeof(float) * h->D, h->C, cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
     h->inited = true;
+    return 0;
+}
+
+// ---- HMCECS inner potential ---------------------------------------------------------------
+int b200nuts_ecs_set_proxy(B200Nuts* h, const float* ref, const float* eta_ref, const float* G, const float* H, float L0) {
+    if (!h) return B200NUTS_EINVAL;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->fam.ecs_m <= 0 || h->fam.ecs_degree == 0) { h->err = "not an HMCECS handle with a Taylor proxy"; return B200NUTS_ESTATE; }
+    if (!ref || !eta_ref || !G || (h->fam.ecs_degree == 2 && !H)) return B200NUTS_EINVAL;
+    if (int rc0 = sync_locked(h)) return rc0;
+    h->fam.ecs_ref = ref; h->fam.ecs_eta_ref = eta_ref; h->fam.ecs_G = G; h->fam.ecs_H = H; h->fam.ecs_L0 = L0;
+    h->ecs_proxy_set = true;
+    return 0;
+}
+
+int b200nuts_ecs_set_indices(B200Nuts* h, const int32_t* idx, void* stream) {
+    if (!h || !idx) return B200NUTS_EINVAL;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->fam.ecs_m <= 0) { h->err = "not an HMCECS handle"; return B200NUTS_ESTATE; }
+    if (int rc0 = sync_locked(h)) return rc0;
+    const size_t n = (size_t)h->fam.ecs_m * h->C;
+    for (size_t i = 0; i < n; ++i)
+        if (idx[i] < 0 || (long long)idx[i] >= h->fam.N) { h->err = "b200nuts_ecs_set_indices: row index out of range"; return B200NUTS_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(h->ecs_idx, idx, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    h->ecs_idx_set = true;
     return 0;
 }
 
@@ -853,7 +905,10 @@ int b200nuts_potential_and_grad(B200Nuts* h, const float* z, float* U, float* g,
     if (int rc0 = sync_locked(h)) return rc0;
     cudaStream_t st = (cudaStream_t)stream;
     if (h->regime == B200NUTS_REGIME_WARP) {
-        k_potential_warp<<<(h->C + 3) / 4, 128, 0, st>>>(h->fam, z, U, g, h->scratch, (long long)h->fam.N + h->fam.Dx, h->C);
+        if (h->fam.ecs_m > 0 && !(h->ecs_idx_set && (h->ecs_proxy_set || h->fam.ecs_degree == 0))) {
+            h->err = "HMCECS handle: call b200nuts_ecs_set_proxy / b200nuts_ecs_set_indices first"; return B200NUTS_ESTATE;
+        }
+        k_potential_warp<<<(h->C + 3) / 4, 128, 0, st>>>(h->fam, z, U, g, h->scratch, scratch_stride(h), h->C);
         CK(cudaGetLastError());
         h->launches += 1;
         return 0;

@@ -98,6 +98,12 @@ inline std::string make_family(const B200NutsConfig& c, FamilySpec& f, SiteLayou
             if (normal) { sites.off[n] = f.off_prec; sites.size[n++] = 1; }
         }
         sites.n_sites = n;
+        if (c.ecs_subsample_size > 0) {
+            if (local || glob || normal) return "energy-conserving subsampling is implemented for the plain GLM (coefs only, Bernoulli / Poisson)";
+            if (c.ecs_subsample_size > c.n_rows) return "ecs_subsample_size > n_rows";
+            if (c.ecs_proxy_degree < 0 || c.ecs_proxy_degree > 2) return "ecs_proxy_degree must be 0, 1 or 2";
+            f.ecs_m = c.ecs_subsample_size; f.ecs_degree = c.ecs_proxy_degree;
+        }
         return "";
     }
     default: return "unknown family";

@@ -36,6 +36,16 @@ struct FamilySpec {
     //   plain: coefs | horseshoe: lambdas, (prec_obs), tau, unscaled_betas | hierarchical: coefs, tau
     int32_t likelihood, off_lambda, off_tau, off_prec, off_u, gscale, g0, g1;
     float tau_scale, mu_scale;
+    // Energy-conserving subsampling (HMCECS, numpyro/infer/hmc_gibbs.py:502-690; plain GLM only): the likelihood is estimated
+    // from ecs_m of the N rows with a Taylor-proxy control variate around `ecs_ref` (contrib/ecs_proxies.py:23-50, 95-300)
+    int32_t ecs_m;                 // 0: off
+    int32_t ecs_degree;            // Taylor proxy degree 1 / 2; 0 = no proxy (plate-scaled subsample likelihood)
+    const int32_t* ecs_idx;        // [ecs_m] subsample rows of THIS chain (the caller offsets the per-chain table)
+    const float* ecs_eta_ref;      // [N]  x_i . ref
+    const float* ecs_ref;          // [Dx]
+    const float* ecs_G;            // [Dx] gradient of the full-data log-likelihood at ref
+    const float* ecs_H;            // [Dx][Dx] its Hessian (degree 2)
+    float ecs_L0;                  // full-data log-likelihood at ref
 };
 
 constexpr float kLogSqrt2Pi = 0.918938533204672742f;
@@ -179,6 +189,88 @@ B2_HD void glm_finish(const FamilySpec& f, const float* z, float nll, const floa
     B2_LAPQ(10);
 }
 
+// ---- HMCECS potential (one warp): prior + bias-corrected subsample estimate of the log-likelihood -----------------------
+// perturbed_method (contrib/ecs_proxies.py:23-50) with the Taylor proxy (:95-300) written out for a GLM: per subsampled row
+// only eta_i = x_i . z and e0_i = x_i . ref are needed, because the row's log-likelihood depends on z through eta_i alone:
+//   proxy_i(z) = l(e0) + l'(e0) a + 0.5 l''(e0) a^2,  a = eta - e0   (= ll_i(ref) + g_i . dz + 0.5 dz' H_i dz)
+//   diff_i = l(eta) - proxy_i;   ll = proxy_all + N mean(diff) - 0.5 (N^2 / m) var(diff)
+// scratch: >= 2 m + Dx floats.
+B2_HD void potential_ecs_inwarp(const FamilySpec& f, const float* z, float* scratch, float& u_out, float* g) {
+    const int m = f.ecs_m, Dx = f.Dx, deg = f.ecs_degree;
+    float* diff = scratch; float* wc = scratch + m; float* dz = scratch + 2 * m;
+    const float Nf = (float)f.N, mf = (float)m;
+    if (deg > 0) { B2_FOR_D(j, Dx) dz[j] = z[f.off_u + j] - f.ecs_ref[j]; }
+    lane_sync();
+    // pass 1 over the subsample: diff_k and c_k = d diff_k / d eta
+    const float sum_diff = lane_sum(m, [&](int k) {
+        const long long i = f.ecs_idx[k];
+        const float* x = f.X + (size_t)i * Dx;
+        float eta = 0.0f;
+        for (int j = 0; j < Dx; ++j) eta = fmaf(x[j], z[f.off_u + j], eta);
+        const float y = f.y[i];
+        float loss, dl;
+        glm_loss(f.likelihood, eta, y, loss, dl);
+        float ll = -loss;
+        if (f.likelihood == LIK_POISSON) ll = ll - lgammaf(y + 1.0f);
+        float d = ll, c = -dl;
+        if (deg > 0) {
+            const float e0 = f.ecs_eta_ref[i];
+            float loss0, dl0;
+            glm_loss(f.likelihood, e0, y, loss0, dl0);
+            float ll0 = -loss0;
+            if (f.likelihood == LIK_POISSON) ll0 = ll0 - lgammaf(y + 1.0f);
+            const float a = eta - e0;
+            float proxy = ll0 + (-dl0) * a;
+            c = c - (-dl0);
+            if (deg == 2) {
+                float l2;                                     // l''(e0)
+                if (f.likelihood == LIK_BERNOULLI) { const float s = 1.0f / (1.0f + expf(-e0)); l2 = -(s * (1.0f - s)); }
+                else l2 = -expf(e0);
+                proxy = proxy + 0.5f * l2 * a * a;
+                c = c - l2 * a;
+            }
+            d = ll - proxy;
+        }
+        diff[k] = d; wc[k] = c;
+        return d;
+    });
+    lane_sync();
+    const float mean = sum_diff / mf;
+    float ll_est, w_var = 0.0f;
+    if (deg > 0) {
+        const float ss = lane_sum(m, [&](int k) { const float t = diff[k] - mean; return t * t; });
+        const float var = ss / mf;                            // jnp.var: population variance
+        // proxy over all rows: L0 + G . dz + 0.5 dz' H dz
+        float lin, quad = 0.0f;
+        lin = lane_sum(Dx, [&](int j) { return f.ecs_G[j] * dz[j]; });
+        if (deg == 2) quad = lane_sum(Dx, [&](int i) {
+            const float* row = f.ecs_H + (size_t)i * Dx;
+            float a = 0.0f;
+            for (int j = 0; j < Dx; ++j) a = fmaf(row[j], dz[j], a);
+            return a * dz[i];
+        });
+        ll_est = (f.ecs_L0 + lin + 0.5f * quad) + Nf * mean - 0.5f * ((Nf * Nf / mf) * var);
+        w_var = Nf * Nf / (mf * mf);
+    } else {
+        ll_est = (Nf / mf) * sum_diff;                        // plate scaling N / m (primitives.py plate, no proxy)
+    }
+    // weights of the rows in the gradient: d ll / d diff_k = N/m - (N^2/m^2)(diff_k - mean)
+    B2_FOR_D(k, m) wc[k] = wc[k] * (Nf / mf - w_var * (diff[k] - mean));
+    lane_sync();
+    const float prior = lane_sum(Dx, [&](int j) { const float u = z[f.off_u + j]; return 0.5f * u * u; });
+    B2_FOR_D(j, Dx) {
+        float a = 0.0f;
+        for (int k = 0; k < m; ++k) a = fmaf(f.X[(size_t)f.ecs_idx[k] * Dx + j], wc[k], a);
+        if (deg > 0) {
+            a = a + f.ecs_G[j];
+            if (deg == 2) { const float* row = f.ecs_H + (size_t)j * Dx; float h = 0.0f; for (int q = 0; q < Dx; ++q) h = fmaf(row[q], dz[q], h); a = a + h; }
+        }
+        g[f.off_u + j] = z[f.off_u + j] - a;
+    }
+    u_out = (prior + (float)Dx * kLogSqrt2Pi) - ll_est;
+    lane_sync();
+}
+
 // ---- whole potential inside one warp (tiny models, regime R1) ---------------------------------
 // scratch: >= N + Dx floats private to the chain (residuals, beta), gtmp: D floats.
 B2_HD void potential_inwarp(const FamilySpec& f, const float* z, float* scratch, float& u_out, float* g) {
@@ -224,6 +316,7 @@ B2_HD void potential_inwarp(const FamilySpec& f, const float* z, float* scratch,
         }
         return;
     }
+    if (f.ecs_m > 0) { potential_ecs_inwarp(f, z, scratch, u_out, g); return; }
     // FAM_GLM, small N: lanes over rows for eta / residuals, then lanes over columns for X^T r
     float* beta = scratch; float* resid = scratch + f.Dx;
     glm_coef(f, z, beta);

@@ -239,6 +239,21 @@ class Engine:
                                                       None if m2 is None else m2.ctypes.data_as(C.c_void_p), self._stream()),
                     "b200nuts_set_dense_state")
 
+    # ------------------------------------------------------------------ HMCECS inner potential
+    @_on_device
+    def ecs_set_proxy(self, ref, eta_ref, G, H, L0: float):
+        """Device tensors (borrowed: the caller keeps them alive): reference point, X ref, gradient and Hessian of the
+        full-data log-likelihood at it; L0 its value (b200nuts_ecs_set_proxy)."""
+        self._ecs_keep = (ref, eta_ref, G, H)
+        self._check(self.lib.b200nuts_ecs_set_proxy(self.h, _ptr(ref), _ptr(eta_ref), _ptr(G), _ptr(H), C.c_float(L0)),
+                    "b200nuts_ecs_set_proxy")
+
+    @_on_device
+    def ecs_set_indices(self, idx):
+        """The current subsample of every chain, int32 [C, m] (b200nuts_ecs_set_indices)."""
+        idx = np.ascontiguousarray(idx, np.int32).reshape(self.C, -1)
+        self._check(self.lib.b200nuts_ecs_set_indices(self.h, idx.ctypes.data_as(C.c_void_p), self._stream()), "b200nuts_ecs_set_indices")
+
     # ------------------------------------------------------------------ parity hooks
     @_on_device
     def potential_and_grad(self, z):

@@ -347,8 +347,9 @@ class MCMC:
         """``row_shards`` (extension; the reference's analogue is passing GSPMD-sharded model arguments,
         mcmc.py:240-266): split the rows of a tall GLM dataset over ``row_shards`` GPUs of this process; every GPU runs
         all chains over its rows and the per-gradient all-reduce happens inside the kernels (BASELINE config 5)."""
-        if not isinstance(sampler, HMC):
-            raise TypeError("sampler must be numpyro_b200.infer.NUTS or HMC")
+        self._generic = not isinstance(sampler, HMC)
+        if self._generic and not (hasattr(sampler, "init") and hasattr(sampler, "sample") and hasattr(sampler, "inner_kernel")):
+            raise TypeError("sampler must be numpyro_b200.infer.NUTS / HMC or a Gibbs kernel over one (numpyro_b200.hmc_gibbs)")
         if not isinstance(num_warmup, int) or num_warmup < 0:
             raise ValueError("num_warmup must be a non-negative integer")
         if thinning < 1:
@@ -472,7 +473,49 @@ class MCMC:
             self._run(rng_key, args, kwargs, extra_fields, init_params, lower=self.num_warmup,
                       upper=self.num_warmup + self.num_samples)
 
+    def _run_generic(self, rng_key, args, kwargs, extra_fields, init_params, lower, upper, resume):
+        """mcmc.py:466-521 for a kernel that is driven one ``sample`` at a time from the host (HMCGibbs / HMCECS): the chains
+        of the run are one vectorised kernel state; collection as fori_collect (util.py:368-403)."""
+        keys = self._chain_keys(rng_key)
+        C = self.num_chains
+        k = self.sampler
+        if resume is None:
+            state = k.init(keys if C > 1 else keys[0], self.num_warmup, init_params, args, kwargs)
+            i0 = 0
+        else:
+            state = resume._replace(rng_key=(keys if C > 1 else keys[0]))
+            i0 = int(np.ravel(state.hmc_state.i)[0])
+            lower, upper = i0, i0 + self.num_samples
+        post = k.postprocess_fn(args, kwargs)
+        S = max((upper - lower) // self.thinning, 0)
+        start = lower + (upper - lower) % self.thinning
+        rows, extra = [], {f: [] for f in extra_fields}
+
+        def field(st, path):
+            for part in path.split("."):
+                st = st[part] if isinstance(st, dict) else getattr(st, part)
+            return np.asarray(st)
+        for i in range(i0, upper):
+            state = k.sample(state, args, kwargs)
+            if i >= start and (i - start + 1) % self.thinning == 0:
+                rows.append({n: np.array(v) for n, v in post(state.z).items()})
+                for f in extra_fields:
+                    extra[f].append(field(state, f))
+        lead = (lambda a: a) if C > 1 else (lambda a: a[None])
+        stack = lambda seq: np.moveaxis(np.stack([lead(a) for a in seq]), 0, 1) if seq else np.zeros((C, 0))
+        self._states = {"z": {n: stack([r[n] for r in rows]) for n in (rows[0] if rows else {})}}
+        for f in extra_fields:
+            self._states[f] = stack(extra[f])
+        div = np.zeros((C, S), bool)
+        self._states.setdefault("diverging", div)
+        self._states_flat = None
+        self._last_state = state
+        self._bound = getattr(k, "_hmc_bound", None)
+        self.total_grad_evals = None
+
     def _run(self, rng_key, args, kwargs, extra_fields, init_params, lower=None, upper=None, resume=None):
+        if self._generic:
+            return self._run_generic(rng_key, args, kwargs, extra_fields, init_params, lower, upper, resume)
         import time as _time
         t_begin = _time.perf_counter()
         keys = self._chain_keys(rng_key)
