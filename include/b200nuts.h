@@ -92,6 +92,9 @@ typedef struct B200NutsConfig {
     int32_t ecs_subsample_size;  /* m > 0: the likelihood is estimated from m of the n_rows rows (b200nuts_ecs_set_indices) */
     int32_t ecs_proxy_degree;    /* Taylor proxy degree 1 / 2 (b200nuts_ecs_set_proxy), 0 = no proxy (plate-scaled estimate) */
     int32_t reserved0;
+    /* --- conditioning on Gibbs sites, the inner potential of HMCGibbs (hmc_gibbs.py:38-192); warp regime --- */
+    const int32_t* cond_fixed;   /* HOST, [D of the full model] or NULL: 1 = coordinate belongs to a Gibbs site (whole sites only);
+                                    the handle's latent dimension (b200nuts_dim) is then the number of free coordinates */
 } B200NutsConfig;
 
 /* Collection window of one run = fori_collect(lower, upper, thinning) (numpyro/util.py:321-454). */
@@ -207,6 +210,13 @@ int b200nuts_set_dense_state(B200Nuts* h, const float* inverse_mass_matrix, cons
  * chain, host int32 [num_chains][m] (the Gibbs site of HMCECS); every later potential / transition uses it. */
 int b200nuts_ecs_set_proxy(B200Nuts* h, const float* ref, const float* eta_ref, const float* G, const float* H, float L0);
 int b200nuts_ecs_set_indices(B200Nuts* h, const int32_t* idx, void* stream);
+
+/* HMCGibbs inner potential (hmc_gibbs.py:153-186): current values of the Gibbs sites of every chain, host fp32
+ * [num_chains][D_full + 1] -- unconstrained values at the fixed coordinates (free ones ignored) and, last, the amount added
+ * to the potential (sum of the unconstrained values of fixed positive sites: the conditioned model has no Jacobian term for
+ * them).  b200nuts_constrain of a conditioned handle takes vectors of the FULL model. */
+int b200nuts_cond_set_values(B200Nuts* h, const float* values, void* stream);
+int b200nuts_full_dim(const B200Nuts* h);
 
 /* PRNG parity hooks: host in / host out, computed on the device, synchronising. */
 int b200nuts_prng_split(const uint32_t* keys, int64_t n_keys, int32_t num, uint32_t* out);      /* out [n_keys][num][2] */

@@ -40,6 +40,7 @@ class Config(C.Structure):
         ("shard_rank", i32), ("shard_count", i32), ("nccl_comm", vp),
         ("n_rows_global", i64),
         ("dense_mass", i32), ("ecs_subsample_size", i32), ("ecs_proxy_degree", i32), ("reserved0", i32),
+        ("cond_fixed", vp),
     ]
 
 
@@ -115,6 +116,8 @@ EXPORTS = {
     "b200nuts_set_dense_state": (C.c_int, [vp, vp, vp, vp]),
     "b200nuts_ecs_set_proxy": (C.c_int, [vp, vp, vp, vp, vp, f32]),
     "b200nuts_ecs_set_indices": (C.c_int, [vp, vp, vp]),
+    "b200nuts_cond_set_values": (C.c_int, [vp, vp, vp]),
+    "b200nuts_full_dim": (C.c_int, [vp]),
     "b200nuts_prng_split": (C.c_int, [vp, i64, i32, vp]),
     "b200nuts_prng_bits": (C.c_int, [vp, i64, vp]),
     "b200nuts_prng_uniform": (C.c_int, [vp, i64, f32, f32, vp]),

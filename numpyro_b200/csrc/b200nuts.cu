@@ -31,6 +31,7 @@ struct B200Nuts {
     uint32_t* keys = nullptr;
     float* dense = nullptr;                    // dense_mass: [C][4][D][D] (ChainVecs::dense)
     int32_t* ecs_idx = nullptr; bool ecs_proxy_set = false, ecs_idx_set = false;     // HMCECS: [C][m] subsample rows
+    int32_t* cond_map = nullptr; float* cond_val = nullptr; float* cond_scratch = nullptr; bool cond_set = false;   // HMCGibbs
     bool imm_given = false;                    // b200nuts_set_inverse_mass_matrix was called
     // R2
     float2* partial = nullptr; uint4* beta = nullptr; StreamSync* sync = nullptr;
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(128) k_warp_run(TickCfg cfg, FamilySpec fam, O
     float* g = gtmp + (size_t)chain * Dp;
     float* scr = scratch ? scratch + (size_t)chain * scratch_stride : nullptr;
     if (fam.ecs_m > 0) fam.ecs_idx += (size_t)chain * fam.ecs_m;
+    if (fam.cond_Dfree > 0) { fam.cond_val += (size_t)chain * (fam.D + 1); fam.cond_scratch += (size_t)chain * 2 * fam.D; }
     while (c.phase != PH_DONE) {
         __syncwarp();
         float u;
@@ -122,9 +124,11 @@ __global__ void k_potential_warp(FamilySpec fam, const float* z, float* U, float
     const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (chain >= C) return;
     if (fam.ecs_m > 0) fam.ecs_idx += (size_t)chain * fam.ecs_m;
+    const int Dz = fam.cond_Dfree > 0 ? fam.cond_Dfree : fam.D;
+    if (fam.cond_Dfree > 0) { fam.cond_val += (size_t)chain * (fam.D + 1); fam.cond_scratch += (size_t)chain * 2 * fam.D; }
     float u;
-    potential_inwarp(fam, z + (size_t)chain * fam.D, scratch ? scratch + (size_t)chain * scratch_stride : nullptr, u,
-                     g + (size_t)chain * fam.D);
+    potential_inwarp(fam, z + (size_t)chain * Dz, scratch ? scratch + (size_t)chain * scratch_stride : nullptr, u,
+                     g + (size_t)chain * Dz);
     if ((threadIdx.x & 31) == 0) U[chain] = u;
 }
 
@@ -431,14 +435,15 @@ int b200nuts_debug_clocks(const B200Nuts* h, uint64_t* out16) {
 
 int b200nuts_constrained_dim(const B200Nuts* h) {
     if (!h) return B200NUTS_EINVAL;
-    if (h->fam.family == FAM_EIGHT_SCHOOLS) return h->D + (h->D - 2);
-    if (h->fam.family == FAM_GLM && (h->fam.off_lambda >= 0 || h->fam.gscale != SCALE_NONE)) return h->D + h->fam.Dx;
-    return h->D;
+    const int Df = h->fam.D;                       // (the full model's dimension, also for a handle conditioned on Gibbs sites)
+    if (h->fam.family == FAM_EIGHT_SCHOOLS) return Df + (Df - 2);
+    if (h->fam.family == FAM_GLM && (h->fam.off_lambda >= 0 || h->fam.gscale != SCALE_NONE)) return Df + h->fam.Dx;
+    return Df;
 }
 
 void b200nuts_destroy(B200Nuts* h) {
     if (!h) return;
-    cudaFree(h->ctl); cudaFree(h->vecs); cudaFree(h->gtmp); cudaFree(h->scratch); cudaFree(h->keys); cudaFree(h->dense); cudaFree(h->ecs_idx);
+    cudaFree(h->ctl); cudaFree(h->vecs); cudaFree(h->gtmp); cudaFree(h->scratch); cudaFree(h->keys); cudaFree(h->dense); cudaFree(h->ecs_idx); cudaFree(h->cond_map); cudaFree(h->cond_val); cudaFree(h->cond_scratch);
     cudaFree(h->partial); cudaFree(h->beta); cudaFree(h->sync); cudaFree(h->img);
     if (h->trace_host) cudaFreeHost(h->trace_host);
     for (int q = 0; q < kMaxShards; ++q) if (h->mail_ipc[q] && h->mail_peer[q]) cudaIpcCloseMemHandle(h->mail_peer[q]);
@@ -460,7 +465,27 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
     if (e.empty() && (cfg->shard_count < 0 || cfg->shard_count > kMaxShards || (cfg->shard_count > 1 && (cfg->shard_rank < 0 || cfg->shard_rank >= cfg->shard_count))))
         e = "shard_rank / shard_count out of range";
     if (!e.empty()) { g_create_err = e; delete h; return B200NUTS_EINVAL; }
-    h->C = cfg->num_chains; h->D = h->fam.D; h->Dp = (h->D + 3) & ~3;
+    h->C = cfg->num_chains; h->D = h->fam.D;
+    std::vector<int32_t> cond_map_host;
+    if (cfg->cond_fixed) {                       // HMCGibbs: drop the Gibbs sites from the chain's vector (whole sites only)
+        const int Df = h->fam.D;
+        cond_map_host.assign(Df, -1);
+        SiteLayout red; memset(&red, 0, sizeof(red));
+        // free coordinates keep their (sorted-site) order; the init sites keep their trace order
+        int nfree = 0;
+        for (int d = 0; d < Df; ++d) if (!cfg->cond_fixed[d]) cond_map_host[d] = nfree++;
+        for (int s = 0; s < h->sites.n_sites; ++s) {
+            int fixed = 0;
+            for (int j = 0; j < h->sites.size[s]; ++j) fixed += cfg->cond_fixed[h->sites.off[s] + j] ? 1 : 0;
+            if (fixed == h->sites.size[s]) continue;
+            if (fixed != 0) { g_create_err = "cond_fixed must cover whole sites"; delete h; return B200NUTS_EINVAL; }
+            red.off[red.n_sites] = cond_map_host[h->sites.off[s]]; red.size[red.n_sites] = h->sites.size[s]; red.n_sites += 1;
+        }
+        if (nfree == 0 || nfree == Df) { g_create_err = "cond_fixed: at least one free and one fixed coordinate"; delete h; return B200NUTS_EINVAL; }
+        if (cfg->shard_count > 1 || cfg->ecs_subsample_size > 0) { g_create_err = "conditioning does not combine with row sharding / subsampling"; delete h; return B200NUTS_EINVAL; }
+        h->sites = red; h->fam.cond_Dfree = nfree; h->D = nfree;
+    }
+    h->Dp = (h->D + 3) & ~3;
     make_tick_cfg(*cfg, h->fam, h->sites, 0, false, h->tick);
     cudaGetDevice(&h->device);
     cudaDeviceSetLimit(cudaLimitStackSize, 4096);      // per-chain state machine frames (tick.cuh)
@@ -475,6 +500,12 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
         if (gemm_ok && h->C >= 128 && (long long)h->fam.N * h->fam.Dx >= (1LL << 17)) regime = B200NUTS_REGIME_GEMM;
         else if (stream_ok && (long long)h->fam.N * h->fam.Dx >= (1LL << 20)) regime = cfg->dense_mass ? B200NUTS_REGIME_GEMM : B200NUTS_REGIME_STREAM;
         else regime = B200NUTS_REGIME_WARP;
+    }
+    if (h->fam.cond_Dfree > 0) {
+        if (regime != B200NUTS_REGIME_WARP && cfg->regime != B200NUTS_REGIME_AUTO) {
+            g_create_err = "a handle conditioned on Gibbs sites runs in the warp regime"; delete h; return B200NUTS_EINVAL;
+        }
+        regime = B200NUTS_REGIME_WARP;
     }
     if (h->fam.ecs_m > 0) {                       // HMCECS inner potential: O(m) rows per gradient, evaluated inside the chain's warp
         if (regime != B200NUTS_REGIME_WARP && cfg->regime != B200NUTS_REGIME_AUTO) {
@@ -514,6 +545,15 @@ int b200nuts_create(const B200NutsConfig* cfg, B200Nuts** out) {
     if ((ce = cudaMalloc(&h->keys, sizeof(uint32_t) * 2 * h->C)) != cudaSuccess) return fail("cudaMalloc keys", ce);
     cudaMemset(h->vecs, 0, sizeof(float) * (size_t)V_COUNT * h->C * h->Dp);
     cudaMemset(h->ctl, 0, sizeof(ChainCtl) * h->C);
+    if (h->fam.cond_Dfree > 0) {
+        const int Df = h->fam.D;
+        if ((ce = cudaMalloc(&h->cond_map, sizeof(int32_t) * Df)) != cudaSuccess) return fail("cudaMalloc cond_map", ce);
+        if ((ce = cudaMalloc(&h->cond_val, sizeof(float) * (size_t)h->C * (Df + 1))) != cudaSuccess) return fail("cudaMalloc cond_val", ce);
+        if ((ce = cudaMalloc(&h->cond_scratch, sizeof(float) * (size_t)h->C * 2 * Df)) != cudaSuccess) return fail("cudaMalloc cond_scratch", ce);
+        cudaMemcpy(h->cond_map, cond_map_host.data(), sizeof(int32_t) * Df, cudaMemcpyHostToDevice);
+        cudaMemset(h->cond_val, 0, sizeof(float) * (size_t)h->C * (Df + 1));
+        h->fam.cond_map = h->cond_map; h->fam.cond_val = h->cond_val; h->fam.cond_scratch = h->cond_scratch;
+    }
     if (cfg->dense_mass) {
         const size_t bytes = sizeof(float) * (size_t)h->C * 4 * h->D * h->D;
         if (bytes > ((size_t)8 << 30)) { g_create_err = "dense_mass: num_chains x 4 x D^2 floats exceed 8 GiB"; b200nuts_destroy(h); return B200NUTS_EINVAL; }
@@ -755,6 +795,20 @@ int b200nuts_set_state(B200Nuts* h, const B200NutsChainState* states, const floa
     h->inited = true;
     return 0;
 }
+
+// ---- HMCGibbs inner potential: values of the Gibbs sites --------------------------------------------------------------
+int b200nuts_cond_set_values(B200Nuts* h, const float* values, void* stream) {
+    if (!h || !values) return B200NUTS_EINVAL;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->fam.cond_Dfree <= 0) { h->err = "not a handle conditioned on Gibbs sites"; return B200NUTS_ESTATE; }
+    if (int rc0 = sync_locked(h)) return rc0;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(h->cond_val, values, sizeof(float) * (size_t)h->C * (h->fam.D + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    h->cond_set = true;
+    return 0;
+}
+int b200nuts_full_dim(const B200Nuts* h) { return h ? h->fam.D : B200NUTS_EINVAL; }
 
 // ---- HMCECS inner potential ---------------------------------------------------------------
 int b200nuts_ecs_set_proxy(B200Nuts* h, const float* ref, const float* eta_ref, const float* G, const float* H, float L0) {

@@ -113,7 +113,7 @@ inline std::string make_family(const B200NutsConfig& c, FamilySpec& f, SiteLayou
 inline std::string make_tick_cfg(const B200NutsConfig& c, const FamilySpec& f, const SiteLayout& sites,
                                  int num_warmup, bool init_given, TickCfg& t) {
     memset(&t, 0, sizeof(t));
-    t.D = f.D;
+    t.D = f.cond_Dfree > 0 ? f.cond_Dfree : f.D;
     t.num_warmup = num_warmup; t.total_iters = 0;
     t.md_warm = c.max_tree_depth_warmup > 0 ? c.max_tree_depth_warmup : 10;
     t.md_post = c.max_tree_depth > 0 ? c.max_tree_depth : 10;

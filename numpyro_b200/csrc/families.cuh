@@ -46,6 +46,13 @@ struct FamilySpec {
     const float* ecs_G;            // [Dx] gradient of the full-data log-likelihood at ref
     const float* ecs_H;            // [Dx][Dx] its Hessian (degree 2)
     float ecs_L0;                  // full-data log-likelihood at ref
+    // Conditioning on Gibbs sites (HMCGibbs, numpyro/infer/hmc_gibbs.py:38-192): the chain's vector holds only the cond_Dfree
+    // free coordinates; the potential is the full model's with the fixed coordinates substituted (warp regime)
+    int32_t cond_Dfree;            // 0: off
+    const int32_t* cond_map;       // [D] index into the chain's reduced vector, or -1 for a fixed (Gibbs) coordinate
+    const float* cond_val;         // [D + 1] of THIS chain: unconstrained values of the fixed coordinates; [D] = what to add to U (the
+                                   // exp-transform Jacobians of fixed positive sites, absent from the conditioned model)
+    float* cond_scratch;           // [2 D] of THIS chain
 };
 
 constexpr float kLogSqrt2Pi = 0.918938533204672742f;
@@ -273,7 +280,7 @@ B2_HD void potential_ecs_inwarp(const FamilySpec& f, const float* z, float* scra
 
 // ---- whole potential inside one warp (tiny models, regime R1) ---------------------------------
 // scratch: >= N + Dx floats private to the chain (residuals, beta), gtmp: D floats.
-B2_HD void potential_inwarp(const FamilySpec& f, const float* z, float* scratch, float& u_out, float* g) {
+B2_HD void potential_inwarp_full(const FamilySpec& f, const float* z, float* scratch, float& u_out, float* g) {
     if (f.family == FAM_DIAG_GAUSSIAN) {
         const float* mu = f.aux0; const float* sg = f.aux1;
         u_out = 0.5f * lane_sum(f.D, [&](int d) { const float t = (z[d] - mu[d]) / sg[d]; return t * t; });
@@ -339,6 +346,20 @@ B2_HD void potential_inwarp(const FamilySpec& f, const float* z, float* scratch,
     }
     lane_sync();
     glm_finish(f, z, nll, beta, u_out, g);
+}
+
+// The potential the chain's state machine sees: the family's, or -- conditioned on Gibbs sites (HMCGibbs) -- the family's with the
+// fixed coordinates substituted: HMC sites -> full vector, full potential, gradient of the free coordinates back.
+B2_HD void potential_inwarp(const FamilySpec& f, const float* z, float* scratch, float& u_out, float* g) {
+    if (f.cond_Dfree <= 0) { potential_inwarp_full(f, z, scratch, u_out, g); return; }
+    float* zf = f.cond_scratch; float* gf = f.cond_scratch + f.D;
+    B2_FOR_D(d, f.D) { const int k = f.cond_map[d]; zf[d] = (k >= 0) ? z[k] : f.cond_val[d]; }
+    lane_sync();
+    potential_inwarp_full(f, zf, scratch, u_out, gf);
+    lane_sync();
+    B2_FOR_D(d, f.D) { const int k = f.cond_map[d]; if (k >= 0) g[k] = gf[d]; }
+    u_out = u_out + f.cond_val[f.D];
+    lane_sync();
 }
 
 }  // namespace b2

@@ -51,7 +51,11 @@ class Engine:
             self.device = torch.device("cuda", torch.cuda.current_device())
         to = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float32).to(self.device).contiguous()
         self.X, self.y, self.aux = to(X), to(y), to(aux)            # borrowed by the handle: keep alive
+        cond_fixed = cfg.pop("cond_fixed", None)
         c = _capi.default_config(**cfg)
+        if cond_fixed is not None:                                  # HMCGibbs: host int32 mask over the full model's coordinates
+            self._cond_fixed = np.ascontiguousarray(cond_fixed, np.int32)
+            c.cond_fixed = self._cond_fixed.ctypes.data_as(C.c_void_p)
         if self.X is not None:
             c.X = self.X.data_ptr()
             c.n_rows, c.n_cols = self.X.shape
@@ -67,6 +71,7 @@ class Engine:
             raise EngineError(f"b200nuts_create failed ({rc}): {self.lib.b200nuts_last_error(None).decode()}")
         self.C = int(c.num_chains)
         self.D = self.lib.b200nuts_dim(self.h)
+        self.Dfull = self.lib.b200nuts_full_dim(self.h)      # (== D unless the handle is conditioned on Gibbs sites)
         self.Dc = self.lib.b200nuts_constrained_dim(self.h)
         self.regime = self.lib.b200nuts_regime(self.h)
         self.shard_rank, self.shard_count = int(c.shard_rank), int(c.shard_count)
@@ -277,8 +282,14 @@ class Engine:
         return z, r, U, g
 
     @_on_device
+    def cond_set_values(self, values):
+        """Conditioned handles: [C, Dfull + 1] unconstrained values of the Gibbs coordinates + the potential shift."""
+        v = np.ascontiguousarray(values, np.float32).reshape(self.C, self.Dfull + 1)
+        self._check(self.lib.b200nuts_cond_set_values(self.h, v.ctypes.data_as(C.c_void_p), self._stream()), "b200nuts_cond_set_values")
+
+    @_on_device
     def constrain(self, z: torch.Tensor) -> torch.Tensor:
-        z = z.contiguous().view(-1, self.D)
+        z = z.contiguous().view(-1, self.Dfull)
         out = torch.empty((z.shape[0], self.Dc), dtype=torch.float32, device=self.device)
         if z.shape[0] == 0:
             return out

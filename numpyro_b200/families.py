@@ -40,6 +40,7 @@ class BoundModel:
     y: Optional[np.ndarray]
     aux: Optional[np.ndarray]
     sites: List[Site]                # latent sites in flat (sorted-name) order, then deterministic sites
+    trace_order: Optional[List[str]] = None     # latent site names in model-trace order (None: the flat order)
 
     @property
     def latent_sites(self) -> List[Site]:
@@ -137,7 +138,7 @@ class _GLM(Model):
         if X.ndim != 2 or y.shape[0] != X.shape[0]:
             raise ValueError("X must be [N, D] and y [N]")
         lat, det = self._sites(X.shape[1])
-        return BoundModel(self._cfg(X), X, y, None, _layout(lat, det))
+        return BoundModel(self._cfg(X), X, y, None, _layout(lat, det), trace_order=[s.name for s in lat])
 
 
 class LogisticRegression(_GLM):

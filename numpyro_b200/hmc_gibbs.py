@@ -162,13 +162,143 @@ class HMCGibbs(_KernelBase):
         e.transition(1)
 
     # ---- MCMCKernel
+    def _layout(self, bound):
+        """Full-model coordinates of the Gibbs sites, and the inner kernel's (reduced) site table."""
+        names = {s.name for s in bound.latent_sites}
+        missing = [g for g in self._gibbs_sites if g not in names]
+        if missing:
+            raise ValueError(f"gibbs_sites {missing} are not latent sites of the model ({sorted(names)})")
+        Dfull = sum(s.size for s in bound.latent_sites)
+        fixed = np.zeros(Dfull, np.int32)
+        hmc_sites, off = [], 0
+        for s in bound.latent_sites:                                          # flat (sorted-name) order
+            if s.name in self._gibbs_sites:
+                fixed[s.z_offset:s.z_offset + s.size] = 1
+            else:
+                hmc_sites.append(families.Site(s.name, s.shape, s.positive, False, off, off))
+                off += s.size
+        return fixed, families.BoundModel(bound.cfg, bound.X, bound.y, bound.aux, hmc_sites)
+
+    def _prior_draw(self, site, key, bound):
+        """The prototype trace's draw of a Gibbs site (hmc_gibbs.py:127-131: seed + init_to_sample), for the priors restated
+        here: Normal(0, scale).  Other priors: pass the initial value through ``init_params``."""
+        if bound.cfg.get("family") == _capi.FAMILY_EIGHT_SCHOOLS and site.name == "mu":
+            return np.float32(bound.cfg.get("mu_scale", 5.0)) * _engine.prng_normal(key, 1)[0]          # continuous.py:2961-2967
+        raise NotImplementedError(f"initial value of Gibbs site {site.name!r}: pass it in init_params "
+                                  "(only Normal priors are drawn from the prototype trace here)")
+
+    def _push_gibbs(self, gibbs_values):
+        """gibbs_values: {site: [C, ...] constrained values} -> the conditioned handle."""
+        e, bound = self._engine, self._bound
+        vals = np.zeros((e.C, e.Dfull + 1), np.float32)
+        for s in bound.latent_sites:
+            if s.name in self._gibbs_sites:
+                v = np.asarray(gibbs_values[s.name], np.float32).reshape(e.C, s.size)
+                if s.positive:
+                    v = np.log(v)
+                    vals[:, -1] += v.sum(axis=1)                              # no Jacobian term for a conditioned site
+                vals[:, s.z_offset:s.z_offset + s.size] = v
+        e.cond_set_values(vals)
+        self._cond_vals = vals
+
+    def _full_z(self, z_hmc_flat):
+        full = self._cond_vals[:, :-1].copy()
+        full[:, self._fixed == 0] = z_hmc_flat
+        return full
+
+    def _constrained(self, z_hmc_flat):
+        """inner_kernel.postprocess_fn with the Gibbs sites substituted (hmc_gibbs.py:112-121, :166-168)."""
+        e, bound = self._engine, self._bound
+        con = e.constrain(torch.from_numpy(self._full_z(z_hmc_flat)).to(e.device)).cpu().numpy()
+        return {s.name: con[:, s.c_offset:s.c_offset + s.size].reshape((e.C,) + tuple(s.shape)) for s in bound.sites
+                if s.name not in self._gibbs_sites}
+
     def init(self, rng_key, num_warmup, init_params=None, model_args=(), model_kwargs=None):
-        """hmc_gibbs.py:123-151.  Conditioning on user Gibbs sites is implemented for the eight-schools family (site ``mu``)
-        and the diagonal Gaussian (any coordinates); other families raise."""
-        raise NotImplementedError("HMCGibbs.init is provided by the subclasses HMCECS and ConditionedHMCGibbs")
+        """hmc_gibbs.py:123-151, for one key or a batch of keys [C, 2]."""
+        keys = np.asarray(rng_key, U32)
+        self._single = keys.ndim == 1
+        keys = keys.reshape(-1, 2)
+        C = keys.shape[0]
+        bound = self.inner_kernel.model.bind(*model_args, **(model_kwargs or {}))
+        self._fixed, self._hmc_bound = self._layout(bound)
+        init_params = dict(init_params or {})
+        k2 = b2random.split_each(keys)                                        # rng_key, key_u (prototype trace)
+        rng, key_u = k2[:, 0], k2[:, 1]
+        gibbs = {}
+        # seed handler (handlers.py:887-897): every latent site of the trace takes split(key)[1] in trace order
+        order = {}
+        kk = key_u
+        for name in (bound.trace_order or [s.name for s in bound.latent_sites]):
+            sp = b2random.split_each(kk)
+            kk, order[name] = sp[:, 0], sp[:, 1]
+        for s in bound.latent_sites:
+            if s.name in self._gibbs_sites:
+                if s.name in init_params:
+                    gibbs[s.name] = np.broadcast_to(np.asarray(init_params.pop(s.name), np.float32), (C,) + tuple(s.shape)).copy()
+                else:
+                    gibbs[s.name] = np.stack([self._prior_draw(s, order[s.name][c], bound) for c in range(C)]).reshape((C,) + tuple(s.shape))
+        k2 = b2random.split_each(rng)                                         # rng_key, key_z
+        rng, key_z = k2[:, 0], k2[:, 1]
+        e = self._make_engine(keys, num_warmup, bound, dict(cond_fixed=self._fixed, regime=_capi.REGIME_WARP))
+        self._push_gibbs(gibbs)
+        z0 = None
+        if init_params:
+            z0 = _flatten_init(init_params, self._hmc_bound, e.D)
+        elif self.inner_kernel._init_strategy.kind == "feasible":
+            z0 = np.zeros((C, e.D), np.float32)
+        e.init(key_z, int(num_warmup), z0)
+        e.run(0, 0, fields=())
+        hs, _, _ = self._hmc_state()
+        self._gibbs = gibbs
+        return self._pack(hs, rng)
+
+    def _pack(self, hs, rng):
+        sq = (lambda a: a[0]) if self._single else (lambda a: a)
+        z = {**{k: sq(v) for k, v in self._gibbs.items()}, **hs.z}
+        return HMCGibbsState(z, hs, sq(np.asarray(rng, U32)))
+
+    def sample(self, state, model_args=(), model_kwargs=None):
+        """hmc_gibbs.py:153-186, all chains of the handle in lock-step (``gibbs_fn`` is called once per chain)."""
+        e = self._engine
+        if e is None:
+            raise RuntimeError("sample() called before init()")
+        C = e.C
+        k2 = b2random.split_each(np.asarray(state.rng_key, U32).reshape(C, 2))
+        rng, rng_gibbs = k2[:, 0], k2[:, 1]
+        hs, st, vec = self._hmc_state()
+        if self.inner_kernel._dense_mass:
+            self._dense = e.dense_state()
+        z_hmc = self._constrained(vec["z"])
+        new = {k: [] for k in self._gibbs}
+        for c in range(C):
+            out = self._gibbs_fn(rng_key=rng_gibbs[c], gibbs_sites={k: v[c] for k, v in self._gibbs.items()},
+                                 hmc_sites={k: v[c] for k, v in z_hmc.items()})
+            for k in new:
+                new[k].append(np.asarray(out[k], np.float32))
+        self._gibbs = {k: np.stack(v).reshape(self._gibbs[k].shape) for k, v in new.items()}
+        self._push_gibbs(self._gibbs)
+        pe, grad = e.potential_and_grad(vec["z"])                             # value_and_grad(potential_fn(z_gibbs))(hmc_state.z)
+        self._inner_transition(st, vec, pe.cpu().numpy(), grad.cpu().numpy())
+        hs, _, _ = self._hmc_state()
+        return self._pack(hs, rng)
 
     def postprocess_fn(self, args=(), kwargs=None):
-        raise NotImplementedError
+        """hmc_gibbs.py:112-121: Gibbs sites as they are, HMC sites constrained (+ the deterministic sites)."""
+        def fn(z):
+            bound = self._bound
+            first = np.asarray(z[self._hmc_bound.latent_sites[0].name])
+            lead = first.shape[:first.ndim - len(self._hmc_bound.latent_sites[0].shape)]
+            n = int(np.prod(lead)) if lead else 1
+            if n != self._engine.C:
+                raise NotImplementedError("postprocess_fn of HMCGibbs maps one state (all chains of the handle) at a time")
+            flat = np.zeros((n, self._engine.D), np.float32)
+            for s in self._hmc_bound.latent_sites:
+                flat[:, s.z_offset:s.z_offset + s.size] = np.asarray(z[s.name], np.float32).reshape(n, s.size)
+            out = {k: np.asarray(z[k]) for k in self._gibbs_sites}
+            for k, v in self._constrained(flat).items():
+                out[k] = v.reshape(tuple(lead) + v.shape[1:])
+            return out
+        return fn
 
 
 class HMCECS(HMCGibbs):

@@ -190,3 +190,49 @@ class HMCECS:
         hs = replace(s.hmc_state, z_grad=g, potential_energy=F(pe))
         hs = self._kernel(u).sample(hs)
         return ECSState(u, hs, rng_key, acc)
+
+
+# ---------------------------------------------------------------- HMCGibbs (hmc_gibbs.py:38-192)
+@dataclass
+class GibbsState:
+    gibbs: dict               # Gibbs sites (constrained values)
+    hmc_state: ch.HMCState
+    rng_key: np.ndarray
+
+
+class HMCGibbs:
+    """One chain of HMC-within-Gibbs over the oracle kernel.  ``potential_at(gibbs)`` -> (z_hmc -> (U, grad)) is the potential
+    conditioned on the Gibbs sites, ``constrain_hmc(z_hmc, gibbs)`` the inner kernel's postprocess_fn, ``prior_draw(key_u)`` the
+    Gibbs sites' values in the seeded prototype trace (:127-131)."""
+
+    def __init__(self, kernel_kwargs, potential_at, gibbs_fn, constrain_hmc, prior_draw):
+        self.kw, self.potential_at, self.gibbs_fn = dict(kernel_kwargs), potential_at, gibbs_fn
+        self.constrain_hmc, self.prior_draw = constrain_hmc, prior_draw
+
+    def init(self, rng_key, num_warmup: int, reduced_family, init_z=None) -> GibbsState:
+        rng_key, key_u = prng.split(np.asarray(rng_key, U32))
+        gibbs = self.prior_draw(key_u)
+        rng_key, key_z = prng.split(rng_key)
+        k_hmc, k_init = prng.split(key_z)
+        pot = self.potential_at(gibbs)
+        if init_z is None:
+            z, pe, g, ok = ch.init_to_uniform(k_init, reduced_family.init_sites, reduced_family.layout, pot)
+            assert ok
+        else:
+            z = np.asarray(init_z, F)
+            pe, g = pot(z)
+        kern = ch.Kernel(pot, **self.kw)
+        hs = kern.init(k_hmc, num_warmup, z, pe, g)
+        self._adapter, self._num_warmup = kern.adapter, num_warmup
+        return GibbsState(gibbs, hs, rng_key)
+
+    def sample(self, s: GibbsState) -> GibbsState:
+        rng_key, rng_gibbs = prng.split(s.rng_key)
+        z_hmc = self.constrain_hmc(s.hmc_state.z, s.gibbs)
+        gibbs = self.gibbs_fn(rng_key=rng_gibbs, gibbs_sites=s.gibbs, hmc_sites=z_hmc)
+        pot = self.potential_at(gibbs)
+        pe, g = pot(s.hmc_state.z)
+        hs = replace(s.hmc_state, z_grad=np.asarray(g, F), potential_energy=F(pe))
+        k = ch.Kernel(pot, **self.kw)
+        k.adapter, k.num_warmup = self._adapter, self._num_warmup
+        return GibbsState(gibbs, k.sample(hs), rng_key)
