@@ -575,11 +575,13 @@ def run_gemm(args):
                      "traffic": None, "peak_source": peaks["source"] + "; kind::tf32 peak taken as 1/2 of the measured sustained bf16 rate",
                      "kernel": "gemm_pass_kernel", "algorithmic_flops_per_grad_eval": 4.0 * N * D,
                      "split": "every product is 3 tf32 MMAs (hi*hi + lo*hi + hi*lo) for fp32 parity: the executed tensor work is 3x the "
-                              "algorithmic flops, so frac <= 1/3" + ("; plus the forward product repeated per 256-column block (4x)" if D > 256 else ""),
-                     "executed_tensor_frac": achieved * 3 * ((1 + (D + 255) // 256) / 2 if D > 256 else 1) / tf32_peak,
+                              "algorithmic flops, so frac <= 1/3" + ("; more than 256 columns: one forward product per row chunk, one backward product "
+                                                                  "per 256-column block from the residuals kept in tensor memory" if D > 256 else ""),
+                     "executed_tensor_frac": achieved * 3 / tf32_peak,
                      "frac_of_bf16_sustained": achieved / peaks["bf16_tflops_sustained"],
                      "cta0_cycles_per_pass": cyc[0] / max(passes, 1), "cta0_wait_epilogue": cyc[2] / max(cyc[0], 1),
-                     "cta0_wait_tile_copies": cyc[3] / max(cyc[0], 1), "cta0_wait_own_mma": cyc[4] / max(cyc[0], 1)},
+                     "cta0_wait_tile_copies": cyc[3] / max(cyc[0], 1), "cta0_wait_own_mma": cyc[4] / max(cyc[0], 1),
+                     "cta0_wait_gbeta_drain": cyc[5] / max(cyc[0], 1)},
         "cpu_baseline": cpu, "clocks": clk, "per_rank": per_rank,
     }
     print(json.dumps(line))

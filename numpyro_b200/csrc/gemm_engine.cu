@@ -14,7 +14,7 @@ struct GemmRegime {
     int C = 0, Dp = 0, CT = 0, num_sms = 0, grid = 0;
     GemmParams gp;
     float *bimg = nullptr, *ximg = nullptr, *xtimg = nullptr, *yimg = nullptr, *partial = nullptr, *pnll = nullptr;
-    float *gtmp = nullptr, *gbeta = nullptr;
+    float *gtmp = nullptr, *gbeta = nullptr, *nll = nullptr;
     int *tile_count = nullptr, *active_tiles = nullptr;
     GemmSched* sched = nullptr; GemmCtx* ctx = nullptr;
     ChainCtl* ctl = nullptr; float* vecs = nullptr; float* dense = nullptr;
@@ -44,9 +44,21 @@ static std::string launch_pass(GemmRegime* g, cudaStream_t st) {
     return "";
 }
 
+static int reduce_blocks(const GemmRegime* g) {
+    const long long words = (long long)g->C * (g->gp.Dxp >> 2);
+    const long long b = (words + 255) / 256;
+    return (int)(b < 8ll * g->num_sms ? (b > 0 ? b : 1) : 8ll * g->num_sms);
+}
+
+static std::string launch_reduce(GemmRegime* g, cudaStream_t st) {
+    k_gemm_reduce<<<reduce_blocks(g), 256, 0, st>>>(g->gp, g->gbeta, g->nll, g->C);
+    GCK(cudaGetLastError());
+    return "";
+}
+
 static std::string launch_tick(GemmRegime* g, int first, cudaStream_t st) {
     const int blocks = (g->C + 3) / 4;
-    k_gemm_tick<<<blocks, 128, 0, st>>>(g->gp, g->ctx, g->sched, g->fam, g->ctl, g->vecs, g->gtmp, g->gbeta, g->bimg, g->tile_count,
+    k_gemm_tick<<<blocks, 128, 0, st>>>(g->gp, g->ctx, g->sched, g->fam, g->ctl, g->vecs, g->gtmp, g->gbeta, g->nll, g->bimg, g->tile_count,
                                         g->C, g->Dp, first, g->shard, g->dense);
     GCK(cudaGetLastError());
     k_gemm_sched<<<1, 32, 0, st>>>(g->ctx, g->sched, g->tile_count, g->active_tiles, g->CT, first, g->cond, 0);
@@ -54,7 +66,7 @@ static std::string launch_tick(GemmRegime* g, int first, cudaStream_t st) {
     return "";
 }
 
-// graph = WHILE (cond) { gemm pass; tick; schedule (sets cond) }
+// graph = WHILE (cond) { gemm pass; reduce; tick; schedule (sets cond) }
 static std::string build_graph(GemmRegime* g) {
     GCK(cudaGraphCreate(&g->graph, 0));
     GCK(cudaGraphConditionalHandleCreate(&g->cond, g->graph, 1, cudaGraphCondAssignDefault));
@@ -63,7 +75,7 @@ static std::string build_graph(GemmRegime* g) {
     cudaGraphNode_t wnode;
     GCK(cudaGraphAddNode(&wnode, g->graph, nullptr, 0, &np));
     cudaGraph_t body = np.conditional.phGraph_out[0];
-    cudaGraphNode_t n_pass, n_tick, n_sched;
+    cudaGraphNode_t n_pass, n_red, n_tick, n_sched;
     {
         void* args[] = {&g->gp};
         cudaKernelNodeParams kp; memset(&kp, 0, sizeof(kp));
@@ -72,11 +84,17 @@ static std::string build_graph(GemmRegime* g) {
         GCK(cudaGraphAddKernelNode(&n_pass, body, nullptr, 0, &kp));
     }
     {
+        void* args[] = {&g->gp, &g->gbeta, &g->nll, &g->C};
+        cudaKernelNodeParams kp; memset(&kp, 0, sizeof(kp));
+        kp.func = (void*)k_gemm_reduce; kp.gridDim = dim3(reduce_blocks(g)); kp.blockDim = dim3(256); kp.kernelParams = args;
+        GCK(cudaGraphAddKernelNode(&n_red, body, &n_pass, 1, &kp));
+    }
+    {
         int first = 0;
-        void* args[] = {&g->gp, &g->ctx, &g->sched, &g->fam, &g->ctl, &g->vecs, &g->gtmp, &g->gbeta, &g->bimg, &g->tile_count, &g->C, &g->Dp, &first, &g->shard, &g->dense};
+        void* args[] = {&g->gp, &g->ctx, &g->sched, &g->fam, &g->ctl, &g->vecs, &g->gtmp, &g->gbeta, &g->nll, &g->bimg, &g->tile_count, &g->C, &g->Dp, &first, &g->shard, &g->dense};
         cudaKernelNodeParams kp; memset(&kp, 0, sizeof(kp));
         kp.func = (void*)k_gemm_tick; kp.gridDim = dim3((g->C + 3) / 4); kp.blockDim = dim3(128); kp.kernelParams = args;
-        GCK(cudaGraphAddKernelNode(&n_tick, body, &n_pass, 1, &kp));
+        GCK(cudaGraphAddKernelNode(&n_tick, body, &n_red, 1, &kp));
     }
     {
         int first = 0, use_cond = 1;
@@ -126,6 +144,7 @@ std::string gemm_create(GemmRegime** out, const FamilySpec& fam, int C, int Dp, 
     GALLOC(g->pnll, (size_t)CT * S * 4 * kGtChains * 4);
     GALLOC(g->gtmp, (size_t)C * Dp * 4);
     GALLOC(g->gbeta, (size_t)C * Dxp * 4);
+    GALLOC(g->nll, (size_t)C * 4);
     GALLOC(g->tile_count, (size_t)2 * CT * 4);
     GALLOC(g->active_tiles, (size_t)CT * 4);
     GALLOC(g->sched, sizeof(GemmSched));
@@ -152,7 +171,8 @@ std::string gemm_create(GemmRegime** out, const FamilySpec& fam, int C, int Dp, 
         return fail(std::string("cudaFuncSetAttribute(gemm_pass_kernel): ") + cudaGetErrorString(ce));
     {   // load every kernel now (lazy module loading must not happen inside a captured / conditional launch)
         cudaFuncAttributes fa;
-        const void* fns[] = {fn, (const void*)k_gemm_tick, (const void*)k_gemm_sched, (const void*)k_gemm_hook_begin, (const void*)k_gemm_hook_finish};
+        const void* fns[] = {fn, (const void*)k_gemm_tick, (const void*)k_gemm_sched, (const void*)k_gemm_hook_begin, (const void*)k_gemm_hook_finish,
+                             (const void*)k_gemm_reduce};
         for (const void* f : fns)
             if ((ce = cudaFuncGetAttributes(&fa, f)) != cudaSuccess) return fail(std::string("cudaFuncGetAttributes: ") + cudaGetErrorString(ce));
     }
@@ -172,7 +192,7 @@ void gemm_destroy(GemmRegime* g) {
     if (g->exec) cudaGraphExecDestroy(g->exec);
     if (g->graph) cudaGraphDestroy(g->graph);
     cudaFree(g->bimg); cudaFree(g->ximg); cudaFree(g->xtimg); cudaFree(g->yimg); cudaFree(g->partial); cudaFree(g->pnll);
-    cudaFree(g->gtmp); cudaFree(g->gbeta); cudaFree(g->tile_count); cudaFree(g->active_tiles); cudaFree(g->sched); cudaFree(g->ctx);
+    cudaFree(g->gtmp); cudaFree(g->gbeta); cudaFree(g->nll); cudaFree(g->tile_count); cudaFree(g->active_tiles); cudaFree(g->sched); cudaFree(g->ctx);
     delete g;
 }
 
@@ -214,6 +234,7 @@ std::string gemm_run(GemmRegime* g, const TickCfg& cfg, const OutBufs& out, int 
         GCK(cudaStreamSynchronize(st));
         if (s.n_active == 0 || s.abort_flag != 0u || (max_passes > 0 && s.pass_in_run >= max_passes)) break;
         if (!(e = launch_pass(g, st)).empty()) return e;
+        if (!(e = launch_reduce(g, st)).empty()) return e;
         if (!(e = launch_tick(g, 0, st)).empty()) return e;
     }
     return "";
@@ -225,9 +246,10 @@ std::string gemm_potential(GemmRegime* g, const float* z, float* U, float* grad,
     GCK(cudaGetLastError());
     std::string e = launch_pass(g, st);
     if (!e.empty()) return e;
-    k_gemm_hook_finish<<<blocks, 128, 0, st>>>(g->gp, g->fam, z, U, grad, g->gbeta, g->C, g->shard, ++g->epoch);
+    if (!(e = launch_reduce(g, st)).empty()) return e;
+    k_gemm_hook_finish<<<blocks, 128, 0, st>>>(g->gp, g->fam, z, U, grad, g->gbeta, g->nll, g->C, g->shard, ++g->epoch);
     GCK(cudaGetLastError());
-    *launches += 3;
+    *launches += 4;
     return "";
 }
 
@@ -235,7 +257,7 @@ std::string gemm_sync(GemmRegime* g, cudaStream_t st, GemmStatus* status, long l
     GemmSched s;
     GCK(cudaMemcpyAsync(&s, g->sched, sizeof(s), cudaMemcpyDeviceToHost, st));
     GCK(cudaStreamSynchronize(st));
-    if (launches) *launches += 3ll * (long long)(s.passes_total - g->passes_seen);
+    if (launches) *launches += 4ll * (long long)(s.passes_total - g->passes_seen);
     g->passes_seen = s.passes_total;
     if (status) {
         status->abort_flag = s.abort_flag; status->passes_total = s.passes_total; status->n_active = s.n_active;

@@ -107,21 +107,21 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_pass_kernel(const __grid_c
     const uint32_t tmem = *tmem_slot;
 
     const int n_active = *p.n_active;
-    const int per_block = n_active * p.S;                 // units per column block
-    const int n_units = per_block * p.NDB;
+    const int per_block = n_active * p.S;                 // units = (segment, chain tile)
+    // More than 256 columns: every chunk runs the forward product ONCE and then one backward product per column block
+    // (the residuals stay in tensor memory); a block's sums are drained straight into the unit's partial sums in global memory.
+    const int NJ = p.NDB;
+    const int n_units = per_block;
     const long long t_start = clock64();
-    unsigned long long wait_epi = 0ull, wait_tma = 0ull, wait_mma = 0ull;
+    unsigned long long wait_epi = 0ull, wait_tma = 0ull, wait_mma = 0ull, wait_gfree = 0ull;
 
     if (warp == 0) {
         // ================================================================= producer: one lane feeds the ring
         if (lane == 0) {
             int st = 0; uint32_t ph = 0; unsigned int chunk_no = 0; bool ok = true;
             for (int u = blockIdx.x; u < n_units && ok; u += gridDim.x) {
-                const int j = u / per_block, rem = u - j * per_block;
-                const int s = rem / n_active, t = p.active_tiles[rem - s * n_active];
+                const int s = u / n_active, t = p.active_tiles[u - s * n_active];
                 const int c0 = s * p.cps, c1 = min(p.RC, c0 + p.cps);
-                const int nb = min(kGtNB, p.Dxp - kGtNB * j);
-                const float* xt_base = p.xtimg + gemm_xt_block_floats(p.RC, j);
                 for (int c = c0; c < c1 && ok; ++c, ++chunk_no) {
                     {   // responses of this chunk
                         const int ys = chunk_no % kGtYSlots;
@@ -136,13 +136,17 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_pass_kernel(const __grid_c
                         u_bulk_g2s(dst + 32768, p.ximg + ((size_t)c * p.KB + kb) * 2 * kGtTileFloats, 32768u, &full[st]);
                         if (++st == kGtStages) { st = 0; ph ^= 1u; }
                     }
-                    for (int rk = 0; rk < 4 && ok; ++rk) {
-                        ok = u_mbar_wait(&empty[st], ph ^ 1u, p.spin_limit, p.abort_flag, 12u);
-                        unsigned char* dst = stage + (size_t)st * kGtStageBytes;
-                        const uint32_t bytes = 2u * (uint32_t)nb * 128u;
-                        u_mbar_expect_tx(&full[st], bytes);
-                        u_bulk_g2s(dst, xt_base + ((size_t)c * 4 + rk) * 2 * nb * 32, bytes, &full[st]);
-                        if (++st == kGtStages) { st = 0; ph ^= 1u; }
+                    for (int j = 0; j < NJ && ok; ++j) {
+                        const int nb = min(kGtNB, p.Dxp - kGtNB * j);
+                        const float* xt_base = p.xtimg + gemm_xt_block_floats(p.RC, j);
+                        for (int rk = 0; rk < 4 && ok; ++rk) {
+                            ok = u_mbar_wait(&empty[st], ph ^ 1u, p.spin_limit, p.abort_flag, 12u);
+                            unsigned char* dst = stage + (size_t)st * kGtStageBytes;
+                            const uint32_t bytes = 2u * (uint32_t)nb * 128u;
+                            u_mbar_expect_tx(&full[st], bytes);
+                            u_bulk_g2s(dst, xt_base + ((size_t)c * 4 + rk) * 2 * nb * 32, bytes, &full[st]);
+                            if (++st == kGtStages) { st = 0; ph ^= 1u; }
+                        }
                     }
                 }
             }
@@ -150,21 +154,18 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_pass_kernel(const __grid_c
     } else if (warp == 1) {
         // ================================================================= MMA issuer: one thread
         if (lane == 0) {
-            int st = 0; uint32_t ph = 0; unsigned int chunk_no = 0; bool ok = true;
+            int st = 0; uint32_t ph = 0; unsigned int chunk_no = 0, blk_no = 0; bool ok = true;      // blk_no: backward blocks issued
             const uint32_t idesc_f = umma_idesc_tf32(kGtChains, kGtRows);
             for (int u = blockIdx.x; u < n_units && ok; u += gridDim.x) {
-                const int j = u / per_block, rem = u - j * per_block;
-                const int s = rem / n_active;
+                const int s = u / n_active;
                 const int c0 = s * p.cps, c1 = min(p.RC, c0 + p.cps);
-                const int nb = min(kGtNB, p.Dxp - kGtNB * j);
-                const uint32_t idesc_b = umma_idesc_tf32(kGtChains, nb);
                 for (int c = c0; c < c1 && ok; ++c, ++chunk_no) {
                     const uint32_t cpar = chunk_no & 1u;
                     // the previous chunk's backward MMAs read the residuals from the columns the logits go to: they must
-                    // have completed (g_full of the previous chunk) before the forward MMAs of this chunk are issued
-                    if (chunk_no > 0) {
+                    // have completed (g_full of its last column block) before the forward MMAs of this chunk are issued
+                    if (blk_no > 0) {
                         const long long tw = clock64();
-                        ok = u_mbar_wait(g_full, cpar ^ 1u, p.spin_limit, p.abort_flag, 13u);
+                        ok = u_mbar_wait(g_full, (blk_no - 1u) & 1u, p.spin_limit, p.abort_flag, 13u);
                         wait_mma += (unsigned long long)(clock64() - tw);
                     }
                     tc_fence_after();
@@ -191,11 +192,17 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_pass_kernel(const __grid_c
                     umma_commit(l_full);
                     // the epilogue delivers the residuals in four groups of 32 rows (= one backward k-block each): the backward
                     // MMAs of a group start while the link function of the next groups is still being evaluated
+                    for (int j = 0; j < NJ && ok; ++j, ++blk_no) {
+                    const int nb = min(kGtNB, p.Dxp - kGtNB * j);
+                    const uint32_t idesc_b = umma_idesc_tf32(kGtChains, nb);
                     for (uint32_t rk = 0; rk < 4 && ok; ++rk) {
                         {
                             const long long tw = clock64();
-                            ok = u_mbar_wait(&r_ready[rk], cpar, p.spin_limit, p.abort_flag, 15u);
-                            if (rk == 0 && chunk_no > 0) ok = ok && u_mbar_wait(g_free, cpar ^ 1u, p.spin_limit, p.abort_flag, 16u);
+                            if (j == 0) ok = u_mbar_wait(&r_ready[rk], cpar, p.spin_limit, p.abort_flag, 15u);
+                            const long long tg = clock64();
+                            // the gbeta columns are free once the epilogue has drained the previous block
+                            if (rk == 0 && blk_no > 0) ok = ok && u_mbar_wait(g_free, (blk_no - 1u) & 1u, p.spin_limit, p.abort_flag, 16u);
+                            wait_gfree += (unsigned long long)(clock64() - tg);
                             wait_epi += (unsigned long long)(clock64() - tw);
                         }
                         {
@@ -217,6 +224,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_pass_kernel(const __grid_c
                         if (++st == kGtStages) { st = 0; ph ^= 1u; }
                     }
                     umma_commit(g_full);
+                    }
                 }
             }
         }
@@ -230,12 +238,11 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_pass_kernel(const __grid_c
 #pragma unroll
         for (int i = 0; i < 64; ++i) gsum[i] = 0.0f;
         float nll_unit = 0.0f;
-        unsigned int chunk_no = 0; bool ok = true;
+        unsigned int chunk_no = 0, blk_no = 0; bool ok = true;
         for (int u = blockIdx.x; u < n_units && ok; u += gridDim.x) {
-            const int j = u / per_block, rem = u - j * per_block;
-            const int s = rem / n_active, t = p.active_tiles[rem - s * n_active];
+            const int s = u / n_active, t = p.active_tiles[u - s * n_active];
             const int c0 = s * p.cps, c1 = min(p.RC, c0 + p.cps);
-            const int nb = min(kGtNB, p.Dxp - kGtNB * j);
+            float* const unit_dst = p.partial + (((size_t)t * p.S + s) * kGtChains + chain_row) * p.Dxp + 64 * cg;
             for (int c = c0; c < c1 && ok; ++c, ++chunk_no) {
                 const uint32_t cpar = chunk_no & 1u;
                 const int ys = chunk_no % kGtYSlots;
@@ -275,37 +282,54 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_pass_kernel(const __grid_c
                     if (lane == 0) u_mbar_arrive(&r_ready[rk]);
                 }
                 nll_unit += nl0 + nl1;
-                // ---- drain gbeta of this chunk into the fp32 sums (columns [64 cg, 64 cg + 64) of this thread's chain)
-                ok = u_mbar_wait(g_full, cpar, p.spin_limit, p.abort_flag, 20u);
-                ok = __all_sync(0xFFFFFFFFu, ok);
-                if (!ok) break;
-                tc_fence_after();
+                // ---- drain gbeta of every column block of this chunk (columns [64 cg, 64 cg + 64) of this thread's chain): into
+                //      the fp32 register sums of the unit (one block), or -- several blocks -- into the unit's partial sums in
+                //      global memory (first chunk stores, later chunks add; the unit belongs to this CTA alone)
+                for (int j = 0; j < NJ && ok; ++j, ++blk_no) {
+                    const int nb = min(kGtNB, p.Dxp - kGtNB * j);
+                    ok = u_mbar_wait(g_full, blk_no & 1u, p.spin_limit, p.abort_flag, 20u);
+                    ok = __all_sync(0xFFFFFFFFu, ok);
+                    if (!ok) break;
+                    tc_fence_after();
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int col = 64 * cg + 16 * k;
-                    if (col < nb) {
-                        uint32_t v[16];
-                        tmem_ld16(tmem + lane_base + kColG + col, v);
-                        tmem_wait_ld();
+                    for (int k = 0; k < 4; ++k) {
+                        const int col = 64 * cg + 16 * k;
+                        if (col < nb) {
+                            uint32_t v[16];
+                            tmem_ld16(tmem + lane_base + kColG + col, v);
+                            tmem_wait_ld();
+                            if (NJ == 1) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) gsum[16 * k + i] += __uint_as_float(v[i]);
+                                for (int i = 0; i < 16; ++i) gsum[16 * k + i] += __uint_as_float(v[i]);
+                            } else {
+                                float* dst = unit_dst + kGtNB * j + 16 * k;
+#pragma unroll
+                                for (int i = 0; i < 16; i += 4) {
+                                    float4 a = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+                                    if (c > c0) { const float4 o = *reinterpret_cast<const float4*>(dst + i); a.x = o.x + a.x; a.y = o.y + a.y; a.z = o.z + a.z; a.w = o.w + a.w; }
+                                    *reinterpret_cast<float4*>(dst + i) = a;
+                                }
+                            }
+                        }
                     }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) u_mbar_arrive(g_free);
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) u_mbar_arrive(g_free);
             }
             // ---- end of the unit: write its partial sums
             if (ok) {
-                float* dst = p.partial + (((size_t)t * p.S + s) * kGtChains + chain_row) * p.Dxp + kGtNB * j + 64 * cg;
+                if (NJ == 1) {
+                    const int nb = min(kGtNB, p.Dxp);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (64 * cg + 16 * k < nb) {
+                    for (int k = 0; k < 4; ++k)
+                        if (64 * cg + 16 * k < nb) {
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4)
-                            *reinterpret_cast<float4*>(dst + 16 * k + i) = make_float4(gsum[16 * k + i], gsum[16 * k + i + 1], gsum[16 * k + i + 2], gsum[16 * k + i + 3]);
-                    }
-                if (j == 0) p.pnll[(((size_t)t * p.S + s) * 4 + cg) * kGtChains + chain_row] = nll_unit;
+                            for (int i = 0; i < 16; i += 4)
+                                *reinterpret_cast<float4*>(unit_dst + 16 * k + i) = make_float4(gsum[16 * k + i], gsum[16 * k + i + 1], gsum[16 * k + i + 2], gsum[16 * k + i + 3]);
+                        }
+                }
+                p.pnll[(((size_t)t * p.S + s) * 4 + cg) * kGtChains + chain_row] = nll_unit;
             }
 #pragma unroll
             for (int i = 0; i < 64; ++i) gsum[i] = 0.0f;
@@ -319,7 +343,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_pass_kernel(const __grid_c
     if (blockIdx.x == 0 && tid == 32 && p.dbg) {
         p.dbg[0] += (unsigned long long)(clock64() - t_start);
         p.dbg[1] += (unsigned long long)((n_units + (int)gridDim.x - 1) / (int)gridDim.x);
-        p.dbg[2] += wait_epi; p.dbg[3] += wait_tma; p.dbg[4] += wait_mma;
+        p.dbg[2] += wait_epi; p.dbg[3] += wait_tma; p.dbg[4] += wait_mma; p.dbg[5] += wait_gfree;
     }
 }
 
@@ -396,20 +420,27 @@ B2_D void gemm_write_betas(const FamilySpec& f, const float* z, float* bimg, int
     }
 }
 
-// sum of the S unit partials of one chain, in segment order; every lane gets nll, gbeta[] receives the columns
-B2_D float gemm_gather(const GemmParams& gp, int chain, float* gbeta, int Dx) {
-    const int t = chain / kGtChains, r = chain % kGtChains;
-    const int lane = threadIdx.x & 31;
-    for (int d = lane; d < Dx; d += 32) {
-        float a = 0.0f;
-        const float* src = gp.partial + ((size_t)t * gp.S * kGtChains + r) * gp.Dxp + d;
-        for (int s = 0; s < gp.S; ++s) a += src[(size_t)s * kGtChains * gp.Dxp];
-        gbeta[d] = a;
+// Sum of the S unit partials of every chain, in segment order (fixed order => bit-reproducible): gbeta [C][Dxp], nll [C].
+// A kernel of its own between the GEMM pass and the tick: the sums of a wide model are hundreds of MB per pass
+// (horseshoe config: 79 segments x 1024 chains x 1024 columns), far too much for the one warp per chain of the tick.
+static __global__ void __launch_bounds__(256) k_gemm_reduce(GemmParams gp, float* __restrict__ gbeta, float* __restrict__ nll_out, int C) {
+    const int q4 = gp.Dxp >> 2;                                 // float4 words per chain
+    const long long total = (long long)C * q4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int chain = (int)(i / q4), d4 = (int)(i - (long long)chain * q4);
+        const int t = chain / kGtChains, r = chain % kGtChains;
+        const float4* src = reinterpret_cast<const float4*>(gp.partial + ((size_t)t * gp.S * kGtChains + r) * gp.Dxp) + d4;
+        const size_t stride = (size_t)kGtChains * q4;
+        float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (int s = 0; s < gp.S; ++s) { const float4 v = src[(size_t)s * stride]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+        reinterpret_cast<float4*>(gbeta + (size_t)chain * gp.Dxp)[d4] = a;
+        if (d4 == 0) {
+            float nll = 0.0f;
+            const float* pn = gp.pnll + (size_t)t * gp.S * 4 * kGtChains + r;
+            for (int s = 0; s < gp.S * 4; ++s) nll += pn[(size_t)s * kGtChains];
+            nll_out[chain] = nll;
+        }
     }
-    float nll = 0.0f;
-    const float* pn = gp.pnll + (size_t)t * gp.S * 4 * kGtChains + r;
-    for (int s = 0; s < gp.S * 4; ++s) nll += pn[(size_t)s * kGtChains];
-    return nll;
 }
 
 B2_D void g_st_sys_v2(float2* p, float2 v) { asm volatile("st.volatile.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory"); }
@@ -457,7 +488,7 @@ B2_D float gemm_shard_allreduce(const GemmShardDev& sh, int C, int chain, float*
 // Tick of every chain after a pass (one warp per chain): likelihood sums -> potential -> NUTS state machine -> next betas.
 // first != 0: start of a run -- no gradient yet, only publish the betas of the chains that wait for one.
 static __global__ void __launch_bounds__(128) k_gemm_tick(GemmParams gp, const GemmCtx* ctx, GemmSched* sched, FamilySpec fam, ChainCtl* ctl,
-                                                           float* vecs, float* gtmp, float* gbeta, float* bimg, int* tile_count,
+                                                           float* vecs, float* gtmp, float* gbeta, const float* nll_in, float* bimg, int* tile_count,
                                                            int C, int Dp, int first, GemmShardDev sh, float* dense) {
     __shared__ TickCfg s_cfg; __shared__ OutBufs s_out;
     {
@@ -476,8 +507,7 @@ static __global__ void __launch_bounds__(128) k_gemm_tick(GemmParams gp, const G
     if (!first) {
         Tick t{s_cfg, c, cv, s_out, chain, C};
         float* gb = gbeta + (size_t)chain * gp.Dxp; float* g = gtmp + (size_t)chain * Dp;
-        float nll = gemm_gather(gp, chain, gb, fam.Dx);
-        __syncwarp(); lane_sync();
+        float nll = nll_in[chain];                 // (k_gemm_reduce summed the unit partials)
         if (sh.count > 1) {
             nll = gemm_shard_allreduce(sh, C, chain, gb, nll, fam.Dx, gp.Dxp, gemm_xtag(ctx->epoch, (uint32_t)sched->pass_in_run + 1u),
                                        sched->pass_in_run & 1, gp.abort_flag, 8 * gp.spin_limit);
@@ -524,12 +554,11 @@ static __global__ void __launch_bounds__(128) k_gemm_hook_begin(FamilySpec fam, 
     gemm_write_betas(fam, z_in + (size_t)chain * fam.D, bimg, KB, chain);
 }
 static __global__ void __launch_bounds__(128) k_gemm_hook_finish(GemmParams gp, FamilySpec fam, const float* z_in, float* U, float* g_out,
-                                                                  float* gbeta, int C, GemmShardDev sh, unsigned int epoch) {
+                                                                  float* gbeta, const float* nll_in, int C, GemmShardDev sh, unsigned int epoch) {
     const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (chain >= C) return;
     float* gb = gbeta + (size_t)chain * gp.Dxp;
-    float nll = gemm_gather(gp, chain, gb, fam.Dx);
-    __syncwarp(); lane_sync();
+    float nll = nll_in[chain];
     if (sh.count > 1) {
         nll = gemm_shard_allreduce(sh, C, chain, gb, nll, fam.Dx, gp.Dxp, gemm_xtag(epoch, 0x7FFFFFu), 0, gp.abort_flag, 8 * gp.spin_limit);
         __syncwarp(); lane_sync();
