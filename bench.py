@@ -553,6 +553,7 @@ def run_gemm(args):
     tf32_peak = 0.5 * peaks["bf16_tflops_sustained"]
     achieved = 4.0 * N * D * leap / (ms * 1e-3) / 1e12               # rank 0's kernel
     cyc = (c1 - c0)
+    print("tick laps chain 0 (cycles per pass): glm_finish %.0f advance %.0f" % (cyc[6] / max(passes, 1), cyc[7] / max(passes, 1)), file=sys.stderr)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(config, X, y, depth=3, rounds=3)

@@ -377,6 +377,11 @@ static int check_stream_abort(B200Nuts* h, cudaStream_t st) {
                     (double)s.tick_lap[c][3] / s.passes, s.pre_hit[c][0], s.pre_miss[c][0], s.pre_hit[c][1], s.pre_miss[c][1],
                     s.pre_hit[c][2], s.pre_miss[c][2]);
     }
+    if (getenv("B200NUTS_DEBUG_CTA") && s.passes) {
+        for (int g = 0; g < h->grid && g < 160; ++g)
+            fprintf(stderr, "[b200nuts] cta %3d per pass: wait_beta %.0f sweep %.0f reduce %.0f gather %.0f\n", g, (double)s.cta_lap[g][0] / s.passes,
+                    (double)s.cta_lap[g][1] / s.passes, (double)s.cta_lap[g][2] / s.passes, (double)s.cta_lap[g][3] / s.passes);
+    }
 #ifdef B2_TICK_LAPS
     if (getenv("B200NUTS_DEBUG_TICK") && s.passes) {
         fprintf(stderr, "[b200nuts] chain 0 tick laps, cycles per occurrence (occurrences):");

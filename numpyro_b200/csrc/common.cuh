@@ -120,6 +120,64 @@ B2_HD void lane_sum2(int D, Fn f, float& out0, float& out1) {
 #endif
 }
 
+// ---- wide vectors (D > 64: the GEMM regime's few-but-wide chains) ---------------------------------------------------------------
+// A lane's element loop is a chain of dependent load -> compute -> store round trips (~600 cycles each from L2 / HBM) and a warp
+// owns one chain, so nothing hides the latency.  These variants keep FOUR elements of a lane in flight: all loads of a batch are
+// issued before its first store (explicitly, so no alias analysis is needed).  Per element the arithmetic is unchanged and the
+// reductions add in the same order (k ascending per lane, then the butterfly): identical bits.
+struct Vals { float x[6]; };
+template <class L, class S>
+B2_HD void for_d_wide(int D, L load, S store) {
+#if defined(__CUDA_ARCH__)
+    int d = (int)(threadIdx.x & 31u);
+    for (; d + 96 < D; d += 128) {
+        const Vals a = load(d), b = load(d + 32), c = load(d + 64), e = load(d + 96);
+        store(d, a); store(d + 32, b); store(d + 64, c); store(d + 96, e);
+    }
+    for (; d < D; d += 32) { const Vals a = load(d); store(d, a); }
+#else
+    for (int d = 0; d < D; ++d) { const Vals a = load(d); store(d, a); }
+#endif
+}
+template <class Fn>
+B2_HD float lane_sum_wide(int D, Fn f) {
+#if defined(__CUDA_ARCH__)
+    float p = 0.0f;
+    int d = (int)(threadIdx.x & 31u);
+    for (; d + 96 < D; d += 128) {
+        const float a = f(d), b = f(d + 32), c = f(d + 64), e = f(d + 96);
+        p = p + a; p = p + b; p = p + c; p = p + e;
+    }
+    for (; d < D; d += 32) p = p + f(d);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) p = p + __shfl_xor_sync(0xFFFFFFFFu, p, off);
+    return p;
+#else
+    return lane_sum(D, f);
+#endif
+}
+template <class Fn>
+B2_HD void lane_sum2_wide(int D, Fn f, float& out0, float& out1) {
+#if defined(__CUDA_ARCH__)
+    float p0 = 0.0f, p1 = 0.0f;
+    int d = (int)(threadIdx.x & 31u);
+    for (; d + 96 < D; d += 128) {
+        float a0, b0, a1, b1, a2, b2, a3, b3;
+        f(d, a0, b0); f(d + 32, a1, b1); f(d + 64, a2, b2); f(d + 96, a3, b3);
+        p0 = p0 + a0; p1 = p1 + b0; p0 = p0 + a1; p1 = p1 + b1; p0 = p0 + a2; p1 = p1 + b2; p0 = p0 + a3; p1 = p1 + b3;
+    }
+    for (; d < D; d += 32) { float a, b; f(d, a, b); p0 = p0 + a; p1 = p1 + b; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        p0 = p0 + __shfl_xor_sync(0xFFFFFFFFu, p0, off);
+        p1 = p1 + __shfl_xor_sync(0xFFFFFFFFu, p1, off);
+    }
+    out0 = p0; out1 = p1;
+#else
+    lane_sum2(D, f, out0, out1);
+#endif
+}
+
 // lane-wide "any": a per-lane flag OR-reduced over the lanes owning d in [0, D)
 template <class Fn>
 B2_HD bool lane_any(int D, Fn f) {

@@ -514,11 +514,14 @@ static __global__ void __launch_bounds__(128) k_gemm_tick(GemmParams gp, const G
             __syncwarp(); lane_sync();
         }
         float u;
+        const long long tq0 = clock64();
         glm_finish(fam, cv.v(V_ZS), nll, gb, u, g);
         __syncwarp(); lane_sync();
+        const long long tq1 = clock64();
         t.advance(u, g);
         __syncwarp(); lane_sync();               // the betas below are gathered across lanes from V_ZS
         if ((threadIdx.x & 31) == 0) ctl[chain] = c;
+        if (chain == 0 && (threadIdx.x & 31) == 0) { sched->dbg[6] += (unsigned long long)(tq1 - tq0); sched->dbg[7] += (unsigned long long)(clock64() - tq1); }
     }
     if (c.phase != PH_DONE) {
         gemm_write_betas(fam, cv.v(V_ZS), bimg, gp.KB, chain);

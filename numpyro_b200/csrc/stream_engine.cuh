@@ -98,7 +98,8 @@ struct StreamSync { unsigned int abort_flag, pad_[3]; unsigned long long passes;
                     unsigned long long tick_sum[kMaxStreamChains], tick_max[kMaxStreamChains], tick_lap[kMaxStreamChains][4];
                     unsigned int pre_hit[kMaxStreamChains][4], pre_miss[kMaxStreamChains][4];
                     unsigned long long laps[32];
-                    unsigned int peek_hit[kMaxStreamChains], peek_fallback[kMaxStreamChains], peek_mismatch[kMaxStreamChains]; };     // -DB2_TICK_LAPS builds only: [i] cycles, [16 + i] occurrences   // per owner CTA: tick cycles, look-ahead hits
+                    unsigned int peek_hit[kMaxStreamChains], peek_fallback[kMaxStreamChains], peek_mismatch[kMaxStreamChains];
+                    unsigned long long cta_lap[160][4]; };     // per CTA: wait for betas, sweep, CTA reduction + publish, poll + sum     // -DB2_TICK_LAPS builds only: [i] cycles, [16 + i] occurrences   // per owner CTA: tick cycles, look-ahead hits
 
 struct StreamParams {
     TickCfg cfg; FamilySpec fam; OutBufs out;
@@ -701,7 +702,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
     // A warp with no tiles still owns its (empty) slot 0 as reduction scratch; the others use the slot they drained last.
     int red_slot = 0, red_tile = -1;
 
-    const bool dbg = (cta == 0 && ctid == 0);
+    const bool dbg = (ctid == 0);
     // (lap state lives in shared memory -- tdbg[14] last lap, tdbg[15] start -- so that it costs no registers in the sweep)
     if (dbg) { tdbg[14] = (unsigned long long)clock64(); tdbg[15] = tdbg[14]; }
 #define B2_DBG_LAP(k) do { if (dbg) { const unsigned long long t_now = (unsigned long long)clock64(); tdbg[k] += t_now - tdbg[14]; tdbg[14] = t_now; } } while (0)
@@ -996,6 +997,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
             p.vecs[((size_t)f * p.C + cta) * p.Dp + d] = cvecs[i];
         }
     }
+    if (ctid == 0 && cta < 160) { sy->cta_lap[cta][0] = tdbg[0]; sy->cta_lap[cta][1] = tdbg[1]; sy->cta_lap[cta][2] = tdbg[2]; sy->cta_lap[cta][3] = tdbg[4]; }
     if (cta == 0 && ctid == 0) {
         sy->passes = pass;
         tdbg[5] = (unsigned long long)clock64() - tdbg[15];

@@ -119,17 +119,19 @@ B2_HD bool key_is(const uint32_t* p, Key k) { return p[0] == k.a && p[1] == k.b;
 B2_HD float clip_max1(float p) { return (p > 1.0f) ? 1.0f : p; }      // jnp.clip(p, None, 1): NaN kept
 
 B2_HD float kinetic(int D, const float* imm, const float* r) {
+    if (D > 64) return 0.5f * lane_sum_wide(D, [&](int d) { return (imm[d] * r[d]) * r[d]; });
     return 0.5f * lane_sum(D, [&](int d) { return (imm[d] * r[d]) * r[d]; });
 }
 
 // hmc_util.py:710-746
 B2_HD bool is_turning(int D, const float* imm, const float* r_left, const float* r_right, const float* r_sum) {
     float l, r;
-    lane_sum2(D, [&](int d, float& a, float& b) {
+    auto f = [&](int d, float& a, float& b) {
         const float s = r_sum[d] - (r_left[d] + r_right[d]) / 2.0f;
         a = (imm[d] * r_left[d]) * s;
         b = (imm[d] * r_right[d]) * s;
-    }, l, r);
+    };
+    if (D > 64) lane_sum2_wide(D, f, l, r); else lane_sum2(D, f, l, r);
     return (l <= 0.0f) || (r <= 0.0f);
 }
 
@@ -137,6 +139,11 @@ B2_HD bool is_turning(int D, const float* imm, const float* r_left, const float*
 B2_HD void leap_begin(int D, float eps, const float* imm, const float* z, const float* r, const float* g,
                       float* z_out, float* r_half_out) {
     const float half = 0.5f * eps;
+    if (D > 64) {
+        for_d_wide(D, [&](int d) { Vals v; v.x[0] = r[d]; v.x[1] = g[d]; v.x[2] = z[d]; v.x[3] = imm[d]; return v; },
+                   [&](int d, const Vals& v) { const float rh = v.x[0] - half * v.x[1]; r_half_out[d] = rh; z_out[d] = v.x[2] + eps * (v.x[3] * rh); });
+        return;
+    }
     B2_FOR_D(d, D) {
         const float rh = r[d] - half * g[d];
         r_half_out[d] = rh;
@@ -227,6 +234,7 @@ struct TickT {
 
     B2_HD void copy(int dst, int src) const {
         float* a = v(dst); const float* b = v(src);
+        if (cfg.D > 64) { for_d_wide(cfg.D, [&](int d) { Vals x; x.x[0] = b[d]; return x; }, [&](int d, const Vals& x) { a[d] = x.x[0]; }); return; }
         B2_FOR_D(d, cfg.D) a[d] = b[d];
     }
 
@@ -722,7 +730,9 @@ struct TickT {
         const float* imm = v(V_IMM);
         float *zs = v(V_ZS), *rs = v(V_RS), *gs = v(V_GS);
         B2_LAPQ(-1);
-        B2_FOR_D(d, Dn) { const float gg = g[d]; gs[d] = gg; rs[d] = rs[d] - half * gg; }
+        for_d_wide(Dn, [&](int d) { Vals x; x.x[0] = g[d]; x.x[1] = rs[d]; return x; },
+                   [&](int d, const Vals& x) { gs[d] = x.x[0]; rs[d] = x.x[1] - half * x.x[0]; });
+        lane_sync();
         c.total_leapfrogs += 1ull;
         // _build_basetree (hmc_util.py:866-875)
         const float energy_new = u + kin(rs);
@@ -740,17 +750,20 @@ struct TickT {
         const int leaf_idx = c.n_sub;
         float *zps = v(V_ZPS), *gps = v(V_GPS), *rsum_s = v(V_RSUMS);
         if (leaf_idx == 0) {
-            B2_FOR_D(d, Dn) { zps[d] = zs[d]; gps[d] = gs[d]; rsum_s[d] = rs[d]; }
+            for_d_wide(Dn, [&](int d) { Vals x; x.x[0] = zs[d]; x.x[1] = gs[d]; x.x[2] = rs[d]; return x; },
+                       [&](int d, const Vals& x) { zps[d] = x.x[0]; gps[d] = x.x[1]; rsum_s[d] = x.x[2]; });
             c.sub_prop_pe = u; c.sub_prop_energy = energy_new;
             c.sub_weight = leaf_w; c.sub_sum_acc = leaf_acc;
         } else {                                                   // _combine_tree, uniform kernel
             const float p = d_expit(leaf_w - c.sub_weight);
             const bool take = u_leaf < p;
             if (take) {
-                B2_FOR_D(d, Dn) { zps[d] = zs[d]; gps[d] = gs[d]; }
+                for_d_wide(Dn, [&](int d) { Vals x; x.x[0] = zs[d]; x.x[1] = gs[d]; return x; },
+                           [&](int d, const Vals& x) { zps[d] = x.x[0]; gps[d] = x.x[1]; });
                 c.sub_prop_pe = u; c.sub_prop_energy = energy_new;
             }
-            B2_FOR_D(d, Dn) rsum_s[d] = rsum_s[d] + rs[d];
+            for_d_wide(Dn, [&](int d) { Vals x; x.x[0] = rsum_s[d]; x.x[1] = rs[d]; return x; },
+                       [&](int d, const Vals& x) { rsum_s[d] = x.x[0] + x.x[1]; });
             c.sub_weight = d_logaddexp(c.sub_weight, leaf_w);
             c.sub_sum_acc = c.sub_sum_acc + leaf_acc;
         }
@@ -763,7 +776,8 @@ struct TickT {
         const int idx_min = idx_max - popc32((~n & (n + 1u)) - 1u) + 1;
         if ((leaf_idx & 1) == 0) {
             float* cr = v(V_CKPT_R + idx_max); float* cs = v(V_CKPT_RSUM + idx_max);
-            B2_FOR_D(d, Dn) { cr[d] = rs[d]; cs[d] = rsum_s[d]; }
+            for_d_wide(Dn, [&](int d) { Vals x; x.x[0] = rs[d]; x.x[1] = rsum_s[d]; return x; },
+                       [&](int d, const Vals& x) { cr[d] = x.x[0]; cs[d] = x.x[1]; });
         }
         bool sub_turning = false;
         if (dense_on() && idx_max >= idx_min) matvec(dmat(0), rs, v(V_TMP1));          // M^-1 r of the new leaf, once
@@ -780,7 +794,7 @@ struct TickT {
                     b = vr[d] * s;
                 }, l, r);
             } else
-            lane_sum2(Dn, [&](int d, float& a, float& b) {
+            lane_sum2_wide(Dn, [&](int d, float& a, float& b) {
                 const float sub = (rsum_s[d] - cs[d]) + cr[d];
                 const float s = sub - (cr[d] + rs[d]) / 2.0f;
                 a = (imm[d] * cr[d]) * s;
@@ -843,7 +857,8 @@ struct TickT {
         } else
 #endif
         {
-            B2_FOR_D(d, Dn) { zo[d] = zs[d]; ro[d] = rs[d]; go[d] = gs[d]; rsum[d] = rsum[d] + rsum_s[d]; }
+            for_d_wide(Dn, [&](int d) { Vals x; x.x[0] = zs[d]; x.x[1] = rs[d]; x.x[2] = gs[d]; x.x[3] = rsum[d]; x.x[4] = rsum_s[d]; return x; },
+                       [&](int d, const Vals& x) { zo[d] = x.x[0]; ro[d] = x.x[1]; go[d] = x.x[2]; rsum[d] = x.x[3] + x.x[4]; });
             lane_sync();
             turning = sub_turning || turning_between(v(V_RL), v(V_RR), rsum);
         }

@@ -18,7 +18,7 @@ e.init(prng.split(prng.key(1), C), W)
 os.environ.pop("B200NUTS_DEBUG_TICK", None)
 e.run(W, W, fields=())
 torch.cuda.synchronize()
-os.environ["B200NUTS_DEBUG_TICK"] = "1"
+os.environ["B200NUTS_DEBUG_TICK"] = "1"; os.environ["B200NUTS_DEBUG_CTA"] = "1"
 p0 = e.pass_count
 t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
 t0.record(); out = e.run(W + 200, W, fields=("num_steps",)); t1.record(); torch.cuda.synchronize()
