@@ -68,8 +68,11 @@ constexpr int kTileRows = 16;            // rows per ring slot = one consumer wa
 constexpr int kMaxStages = 4;            // tile slots per consumer warp (4: tiles are consumed in pairs)
 constexpr int kGStride = 72;             // floats per (cta, chain) partial: gbeta[<=64], nll, pad
 constexpr int kRedWarps = (kConsWarps + 1) / 2;   // rows of the two-stage CTA reduction scratch
-constexpr int kXSeg = 7;                 // segments of the cross-CTA reduction (7 x 65 threads)
-constexpr int kXRedFloats = kXSeg * kGStride + 192;   // owner CTA: segment sums + gradient scratch for the tick
+constexpr int kXSeg = 25;                // segments of the cross-CTA reduction, at most (each adds a contiguous range of CTAs)
+constexpr int kXStride = 66;             // floats per segment / per chain of the packed outputs (3 per 16-byte word, <= 22 words)
+constexpr int kXScratch = kXSeg * kXStride;           // offset of the tick's gradient scratch behind the segment sums
+constexpr int kXRedFloats = kXScratch + 192;          // owner CTA: segment sums + gradient scratch for the tick
+constexpr int kGWords = 24;              // 16-byte words per (cta, chain) partial: {v0, v1, v2, tag}; output e = column e, e = 8 KS: nll
 constexpr int kBarBeta = 1, kBarCons = 2, kBarTick = 3;
 constexpr int kBetaCopies = 4;           // replicas of the published beta (CTA c fetches replica c mod 4)
 constexpr int kBetaWords = 8 * kStreamCT * 4;     // 16-byte words per replica: [k-step][chain][t]
@@ -161,14 +164,38 @@ B2_D bool mbar_wait_bounded(uint64_t* bar, uint32_t parity, long long limit, uns
     }
     return true;
 }
+// ... for the sweep: the abort flag's address and the limit are looked up on the slow path only (no registers held for them)
+B2_D bool mbar_wait_p(uint64_t* bar, uint32_t parity, const unsigned int* const* syncp) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
+    unsigned int it = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++it & 255u) == 0u) {
+            unsigned int* af = const_cast<unsigned int*>(*syncp);
+            if (*(volatile unsigned int*)af) return false;
+            if (clock64() - t0 > 2000000000LL) { atomicCAS(af, 0u, 1u); return false; }
+        }
+    }
+    return true;
+}
 B2_D void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// Polling loads of the on-device exchange (partials, betas): relaxed, GPU scope (one 8- / 16-byte access: value and tag arrive
+// together).  System scope is only needed for the peer mailboxes of a row-sharded handle (ld_sys_v2).
+// 16-byte asynchronous copy global -> shared, L2 only (.cg): the data never occupies a register
+B2_D void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+B2_D void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 B2_D uint4 ld_volatile_v4(const uint4* p) {
-    uint4 v; asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); return v;
+    uint4 v; asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); return v;
 }
 B2_D float2 ld_volatile_v2(const float2* p) {
+    float2 v; asm volatile("ld.relaxed.gpu.global.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory"); return v;
+}
+B2_D float2 ld_sys_v2(const float2* p) {
     float2 v; asm volatile("ld.volatile.global.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory"); return v;
 }
 B2_D void st_sys_v2(float2* p, float2 v) {      // one 8-byte store, visible to peer GPUs (value and tag travel together)
@@ -247,12 +274,19 @@ B2_D bool spin_ge(const unsigned int* ctr, unsigned int target, StreamSync* sy, 
 
 #define B2_TRACE_LANES(stage) do { if (lane == 0) B2_TRACE(1, stage); if (lane == 16) B2_TRACE(4, stage); if (lane == 31) B2_TRACE(5, stage); } while (0)
 
-B2_HD size_t stream_fixed_smem(int Dp, bool vecs_in_smem, bool multi_group) {
+// Shared-memory layout: the fixed-size regions come FIRST (compile-time offsets: their addresses cost no registers in the
+// sweep), then the tile ring (its size depends on the ring depth), then the chain vectors.
+B2_HD constexpr size_t stream_head_smem(bool multi_group) {
     size_t b = 0;
     b += (size_t)kConsWarps * kMaxStages * 8;                      // mbarriers
     b += (size_t)(multi_group ? 2 : 1) * kBetaWords * 16;          // staged beta (two passes with several groups), [k-step][chain][t] {b0, tag, b1, tag}
     b += (size_t)kXRedFloats * 4;                                  // cross-CTA reduction + tick scratch
     b += 64 * 4 + 64 * 4 + 256 + 128;                              // gred(+nll), flags, timers
+    b += (size_t)kStreamCT * kXStride * 4;                         // this CTA's reduced outputs on their way to the packed partial
+    return (b + 127) / 128 * 128;
+}
+B2_HD size_t stream_fixed_smem(int Dp, bool vecs_in_smem, bool multi_group) {
+    size_t b = stream_head_smem(multi_group);
     if (vecs_in_smem) b += (size_t)V_COUNT * Dp * 4;
     return b + 128;
 }
@@ -354,11 +388,442 @@ __device__ __forceinline__ bool stream_tick_deferred(const StreamParams& p, Stre
     return tk.c.phase == PH_DONE;
 }
 
+// Byte offsets of the fixed shared-memory regions (see stream_head_smem)
+template <bool MG> struct StreamSmem {
+    static constexpr size_t kFull = 0;
+    static constexpr size_t kBs = kFull + (size_t)kConsWarps * kMaxStages * 8;
+    static constexpr size_t kXred = kBs + (size_t)(MG ? 2 : 1) * kBetaWords * 16;
+    static constexpr size_t kGred = kXred + (size_t)kXRedFloats * 4;
+    static constexpr size_t kPout = kGred + 64 * 4 + 64 * 4;
+    static constexpr size_t kFlags = kPout + (size_t)kStreamCT * kXStride * 4;
+    static constexpr size_t kTdbg = kFlags + 256;
+    static constexpr size_t kTiles = stream_head_smem(MG);
+    static_assert(kTdbg + 128 <= kTiles, "fixed regions overlap the tile ring");
+};
+// column of X behind n index `n` of backward N-tile `nt` (see the kernel's backward MMAs)
+template <int KS> B2_D int stream_bwd_col(int nt, int n) {
+    return ((KS & 1) && nt == KS - 1) ? 16 * (KS / 2) + n : 16 * (nt >> 1) + 2 * n + (nt & 1);
+}
+
+// Exchange, step 1 (every CTA, consumer warps): the 15 warps' accumulators sit in their reduction scratch slots; add them in
+// warp order, publish the CTA's partial.  Out of line on purpose, like stream_gather below: the register needs of the exchange
+// must not leak into the allocation of the sweep loop (ptxas spilled inside the MMA region when this was inlined).
+template <int KS, bool MG>
+__device__ __noinline__ void stream_reduce_publish(const StreamParams& p, int nst, int grp, uint32_t tag) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using L = StreamSmem<MG>;
+    constexpr int SLOT_FLOATS = stream_slot_floats(KS);
+    constexpr int NOUT = 8 * KS + 1, NW = (NOUT + 2) / 3;
+    const float* tiles = (const float*)(smem_raw + L::kTiles);
+    const int* flags = (const int*)(smem_raw + L::kFlags);
+    float* pout = (float*)(smem_raw + L::kPout);
+    const int ctid = threadIdx.x, cta = blockIdx.x;
+    const int NGRP = MG ? p.num_groups : 1;
+    bar_sync<kBarCons, kConsThreads>();
+    {
+        // thread i adds scratch word i = (value k, lane l) of the 15 warps in warp order (conflict-free: consecutive threads read
+        // consecutive words) and knows where the sum belongs: value k = 2 nt + e of lane l = 4 c + (n >> 1) is (chain c, column
+        // bwd_col(nt, n)) with n = 2 (l & 3) + e; values 16 + e of lanes 0..3 are the nll of chains 2 l + e (output 8 KS).
+        int rs[kConsWarps];
+#pragma unroll
+        for (int w = 0; w < kConsWarps; ++w) rs[w] = (w * nst + flags[16 + w]) * SLOT_FLOATS;
+        for (int i = ctid; i < 18 * 32; i += kConsThreads) {
+            const int k = i >> 5, l = i & 31;
+            int c = -1, e = 8 * KS;
+            if (k < 2 * KS) { c = l >> 2; e = stream_bwd_col<KS>(k >> 1, 2 * (l & 3) + (k & 1)); }
+            else if (k >= 16 && l < 4) c = 2 * l + (k & 1);
+            if (c >= 0) {
+                float a = 0.0f;
+#pragma unroll
+                for (int w = 0; w < kConsWarps; ++w) a += tiles[rs[w] + i];
+                pout[c * kXStride + e] = a;
+            }
+        }
+    }
+    bar_sync<kBarCons, kConsThreads>();          // every scratch slot has been read (the caller refills them); the CTA's sums are in pout
+    // publish: three outputs and the tag per 16-byte word (one store: a reader that sees the tag sees the values next to it)
+    if (ctid < kStreamCT * NW) {
+        const int c = ctid / NW, w = ctid - c * NW;
+        const float* src = pout + c * kXStride + 3 * w;
+        __stcg(reinterpret_cast<float4*>(p.partial) + (((size_t)cta * NGRP + grp) * kStreamCT + c) * kGWords + w,
+               make_float4(src[0], src[1], src[2], __uint_as_float(tag)));
+    }
+}
+
+// Exchange, step 2 (chain owners, consumer warps): poll the partials of all CTAs, add them in fixed order, leave the sums in gred.
+template <int KS, bool MG>
+__device__ __noinline__ void stream_gather(const StreamParams& p, int ggrp, uint32_t gtag) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using L = StreamSmem<MG>;
+    constexpr int NOUT = 8 * KS + 1, NW = (NOUT + 2) / 3;
+    float* xred = (float*)(smem_raw + L::kXred);
+    float* gred = (float*)(smem_raw + L::kGred);
+    unsigned long long* tdbg = (unsigned long long*)(smem_raw + L::kTdbg);
+    const int ctid = threadIdx.x, cta = blockIdx.x, G = gridDim.x;
+    const int NGRP = MG ? p.num_groups : 1;
+    const bool dbg = (ctid == 0);
+    StreamSync* sy = p.sync;
+    // kXSeg segments x NW words: thread (seg, w) adds word w of its segment's CTAs in ascending order.  All loads of a
+    // batch are in flight together (L2 latency overlapped); only the entries that were still stale are polled again
+    // (the owner SM's load path moves about one 32-byte sector per cycle: a full round costs thousands of cycles).
+    constexpr int SEGS = (kConsThreads / NW < kXSeg) ? kConsThreads / NW : kXSeg;   // (few loads per thread: few registers)
+    constexpr int NB = (148 + SEGS - 1) / SEGS;
+    const int seg = ctid / NW, w = ctid - seg * NW;
+    if (seg < SEGS) {
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+        const int g0 = G * seg / SEGS, g1 = G * (seg + 1) / SEGS;
+        const uint4* src = reinterpret_cast<const uint4*>(p.partial) + ((size_t)ggrp * kStreamCT + (MG ? cta % kStreamCT : cta)) * kGWords + w;
+        const size_t cta_stride = (size_t)NGRP * kStreamCT * kGWords;
+        const long long t_w = clock64();
+        for (int gg = g0; gg < g1; gg += NB) {
+            uint4 v[NB];
+            const int nb = (g1 - gg < NB) ? (g1 - gg) : NB;
+            const unsigned want = (1u << nb) - 1u;
+            unsigned ready = 0u;
+            while (true) {
+#pragma unroll
+                for (int k = 0; k < NB; ++k) {
+                    if (k < nb && !((ready >> k) & 1u)) {
+                        v[k] = ld_volatile_v4(src + (size_t)(gg + k) * cta_stride);
+                        if (v[k].w == gtag) ready |= 1u << k;
+                    }
+                }
+                if (dbg) tdbg[3] += 1ull;                 // (poll rounds of thread 0)
+                if (ready == want) break;
+                if (ld_acquire(&sy->abort_flag)) break;
+                if (clock64() - t_w > p.spin_limit) { atomicCAS(&sy->abort_flag, 0u, 3u); break; }
+            }
+#pragma unroll
+            for (int k = 0; k < NB; ++k)
+                if (k < nb) { a0 += __uint_as_float(v[k].x); a1 += __uint_as_float(v[k].y); a2 += __uint_as_float(v[k].z); }
+        }
+        if (dbg) tdbg[12] += (unsigned long long)(clock64() - t_w);
+        float* dst = xred + seg * kXStride + 3 * w;
+        dst[0] = a0; dst[1] = a1; dst[2] = a2;
+    }
+    bar_sync<kBarCons, kConsThreads>();      // the segment sums are in xred: join them in segment order
+    if (dbg) tdbg[13] += (unsigned long long)clock64() - tdbg[14];
+    if (ctid < NOUT) {
+        float a = xred[ctid];
+#pragma unroll
+        for (int sgm = 1; sgm < SEGS; ++sgm) a += xred[sgm * kXStride + ctid];
+        gred[ctid < 8 * KS ? ctid : 64] = a;
+    }
+    __threadfence_block();
+}
+
+// Single chain group: the same gather with the polled words landing in shared memory (cp.async into the reduction scratch slot
+// this warp has just drained -- the owner CTAs refill that slot after the gather) instead of registers: a register-hungry
+// out-of-line function costs the caller registers EVERYWHERE (ptxas moved spills into the sweep's MMA region).
+template <int KS>
+__device__ __noinline__ void stream_gather_land(const StreamParams& p, uint32_t gtag, float* land) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using L = StreamSmem<false>;
+    constexpr int NOUT = 8 * KS + 1, NW = (NOUT + 2) / 3;
+    constexpr int SEGS = (kConsThreads / NW < kXSeg) ? kConsThreads / NW : kXSeg;
+    constexpr int NBW = (148 + SEGS - 1) / SEGS, NBS = stream_slot_floats(KS) * 4 / 512;   // words per thread: wanted / that fit
+    constexpr int NB = NBW < NBS ? NBW : NBS;
+    float* xred = (float*)(smem_raw + L::kXred);
+    float* gred = (float*)(smem_raw + L::kGred);
+    unsigned long long* tdbg = (unsigned long long*)(smem_raw + L::kTdbg);
+    const int ctid = threadIdx.x, lane = ctid & 31, cta = blockIdx.x, G = gridDim.x;
+    const bool dbg = (ctid == 0);
+    const int seg = ctid / NW, w = ctid - seg * NW;
+    uint4* mine = reinterpret_cast<uint4*>(land) + lane;            // word k of this lane: mine[32 k] (conflict-free)
+    if (seg < SEGS) {
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+        const int g0 = G * seg / SEGS, g1 = G * (seg + 1) / SEGS;
+        const uint4* src = reinterpret_cast<const uint4*>(p.partial) + (size_t)cta * kGWords + w;
+        constexpr size_t cta_stride = (size_t)kStreamCT * kGWords;
+        const long long t_w = clock64();
+        for (int gg = g0; gg < g1; gg += NB) {
+            const int nb = (g1 - gg < NB) ? (g1 - gg) : NB;
+            const unsigned want = (1u << nb) - 1u;
+            unsigned ready = 0u;
+            while (true) {
+#pragma unroll
+                for (int k = 0; k < NB; ++k)
+                    if (k < nb && !((ready >> k) & 1u)) cp_async16(mine + 32 * k, src + (size_t)(gg + k) * cta_stride);
+                cp_async_wait_all();
+#pragma unroll
+                for (int k = 0; k < NB; ++k)
+                    if (k < nb && !((ready >> k) & 1u) && reinterpret_cast<const volatile unsigned int*>(mine + 32 * k)[3] == gtag) ready |= 1u << k;
+                if (dbg) tdbg[3] += 1ull;                 // (poll rounds of thread 0)
+                if (ready == want) break;
+                if (ld_acquire(&p.sync->abort_flag)) break;
+                if (clock64() - t_w > p.spin_limit) { atomicCAS(&p.sync->abort_flag, 0u, 3u); break; }
+            }
+#pragma unroll
+            for (int k = 0; k < NB; ++k)
+                if (k < nb) { const uint4 v = mine[32 * k]; a0 += __uint_as_float(v.x); a1 += __uint_as_float(v.y); a2 += __uint_as_float(v.z); }
+        }
+        if (dbg) tdbg[12] += (unsigned long long)(clock64() - t_w);
+        float* dst = xred + seg * kXStride + 3 * w;
+        dst[0] = a0; dst[1] = a1; dst[2] = a2;
+    }
+    bar_sync<kBarCons, kConsThreads>();      // the segment sums are in xred: join them in segment order
+    if (dbg) tdbg[13] += (unsigned long long)clock64() - tdbg[14];
+    if (ctid < NOUT) {
+        float a = xred[ctid];
+#pragma unroll
+        for (int sgm = 1; sgm < SEGS; ++sgm) a += xred[sgm * kXStride + ctid];
+        gred[ctid < 8 * KS ? ctid : 64] = a;
+    }
+    __threadfence_block();
+}
+
 struct StreamOne { static constexpr int value = 1; };
 struct StreamTwo { static constexpr int value = 2; };
 
 // KS = columns / 8 of the padded tile (compile time so every fragment stays in registers), LIK = likelihood.
 // MG = several chain groups (more than 8 chains); with MG = false everything group-related folds to constants.
+// (lap state lives in shared memory -- tdbg[14] last lap, tdbg[15] start -- so that it costs no registers in the sweep)
+#define B2_DBG_LAP(k) do { if (dbg) { const unsigned long long t_now = (unsigned long long)clock64(); tdbg[k] += t_now - tdbg[14]; tdbg[14] = t_now; } } while (0)
+
+// One pass of one consumer warp: beta fragments, the sweep over the warp's tiles, accumulators into the warp's reduction
+// scratch slot.  Out of line on purpose: the sweep gets a register allocation of its own (inlined into the kernel, ptxas let
+// unrelated code -- the exchange, the tick warp -- push spills into the MMA region).  `ring` = slot | parity << 2 of the next
+// tile to consume; returns the new ring position | red_slot << 3 | (red_tile + 1) << 5.
+template <int KS, int LIK, bool MG>
+__device__ __forceinline__ uint32_t stream_sweep(const StreamParams& p, uint32_t ring, unsigned int pass) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using L = StreamSmem<MG>;
+    constexpr int P = stream_pitch(KS);            // row pitch of a tile, floats
+    constexpr int TILE_FLOATS = stream_tile_floats(KS);   // floats moved per tile
+    constexpr int SLOT_FLOATS = stream_slot_floats(KS);   // ring slot stride
+    constexpr int NCH = KS / 2;                    // backward: 16-column chunks (two 8-column MMAs per 128-bit load)
+    constexpr bool ODD = (KS & 1) != 0;            // ... + one 8-column chunk (64-bit loads) when KS is odd
+    // (volatile reads: everything derived from them is recomputed per pass and dies with the sweep -- nothing the sweep needs
+    //  stays live across the exchange that follows it, and nothing of the exchange reaches into the sweep's registers)
+    int tid, cta;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(cta));
+    const int cw = tid >> 5, lane = tid & 31, ctid = tid;
+    const int G = gridDim.x;
+    const int nst = p.stages;
+    uint64_t* full = (uint64_t*)(smem_raw + L::kFull);
+    const uint4* bs = (const uint4*)(smem_raw + L::kBs);
+    int* flags = (int*)(smem_raw + L::kFlags);
+    unsigned long long* tdbg = (unsigned long long*)(smem_raw + L::kTdbg);
+    float* tiles = (float*)(smem_raw + L::kTiles);
+    // (StreamSync starts with abort_flag: &p.sync, read through the parameter, is all the bounded waits need)
+    const unsigned int* const* syncp = reinterpret_cast<const unsigned int* const*>(&p.sync);
+#ifdef B2_STREAM_SWEEP_KNOBS
+    constexpr bool kKnobs = true;                  // timing experiments (B200NUTS_DEBUG_SWEEP / _WARPS): copies only, compute only
+#else
+    constexpr bool kKnobs = false;
+#endif
+    const long long t_begin_tile = p.n_tiles * cta / G, t_end_tile = p.n_tiles * (cta + 1) / G;
+    const int n_tiles = (int)(t_end_tile - t_begin_tile);
+    const bool dbg = (ctid == 0);
+    const int g = lane >> 2, t = lane & 3;           // mma.sync fragment coordinates (groupID, threadID_in_group)
+    // float offsets inside a tile (stream_tile_index): forward lane (g, t) reads pair row g, columns
+    // 8kk + 2t, +1; backward lane (g, t) reads pair row 4ks + t, columns 16j + 2g, +1 (or 16*NCH + g)
+    const int off_f = g * 2 * P + 4 * (t ^ (((g >> 1) & 1) << 1));
+    const int off_b = t * 2 * P + 4 * (g ^ (((t >> 1) & 1) << 1));
+    const int off_b1 = t * 2 * P + 4 * (8 * NCH + ((g >> 1) ^ (((t >> 1) & 1) << 1))) + 2 * (g & 1);
+    const int src_ks0 = (t << 2) | (g >> 1), src_ks1 = ((4 + t) << 2) | (g >> 1);   // shuffle sources, see unit()
+    uint32_t bhi[KS][2], bbf[KS][2];                 // beta as B fragments of the forward MMAs: tf32 (raw fp32 bits; the
+                                                     // tensor core reads the top 19) and bf16x2 {hi part, lo part}
+    float gacc[KS][4];                               // gbeta^T in C-fragment layout: chain g, columns bwd_col(nt, 2t / 2t+1);
+                                                     // [0], [1] = r_hi part, [2], [3] = r_lo part
+    float nll[2] = {0.0f, 0.0f};                     // loss of chains 2t, 2t+1 over this lane's rows
+
+    const int n_mine = (n_tiles > cw) ? (n_tiles - cw + kConsWarps - 1) / kConsWarps : 0;
+    float* my_tiles = tiles + (size_t)cw * nst * SLOT_FLOATS;
+    uint64_t* my_full = full + cw * kMaxStages;
+    const unsigned int my_first = (unsigned int)(t_begin_tile + cw);       // first tile of this warp (the image address is formed at issue time)
+    auto issue = [&](int slot, int j) {              // one lane: tile j of this warp -> slot
+        mbar_expect_tx(&my_full[slot], TILE_FLOATS * 4u);
+        bulk_g2s(my_tiles + (size_t)slot * SLOT_FLOATS, p.img + (size_t)(my_first + (unsigned int)j * kConsWarps) * TILE_FLOATS, TILE_FLOATS * 4u, &my_full[slot]);
+    };
+    int slot = (int)(ring & 3u); uint32_t parity = (ring >> 2) & 1u;
+    const bool pairs = (nst == 4);                   // consume two tiles at a time (two independent instruction streams)
+    // A warp with no tiles still owns its (empty) slot 0 as reduction scratch; the others use the slot they drained last.
+    int red_slot = 0, red_tile = -1;
+
+    // NG 16-row tiles at once (NG = 1 or 2; with 2 the two tiles' instruction streams are independent and
+    // interleave).  Products are split-precision: x = xh + xl (xh = the 19 bits a TF32 MMA reads), likewise beta
+    // and r.  hi*hi runs as TF32 MMAs; the three small cross terms run as BF16 MMAs (k = 16), which is exact
+    // enough because each is already ~2^-11 of the main term (total relative error ~1e-6, fp32 accumulate).
+    auto unit = [&](auto ng_tag, const float* xa, const float* xb) {
+        constexpr int NG = decltype(ng_tag)::value;
+        constexpr int NC = (NG == 2) ? 1 : 2;        // accumulator chains per MMA kind and tile
+        const float* xt[2] = {xa, xb};
+        // ---- forward: logits
+        float acc[NG][2 * NC][4];
+#pragma unroll
+        for (int gi = 0; gi < NG; ++gi)
+#pragma unroll
+            for (int k = 0; k < 2 * NC; ++k) { acc[gi][k][0] = 0.0f; acc[gi][k][1] = 0.0f; acc[gi][k][2] = 0.0f; acc[gi][k][3] = 0.0f; }
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk) {
+#pragma unroll
+            for (int gi = 0; gi < NG; ++gi) {
+                // (row g, col c), (row g+8, c), (row g, c+1), (row g+8, c+1) with c = 8kk + 2t
+                const float4 v = *reinterpret_cast<const float4*>(xt[gi] + off_f + 16 * kk);
+                const uint32_t ar[4] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
+                mma_tf32(acc[gi][kk % NC], ar, bhi[kk][0], bhi[kk][1]);                      // xh * bh
+                // k = (2t, 2t+1): xl at columns (c, c+1);  k = (2t+8, 2t+9): x at columns (c, c+1)
+                float lx, ly, lz, lw;
+                tf32_lo2(v.x, v.y, lx, ly); tf32_lo2(v.z, v.w, lz, lw);
+                const uint32_t ab[4] = {pack_bf16(lx, lz), pack_bf16(ly, lw), pack_bf16(v.x, v.z), pack_bf16(v.y, v.w)};
+                mma_bf16(acc[gi][NC + kk % NC], ab, bbf[kk][0], bbf[kk][1]);                // xl * bh + x * bl
+            }
+        }
+        // ---- link: c0 (row g, chain 2t), c1 (g, 2t+1), c2 (g+8, 2t), c3 (g+8, 2t+1)
+        float dl[NG][4];
+#pragma unroll
+        for (int gi = 0; gi < NG; ++gi) {
+            const float2 yy = *reinterpret_cast<const float2*>(xt[gi] + kTileRows * P + 2 * g);    // y[row g], y[row g+8]
+            float ls[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float eta = acc[gi][0][i] + acc[gi][NC][i];
+                if (NC == 2) eta = (acc[gi][1][i] + acc[gi][3][i]) + eta;
+                link_fn<LIK>(eta, (i < 2) ? yy.x : yy.y, ls[i], dl[gi][i]);
+            }
+            nll[0] += ls[0] + ls[2]; nll[1] += ls[1] + ls[3];
+        }
+        // ---- residuals -> A fragments.  k-step ks covers pair rows 4ks..4ks+3; lane (g, t) needs
+        //      r[row 4ks+t][chain g] and r[row 4ks+t+8][chain g], held by lane (4ks+t, g>>1) of the C layout.
+        //      TF32: stacked A = [r_hi ; r_lo]^T: a0 = r_hi(low row), a1 = r_lo(low), a2 = r_hi(high), a3 = r_lo(high)
+        //      BF16 (k = 16 = both k-steps): a0 = {r(ks0 low), r(ks0 high)}, a2 = {r(ks1 low), r(ks1 high)}, a1 = a3 = 0
+        uint32_t ra[NG][2][4], rb[NG][4];
+#pragma unroll
+        for (int gi = 0; gi < NG; ++gi) {
+            rb[gi][1] = 0u; rb[gi][3] = 0u;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const int src = ks ? src_ks1 : src_ks0;
+                const float e0 = __shfl_sync(0xFFFFFFFFu, dl[gi][0], src), e1 = __shfl_sync(0xFFFFFFFFu, dl[gi][1], src);
+                const float o0 = __shfl_sync(0xFFFFFFFFu, dl[gi][2], src), o1 = __shfl_sync(0xFFFFFFFFu, dl[gi][3], src);
+                const float lo_row = (g & 1) ? e1 : e0, hi_row = (g & 1) ? o1 : o0;
+                ra[gi][ks][0] = __float_as_uint(lo_row); ra[gi][ks][1] = __float_as_uint(tf32_lo(lo_row));
+                ra[gi][ks][2] = __float_as_uint(hi_row); ra[gi][ks][3] = __float_as_uint(tf32_lo(hi_row));
+                rb[gi][2 * ks] = pack_bf16(lo_row, hi_row);
+            }
+        }
+        // ---- backward: gbeta^T[chain][col] += sum_rows r[row][chain] * x[row][col], 16 columns (2 MMAs wide) at a time
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            float ga[NG][2][4];
+#pragma unroll
+            for (int gi = 0; gi < NG; ++gi) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) { ga[gi][k][0] = 0.0f; ga[gi][k][1] = 0.0f; ga[gi][k][2] = 0.0f; ga[gi][k][3] = 0.0f; }
+                float xl[2][4];
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    // col c = 16j+2g: rows (4ks+t, +8); col c+1: rows (4ks+t, +8)
+                    const float4 v = *reinterpret_cast<const float4*>(xt[gi] + off_b + ks * 8 * P + 32 * j);
+                    mma_tf32(ga[gi][0], ra[gi][ks], __float_as_uint(v.x), __float_as_uint(v.y));   // [r_hi ; r_lo] * xh
+                    mma_tf32(ga[gi][1], ra[gi][ks], __float_as_uint(v.z), __float_as_uint(v.w));
+                    tf32_lo2(v.x, v.y, xl[ks][0], xl[ks][1]); tf32_lo2(v.z, v.w, xl[ks][2], xl[ks][3]);
+                }
+                mma_bf16(ga[gi][0], rb[gi], pack_bf16(xl[0][0], xl[0][1]), pack_bf16(xl[1][0], xl[1][1]));   // r * xl, 16 rows
+                mma_bf16(ga[gi][1], rb[gi], pack_bf16(xl[0][2], xl[0][3]), pack_bf16(xl[1][2], xl[1][3]));
+            }
+#pragma unroll
+            for (int gi = 0; gi < NG; ++gi)
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    add2f(gacc[2 * j + k][0], gacc[2 * j + k][1], ga[gi][k][0], ga[gi][k][1]);
+                    add2f(gacc[2 * j + k][2], gacc[2 * j + k][3], ga[gi][k][2], ga[gi][k][3]);
+                }
+        }
+        if (ODD) {
+            float ga[NG][4];
+#pragma unroll
+            for (int gi = 0; gi < NG; ++gi) {
+                ga[gi][0] = 0.0f; ga[gi][1] = 0.0f; ga[gi][2] = 0.0f; ga[gi][3] = 0.0f;
+                float xl[2][2];
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const float2 v = *reinterpret_cast<const float2*>(xt[gi] + off_b1 + ks * 8 * P);
+                    mma_tf32(ga[gi], ra[gi][ks], __float_as_uint(v.x), __float_as_uint(v.y));
+                    tf32_lo2(v.x, v.y, xl[ks][0], xl[ks][1]);
+                }
+                mma_bf16(ga[gi], rb[gi], pack_bf16(xl[0][0], xl[0][1]), pack_bf16(xl[1][0], xl[1][1]));
+            }
+#pragma unroll
+            for (int gi = 0; gi < NG; ++gi) {
+                add2f(gacc[KS - 1][0], gacc[KS - 1][1], ga[gi][0], ga[gi][1]);
+                add2f(gacc[KS - 1][2], gacc[KS - 1][3], ga[gi][2], ga[gi][3]);
+            }
+        }
+    };
+
+
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk) {                                   // beta -> B fragments (k = column, n = chain)
+        const uint4 w = bs[(size_t)(MG ? (pass & 1u) : 0u) * kBetaWords + (kk * kStreamCT + g) * 4 + t];
+        bhi[kk][0] = w.x; bhi[kk][1] = w.y;                             // staged pre-split by the tick warp
+        bbf[kk][0] = w.z;                                               // hi parts: pairs with xl (k = 2t, 2t+1)
+        bbf[kk][1] = w.w;                                               // lo parts: pairs with x  (k = 2t+8, 2t+9)
+    }
+#pragma unroll
+    for (int nt = 0; nt < KS; ++nt) { gacc[nt][0] = 0.0f; gacc[nt][1] = 0.0f; gacc[nt][2] = 0.0f; gacc[nt][3] = 0.0f; }
+    nll[0] = 0.0f; nll[1] = 0.0f;
+    if (ctid == 0) B2_DBG_LAP(7);
+
+    // ---- sweep: consume this warp's tiles in order (two at a time when the ring has 4 slots); a finished
+    //      slot is refilled at once with the tile `nst` positions further down the (cyclic) sequence
+    {
+        int j = 0, jn = nst % (n_mine > 0 ? n_mine : 1);                // jn = (j + nst) mod n_mine
+        while (j < n_mine) {
+            const int s0 = slot; const uint32_t p0 = parity;
+            if (++slot == nst) { slot = 0; parity ^= 1u; }
+            if (pairs && j + 1 < n_mine) {
+                const int s1 = slot; const uint32_t p1 = parity;
+                if (++slot == nst) { slot = 0; parity ^= 1u; }
+                if (!kKnobs || p.dbg_sweep != 2) { mbar_wait_p(&my_full[s0], p0, syncp); mbar_wait_p(&my_full[s1], p1, syncp); }
+                if (!kKnobs || (p.dbg_sweep != 1 && cw < p.dbg_warps)) unit(StreamTwo{}, my_tiles + (size_t)s0 * SLOT_FLOATS, my_tiles + (size_t)s1 * SLOT_FLOATS);
+                __syncwarp();
+                const bool last = (j + 2 >= n_mine);
+                if (lane == 0 && (!kKnobs || p.dbg_sweep != 2)) {
+                    issue(s0, jn); if (++jn == n_mine) jn = 0;
+                    if (!last) issue(s1, jn);
+                }
+                if (last) { red_slot = s1; red_tile = jn; }        // refilled after the CTA reduction below
+                if (++jn == n_mine) jn = 0;
+                j += 2;
+            } else {
+                if (!kKnobs || p.dbg_sweep != 2) mbar_wait_p(&my_full[s0], p0, syncp);
+                if (!kKnobs || (p.dbg_sweep != 1 && cw < p.dbg_warps)) unit(StreamOne{}, my_tiles + (size_t)s0 * SLOT_FLOATS, nullptr);
+                __syncwarp();
+                const bool last = (j + 1 >= n_mine);
+                if (lane == 0 && (!kKnobs || p.dbg_sweep != 2) && !last) issue(s0, jn);
+                if (last) { red_slot = s0; red_tile = jn; }
+                if (++jn == n_mine) jn = 0;
+                j += 1;
+            }
+        }
+    }
+    // ---- reduce warps -> CTA through the ring slot every warp drained last ([value][lane] floats, conflict
+    //      free), one barrier, fixed order => bit-reproducible; then publish {value, tag} pairs.
+    {
+        float val[16];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            val[2 * nt] = (nt < KS) ? gacc[nt < KS ? nt : 0][0] + gacc[nt < KS ? nt : 0][2] : 0.0f;
+            val[2 * nt + 1] = (nt < KS) ? gacc[nt < KS ? nt : 0][1] + gacc[nt < KS ? nt : 0][3] : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            nll[k] += __shfl_xor_sync(0xFFFFFFFFu, nll[k], 4);
+            nll[k] += __shfl_xor_sync(0xFFFFFFFFu, nll[k], 8);
+            nll[k] += __shfl_xor_sync(0xFFFFFFFFu, nll[k], 16);
+        }
+        float* scr = my_tiles + (size_t)red_slot * SLOT_FLOATS;      // >= 18 * 32 floats in every configuration
+#pragma unroll
+        for (int k = 0; k < 16; ++k) scr[k * 32 + lane] = val[k];
+        scr[16 * 32 + lane] = nll[0]; scr[17 * 32 + lane] = nll[1];
+        if (lane == 0) flags[16 + cw] = red_slot;
+    }
+    return (uint32_t)slot | (parity << 2) | ((uint32_t)red_slot << 3) | ((uint32_t)(red_tile + 1) << 5);
+}
+
 template <int KS, int LIK, bool MG>
 __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const __grid_constant__ StreamParams p) {
     const int NGRP = MG ? p.num_groups : 1;        // chain groups
@@ -376,16 +841,17 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
     const int nst = p.stages;
 
     // ---- carve shared memory
-    unsigned char* q = smem_raw;
-    float* tiles = (float*)q; q += (size_t)kConsWarps * nst * SLOT_FLOATS * 4;
-    uint64_t* full = (uint64_t*)q; q += (size_t)kConsWarps * kMaxStages * 8;
-    uint4* bs = (uint4*)q; q += (size_t)(MG ? 2 : 1) * kBetaWords * 16;
-    float* xred = (float*)q; q += (size_t)kXRedFloats * 4;
-    float* gred = (float*)q; q += 64 * 4 + 64 * 4;
-    int* flags = (int*)q; q += 256;                  // per pass parity: [0..1] 0 go / 1 all chains done / 2 abort, [2..3] chain group, [4..5] its round;
+    using L = StreamSmem<MG>;
+    uint64_t* full = (uint64_t*)(smem_raw + L::kFull);
+    uint4* bs = (uint4*)(smem_raw + L::kBs);
+    float* xred = (float*)(smem_raw + L::kXred);
+    float* gred = (float*)(smem_raw + L::kGred);
+    float* pout = (float*)(smem_raw + L::kPout);
+    int* flags = (int*)(smem_raw + L::kFlags);       // per pass parity: [0..1] 0 go / 1 all chains done / 2 abort, [2..3] chain group, [4..5] its round;
                                                      // [8] last pass begun by the consumers, [16..31] reduction slot of warp w, [32..51] rounds per group
-    unsigned long long* tdbg = (unsigned long long*)q; q += 128;
-    float* cvecs = (float*)q;
+    unsigned long long* tdbg = (unsigned long long*)(smem_raw + L::kTdbg);
+    float* tiles = (float*)(smem_raw + L::kTiles);
+    float* cvecs = tiles + (size_t)kConsWarps * nst * SLOT_FLOATS;
 
     // ---- this CTA's slice of tiles
     const long long t_begin_tile = p.n_tiles * cta / G, t_end_tile = p.n_tiles * (cta + 1) / G;
@@ -398,6 +864,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int i = 0; i < 16; ++i) tdbg[i] = 0ull;
         for (int i = 0; i < 64; ++i) flags[i] = 0;
+        for (int i = 0; i < 128; ++i) gred[i] = 0.0f;   // (columns 8 KS .. 63 are never written afterwards)
+        for (int i = 0; i < kStreamCT * kXStride; ++i) pout[i] = 0.0f;   // (nor are the pad outputs of a chain's last word)
         flags[8] = -1;                               // last pass the consumers have begun
     }
     ChainVecs cv; cv.base = nullptr; cv.field_stride = 0;
@@ -567,25 +1035,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                 //      state machine -> next beta (tag my_round + 1)
                 const uint32_t seq = my_round;
                 B2_TRACE_LANES(3);
-                bar_sync<kBarTick, kStreamThreads>();    // segment sums are in `xred`
+                bar_sync<kBarTick, kStreamThreads>();    // the sums over the CTAs' partials are in `gred`
                 B2_LAPQ(-1);
                 B2_TRACE_LANES(4);
                 const long long t_a = clock64();
-                // (uniform trip count + shuffle broadcast on purpose: ptxas 12.9 turned the __syncwarp() after the
-                //  lane-strided form of this loop -- lane 0 runs 3 iterations, the others 2 -- into a NOP and lanes
-                //  1..31 read last pass's gred[64]; gred[j] itself is only ever read back by the lane that wrote it)
-                float a64 = 0.0f;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int d = lane + 32 * k;
-                    if (d < 65) {
-                        float a = xred[d];
-#pragma unroll
-                        for (int sgm = 1; sgm < kXSeg; ++sgm) a += xred[sgm * kGStride + d];
-                        gred[d] = a;
-                        if (k == 2) a64 = a;
-                    }
-                }
+                float a64 = gred[64];                // (the consumers left the sums of the 148 partials in gred: columns, [64] = nll)
                 if (p.shard_count > 1) {
                     // ---- all-reduce over the row shards: store this rank's sums into every rank's mailbox, then add the
                     //      shard_count contributions of this chain in rank order (same order everywhere => identical bits)
@@ -605,7 +1059,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                             for (int sr = 0; sr < p.shard_count; ++sr) {
                                 float2 v;
                                 while (true) {
-                                    v = ld_volatile_v2(box + (size_t)sr * kGStride);
+                                    v = ld_sys_v2(box + (size_t)sr * kGStride);
                                     if (__float_as_uint(v.y) == xtag) break;
                                     if (ld_acquire(&sy->abort_flag)) break;
                                     if (clock64() - t_x > 16 * p.spin_limit) { atomicCAS(&sy->abort_flag, 0u, 4u); break; }
@@ -620,7 +1074,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                 const float nll = __shfl_sync(0xFFFFFFFFu, a64, 0) - (p.shard_count > 1 ? 0.0f : pad_nll);
                 if (lane == 0) tlap[3] += (unsigned long long)(clock64() - t_a);
                 B2_LAPQ(6);
-                float* gz = xred + kXSeg * kGStride; // scratch for the gradient wrt z (<= 64 floats when the early publish applies)
+                float* gz = xred + kXScratch; // scratch for the gradient wrt z (<= 64 floats when the early publish applies)
                 float* zpeek = gz + 64;              // ... and for the position published ahead of the tick (<= 64 floats)
                 bool early = false;
                 if (!chain_done) {
@@ -645,7 +1099,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
             if (tick_first) staged = stage();
             if (deferred) {                          // the bookkeeping of the tick whose next position already went out (also
                                                      // when the launch stops here: the chain must sit in front of that position)
-                chain_done = stream_tick_deferred(p, tk, xred + kXSeg * kGStride, xred + kXSeg * kGStride + 64, def_u, true, tdbg, peek_stat);
+                chain_done = stream_tick_deferred(p, tk, xred + kXScratch, xred + kXScratch + 64, def_u, true, tdbg, peek_stat);
                 deferred = false;
             }
             if (tick_first && staged == 2) break;
@@ -673,19 +1127,6 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
     // =============================================================== consumer warps
     const int cw = warp;                             // 0..14
     const int ctid = tid;                            // 0..479
-    const int g = lane >> 2, t = lane & 3;           // mma.sync fragment coordinates (groupID, threadID_in_group)
-    // float offsets inside a tile (stream_tile_index): forward lane (g, t) reads pair row g, columns
-    // 8kk + 2t, +1; backward lane (g, t) reads pair row 4ks + t, columns 16j + 2g, +1 (or 16*NCH + g)
-    const int off_f = g * 2 * P + 4 * (t ^ (((g >> 1) & 1) << 1));
-    const int off_b = t * 2 * P + 4 * (g ^ (((t >> 1) & 1) << 1));
-    const int off_b1 = t * 2 * P + 4 * (8 * NCH + ((g >> 1) ^ (((t >> 1) & 1) << 1))) + 2 * (g & 1);
-    const int src_ks0 = (t << 2) | (g >> 1), src_ks1 = ((4 + t) << 2) | (g >> 1);   // shuffle sources, see unit()
-    uint32_t bhi[KS][2], bbf[KS][2];                 // beta as B fragments of the forward MMAs: tf32 (raw fp32 bits; the
-                                                     // tensor core reads the top 19) and bf16x2 {hi part, lo part}
-    float gacc[KS][4];                               // gbeta^T in C-fragment layout: chain g, columns bwd_col(nt, 2t / 2t+1);
-                                                     // [0], [1] = r_hi part, [2], [3] = r_lo part
-    float nll[2] = {0.0f, 0.0f};                     // loss of chains 2t, 2t+1 over this lane's rows
-
     // ---- this warp's private ring: its tiles are w, w + 15, w + 30, ... of the CTA's slice, over and over
     const int n_mine = (n_tiles > cw) ? (n_tiles - cw + kConsWarps - 1) / kConsWarps : 0;
     float* my_tiles = tiles + (size_t)cw * nst * SLOT_FLOATS;
@@ -698,132 +1139,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
     int slot = 0; uint32_t parity = 0;               // ring position of the next tile to consume
     if (lane == 0 && n_mine > 0)
         for (int s = 0; s < nst; ++s) issue(s, s % n_mine);
-    const bool pairs = (nst == 4);                   // consume two tiles at a time (two independent instruction streams)
     // A warp with no tiles still owns its (empty) slot 0 as reduction scratch; the others use the slot they drained last.
     int red_slot = 0, red_tile = -1;
 
     const bool dbg = (ctid == 0);
-    // (lap state lives in shared memory -- tdbg[14] last lap, tdbg[15] start -- so that it costs no registers in the sweep)
     if (dbg) { tdbg[14] = (unsigned long long)clock64(); tdbg[15] = tdbg[14]; }
-#define B2_DBG_LAP(k) do { if (dbg) { const unsigned long long t_now = (unsigned long long)clock64(); tdbg[k] += t_now - tdbg[14]; tdbg[14] = t_now; } } while (0)
 
-    // column of X behind n index `n` of backward N-tile `nt`
-    auto bwd_col = [&](int nt, int n) { return (ODD && nt == KS - 1) ? 16 * NCH + n : 16 * (nt >> 1) + 2 * n + (nt & 1); };
-
-    // NG 16-row tiles at once (NG = 1 or 2; with 2 the two tiles' instruction streams are independent and
-    // interleave).  Products are split-precision: x = xh + xl (xh = the 19 bits a TF32 MMA reads), likewise beta
-    // and r.  hi*hi runs as TF32 MMAs; the three small cross terms run as BF16 MMAs (k = 16), which is exact
-    // enough because each is already ~2^-11 of the main term (total relative error ~1e-6, fp32 accumulate).
-    auto unit = [&](auto ng_tag, const float* xa, const float* xb) {
-        constexpr int NG = decltype(ng_tag)::value;
-        constexpr int NC = (NG == 2) ? 1 : 2;        // accumulator chains per MMA kind and tile
-        const float* xt[2] = {xa, xb};
-        // ---- forward: logits
-        float acc[NG][2 * NC][4];
-#pragma unroll
-        for (int gi = 0; gi < NG; ++gi)
-#pragma unroll
-            for (int k = 0; k < 2 * NC; ++k) { acc[gi][k][0] = 0.0f; acc[gi][k][1] = 0.0f; acc[gi][k][2] = 0.0f; acc[gi][k][3] = 0.0f; }
-#pragma unroll
-        for (int kk = 0; kk < KS; ++kk) {
-#pragma unroll
-            for (int gi = 0; gi < NG; ++gi) {
-                // (row g, col c), (row g+8, c), (row g, c+1), (row g+8, c+1) with c = 8kk + 2t
-                const float4 v = *reinterpret_cast<const float4*>(xt[gi] + off_f + 16 * kk);
-                const uint32_t ar[4] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
-                mma_tf32(acc[gi][kk % NC], ar, bhi[kk][0], bhi[kk][1]);                      // xh * bh
-                // k = (2t, 2t+1): xl at columns (c, c+1);  k = (2t+8, 2t+9): x at columns (c, c+1)
-                float lx, ly, lz, lw;
-                tf32_lo2(v.x, v.y, lx, ly); tf32_lo2(v.z, v.w, lz, lw);
-                const uint32_t ab[4] = {pack_bf16(lx, lz), pack_bf16(ly, lw), pack_bf16(v.x, v.z), pack_bf16(v.y, v.w)};
-                mma_bf16(acc[gi][NC + kk % NC], ab, bbf[kk][0], bbf[kk][1]);                // xl * bh + x * bl
-            }
-        }
-        // ---- link: c0 (row g, chain 2t), c1 (g, 2t+1), c2 (g+8, 2t), c3 (g+8, 2t+1)
-        float dl[NG][4];
-#pragma unroll
-        for (int gi = 0; gi < NG; ++gi) {
-            const float2 yy = *reinterpret_cast<const float2*>(xt[gi] + kTileRows * P + 2 * g);    // y[row g], y[row g+8]
-            float ls[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float eta = acc[gi][0][i] + acc[gi][NC][i];
-                if (NC == 2) eta = (acc[gi][1][i] + acc[gi][3][i]) + eta;
-                link_fn<LIK>(eta, (i < 2) ? yy.x : yy.y, ls[i], dl[gi][i]);
-            }
-            nll[0] += ls[0] + ls[2]; nll[1] += ls[1] + ls[3];
-        }
-        // ---- residuals -> A fragments.  k-step ks covers pair rows 4ks..4ks+3; lane (g, t) needs
-        //      r[row 4ks+t][chain g] and r[row 4ks+t+8][chain g], held by lane (4ks+t, g>>1) of the C layout.
-        //      TF32: stacked A = [r_hi ; r_lo]^T: a0 = r_hi(low row), a1 = r_lo(low), a2 = r_hi(high), a3 = r_lo(high)
-        //      BF16 (k = 16 = both k-steps): a0 = {r(ks0 low), r(ks0 high)}, a2 = {r(ks1 low), r(ks1 high)}, a1 = a3 = 0
-        uint32_t ra[NG][2][4], rb[NG][4];
-#pragma unroll
-        for (int gi = 0; gi < NG; ++gi) {
-            rb[gi][1] = 0u; rb[gi][3] = 0u;
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                const int src = ks ? src_ks1 : src_ks0;
-                const float e0 = __shfl_sync(0xFFFFFFFFu, dl[gi][0], src), e1 = __shfl_sync(0xFFFFFFFFu, dl[gi][1], src);
-                const float o0 = __shfl_sync(0xFFFFFFFFu, dl[gi][2], src), o1 = __shfl_sync(0xFFFFFFFFu, dl[gi][3], src);
-                const float lo_row = (g & 1) ? e1 : e0, hi_row = (g & 1) ? o1 : o0;
-                ra[gi][ks][0] = __float_as_uint(lo_row); ra[gi][ks][1] = __float_as_uint(tf32_lo(lo_row));
-                ra[gi][ks][2] = __float_as_uint(hi_row); ra[gi][ks][3] = __float_as_uint(tf32_lo(hi_row));
-                rb[gi][2 * ks] = pack_bf16(lo_row, hi_row);
-            }
-        }
-        // ---- backward: gbeta^T[chain][col] += sum_rows r[row][chain] * x[row][col], 16 columns (2 MMAs wide) at a time
-#pragma unroll
-        for (int j = 0; j < NCH; ++j) {
-            float ga[NG][2][4];
-#pragma unroll
-            for (int gi = 0; gi < NG; ++gi) {
-#pragma unroll
-                for (int k = 0; k < 2; ++k) { ga[gi][k][0] = 0.0f; ga[gi][k][1] = 0.0f; ga[gi][k][2] = 0.0f; ga[gi][k][3] = 0.0f; }
-                float xl[2][4];
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                    // col c = 16j+2g: rows (4ks+t, +8); col c+1: rows (4ks+t, +8)
-                    const float4 v = *reinterpret_cast<const float4*>(xt[gi] + off_b + ks * 8 * P + 32 * j);
-                    mma_tf32(ga[gi][0], ra[gi][ks], __float_as_uint(v.x), __float_as_uint(v.y));   // [r_hi ; r_lo] * xh
-                    mma_tf32(ga[gi][1], ra[gi][ks], __float_as_uint(v.z), __float_as_uint(v.w));
-                    tf32_lo2(v.x, v.y, xl[ks][0], xl[ks][1]); tf32_lo2(v.z, v.w, xl[ks][2], xl[ks][3]);
-                }
-                mma_bf16(ga[gi][0], rb[gi], pack_bf16(xl[0][0], xl[0][1]), pack_bf16(xl[1][0], xl[1][1]));   // r * xl, 16 rows
-                mma_bf16(ga[gi][1], rb[gi], pack_bf16(xl[0][2], xl[0][3]), pack_bf16(xl[1][2], xl[1][3]));
-            }
-#pragma unroll
-            for (int gi = 0; gi < NG; ++gi)
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    add2f(gacc[2 * j + k][0], gacc[2 * j + k][1], ga[gi][k][0], ga[gi][k][1]);
-                    add2f(gacc[2 * j + k][2], gacc[2 * j + k][3], ga[gi][k][2], ga[gi][k][3]);
-                }
-        }
-        if (ODD) {
-            float ga[NG][4];
-#pragma unroll
-            for (int gi = 0; gi < NG; ++gi) {
-                ga[gi][0] = 0.0f; ga[gi][1] = 0.0f; ga[gi][2] = 0.0f; ga[gi][3] = 0.0f;
-                float xl[2][2];
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                    const float2 v = *reinterpret_cast<const float2*>(xt[gi] + off_b1 + ks * 8 * P);
-                    mma_tf32(ga[gi], ra[gi][ks], __float_as_uint(v.x), __float_as_uint(v.y));
-                    tf32_lo2(v.x, v.y, xl[ks][0], xl[ks][1]);
-                }
-                mma_bf16(ga[gi], rb[gi], pack_bf16(xl[0][0], xl[0][1]), pack_bf16(xl[1][0], xl[1][1]));
-            }
-#pragma unroll
-            for (int gi = 0; gi < NG; ++gi) {
-                add2f(gacc[KS - 1][0], gacc[KS - 1][1], ga[gi][0], ga[gi][1]);
-                add2f(gacc[KS - 1][2], gacc[KS - 1][3], ga[gi][2], ga[gi][3]);
-            }
-        }
-    };
-
-    const uint32_t spin_hi = (uint32_t)(p.spin_limit >> 32), spin_lo = (uint32_t)p.spin_limit;   // (kept live across the loop cheaply)
-    (void)spin_hi; (void)spin_lo;
     while (true) {
         // ---- wait until this CTA's tick warp has staged every chain's beta of this pass
         if (ctid == 0) B2_TRACE(0, 1);
@@ -835,50 +1156,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         if (ctid == 0) B2_DBG_LAP(0);
         int grp = 0; uint32_t tag = 0u;
         if (real) {
-#pragma unroll
-        for (int kk = 0; kk < KS; ++kk) {                                   // beta -> B fragments (k = column, n = chain)
-            const uint4 w = bs[(size_t)(MG ? (pass & 1u) : 0u) * kBetaWords + (kk * kStreamCT + g) * 4 + t];
-            bhi[kk][0] = w.x; bhi[kk][1] = w.y;                             // staged pre-split by the tick warp
-            bbf[kk][0] = w.z;                                               // hi parts: pairs with xl (k = 2t, 2t+1)
-            bbf[kk][1] = w.w;                                               // lo parts: pairs with x  (k = 2t+8, 2t+9)
-        }
-#pragma unroll
-        for (int nt = 0; nt < KS; ++nt) { gacc[nt][0] = 0.0f; gacc[nt][1] = 0.0f; gacc[nt][2] = 0.0f; gacc[nt][3] = 0.0f; }
-        nll[0] = 0.0f; nll[1] = 0.0f;
-        if (ctid == 0) B2_DBG_LAP(7);
-
-        // ---- sweep: consume this warp's tiles in order (two at a time when the ring has 4 slots); a finished
-        //      slot is refilled at once with the tile `nst` positions further down the (cyclic) sequence
         {
-            int j = 0, jn = nst % (n_mine > 0 ? n_mine : 1);                // jn = (j + nst) mod n_mine
-            while (j < n_mine) {
-                const int s0 = slot; const uint32_t p0 = parity;
-                if (++slot == nst) { slot = 0; parity ^= 1u; }
-                if (pairs && j + 1 < n_mine) {
-                    const int s1 = slot; const uint32_t p1 = parity;
-                    if (++slot == nst) { slot = 0; parity ^= 1u; }
-                    if (p.dbg_sweep != 2) { mbar_wait_bounded(&my_full[s0], p0, p.spin_limit, &sy->abort_flag); mbar_wait_bounded(&my_full[s1], p1, p.spin_limit, &sy->abort_flag); }
-                    if (p.dbg_sweep != 1 && cw < p.dbg_warps) unit(StreamTwo{}, my_tiles + (size_t)s0 * SLOT_FLOATS, my_tiles + (size_t)s1 * SLOT_FLOATS);
-                    __syncwarp();
-                    const bool last = (j + 2 >= n_mine);
-                    if (lane == 0 && p.dbg_sweep != 2) {
-                        issue(s0, jn); if (++jn == n_mine) jn = 0;
-                        if (!last) issue(s1, jn);
-                    }
-                    if (last) { red_slot = s1; red_tile = jn; }        // refilled after the CTA reduction below
-                    if (++jn == n_mine) jn = 0;
-                    j += 2;
-                } else {
-                    if (p.dbg_sweep != 2) mbar_wait_bounded(&my_full[s0], p0, p.spin_limit, &sy->abort_flag);
-                    if (p.dbg_sweep != 1 && cw < p.dbg_warps) unit(StreamOne{}, my_tiles + (size_t)s0 * SLOT_FLOATS, nullptr);
-                    __syncwarp();
-                    const bool last = (j + 1 >= n_mine);
-                    if (lane == 0 && p.dbg_sweep != 2 && !last) issue(s0, jn);
-                    if (last) { red_slot = s0; red_tile = jn; }
-                    if (++jn == n_mine) jn = 0;
-                    j += 1;
-                }
-            }
+            const uint32_t r = stream_sweep<KS, LIK, MG>(p, (uint32_t)slot | (parity << 2), pass);
+            slot = (int)(r & 3u); parity = (r >> 2) & 1u; red_slot = (int)((r >> 3) & 3u); red_tile = (int)(r >> 5) - 1;
         }
         if (ctid == 0) { B2_DBG_LAP(1); B2_TRACE(0, 3); }
         // (read after the sweep so that they do not occupy registers during it; the tick warp rewrites this pass's words only
@@ -886,50 +1166,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         grp = MG ? flags[2 + (pass & 1u)] : 0;        // chain group served by this pass and the round (tag) of its sweep
         tag = (uint32_t)flags[4 + (pass & 1u)];
 
-        // ---- reduce warps -> CTA through the ring slot every warp drained last ([value][lane] floats, conflict
-        //      free), one barrier, fixed order => bit-reproducible; then publish {value, tag} pairs.
-        {
-            float val[16];
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                val[2 * nt] = (nt < KS) ? gacc[nt < KS ? nt : 0][0] + gacc[nt < KS ? nt : 0][2] : 0.0f;
-                val[2 * nt + 1] = (nt < KS) ? gacc[nt < KS ? nt : 0][1] + gacc[nt < KS ? nt : 0][3] : 0.0f;
-            }
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                nll[k] += __shfl_xor_sync(0xFFFFFFFFu, nll[k], 4);
-                nll[k] += __shfl_xor_sync(0xFFFFFFFFu, nll[k], 8);
-                nll[k] += __shfl_xor_sync(0xFFFFFFFFu, nll[k], 16);
-            }
-            float* scr = my_tiles + (size_t)red_slot * SLOT_FLOATS;      // >= 18 * 32 floats in every configuration
-#pragma unroll
-            for (int k = 0; k < 16; ++k) scr[k * 32 + lane] = val[k];
-            scr[16 * 32 + lane] = nll[0]; scr[17 * 32 + lane] = nll[1];
-            if (lane == 0) flags[16 + cw] = red_slot;
-        }
-        bar_sync<kBarCons, kConsThreads>();
-        {
-            for (int o = ctid; o < kStreamCT * 65; o += kConsThreads) {
-                const int c = o / 65, d = o - c * 65;
-                int src = -1;
-                if (d < 8 * KS) {                // (chain c, column d) lives in lane (g = c, t = n >> 1), value 2 nt + (n & 1)
-                    int nt, n;
-                    if (ODD && d >= 16 * NCH) { nt = KS - 1; n = d - 16 * NCH; }
-                    else { nt = 2 * (d >> 4) + (d & 1); n = (d & 15) >> 1; }
-                    src = (2 * nt + (n & 1)) * 32 + (c << 2) + (n >> 1);
-                } else if (d == 64) {            // nll of chain c = 2t + e: lane t (g = 0), value 16 + e
-                    src = (16 + (c & 1)) * 32 + (c >> 1);
-                }
-                float a = 0.0f;
-                if (src >= 0) {
-#pragma unroll
-                    for (int w = 0; w < kConsWarps; ++w) a += tiles[((size_t)w * nst + flags[16 + w]) * SLOT_FLOATS + src];
-                }
-                __stcg(p.partial + (((size_t)cta * NGRP + grp) * kStreamCT + c) * kGStride + d, make_float2(a, __uint_as_float(tag)));
-            }
-        }
-        bar_sync<kBarCons, kConsThreads>();          // every scratch slot has been read: refill them
-        if (lane == 0 && red_tile >= 0 && p.dbg_sweep != 2) issue(red_slot, red_tile);
+        stream_reduce_publish<KS, MG>(p, nst, grp, tag);
+        // (single group: an owner CTA gathers right away and uses the drained scratch slots as landing zones -- refilled after that)
+        if (!(!MG && is_tick) && lane == 0 && red_tile >= 0 && p.dbg_sweep != 2) issue(red_slot, red_tile);
         if (ctid == 0) { B2_DBG_LAP(2); B2_TRACE(0, 4); }
 
         }   // real pass
@@ -946,35 +1185,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
             }
         }
         if (do_g) {
-            const int o = ctid % 65, seg = ctid / 65;
-            if (seg < kXSeg) {
-                // kXSeg segments x 65 outputs; each thread adds its segment's CTAs in ascending order.  All loads of a
-                // batch are in flight together (L2 latency overlapped); stale entries are simply polled again.
-                float a = 0.0f;
-                const int g0 = G * seg / kXSeg, g1 = G * (seg + 1) / kXSeg;
-                const float2* src = p.partial + ((size_t)ggrp * kStreamCT + (MG ? cta % kStreamCT : cta)) * kGStride + o;
-                const long long t_w = clock64();
-                for (int gg = g0; gg < g1; gg += 24) {
-                    float2 v[24];
-                    while (true) {
-                        bool ok = true;
-#pragma unroll
-                        for (int k = 0; k < 24; ++k) {
-                            if (gg + k < g1) {
-                                v[k] = ld_volatile_v2(src + (size_t)(gg + k) * ((size_t)NGRP * kStreamCT * kGStride));
-                                ok = ok && (__float_as_uint(v[k].y) == gtag);
-                            } else v[k] = make_float2(0.0f, 0.0f);
-                        }
-                        if (ok) break;
-                        if (ld_acquire(&sy->abort_flag)) break;
-                        if (clock64() - t_w > p.spin_limit) { atomicCAS(&sy->abort_flag, 0u, 3u); break; }
-                    }
-#pragma unroll
-                    for (int k = 0; k < 24; ++k) a += v[k].x;
-                }
-                xred[seg * kGStride + o] = a;
-            }
-            __threadfence_block();
+            if constexpr (!MG) {
+                stream_gather_land<KS>(p, gtag, my_tiles + (size_t)red_slot * SLOT_FLOATS);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes before the bulk copy reuses the slot
+                if (lane == 0 && red_tile >= 0 && p.dbg_sweep != 2) issue(red_slot, red_tile);
+            } else stream_gather<KS, MG>(p, ggrp, gtag);
             bar_arrive<kBarTick, kStreamThreads>();  // tick warp takes over; consumers go wait for the next beta
             if (ctid == 0) { B2_DBG_LAP(4); B2_TRACE(0, 5); }
         }
