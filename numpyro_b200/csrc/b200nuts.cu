@@ -352,7 +352,7 @@ static int check_stream_abort(B200Nuts* h, cudaStream_t st) {
                         }
                     for (int c = 0; c < h->C && c < kStreamCT; ++c) {
                         fprintf(stderr, "  partial tags chain %d (word 0) per CTA:", c);
-                        for (int g = 0; g < h->grid; ++g) { unsigned int tg; memcpy(&tg, &hp[((size_t)g * h->num_groups * kStreamCT + c) * kGWords * 2 + 1].y, 4); fprintf(stderr, " %u", tg); }
+                        for (int g = 0; g < h->grid; ++g) { unsigned int tg; memcpy(&tg, &hp[(((size_t)c * h->grid + g) * ((8 * h->ks + 3) / 3)) * 2 + 1].y, 4); fprintf(stderr, " %u", tg); }
                         fprintf(stderr, "\n");
                     }
                 }
@@ -378,8 +378,10 @@ static int check_stream_abort(B200Nuts* h, cudaStream_t st) {
                     s.pre_hit[c][2], s.pre_miss[c][2]);
     }
     if (getenv("B200NUTS_DEBUG_CTA") && s.passes) {
-        fprintf(stderr, "[b200nuts] owner 0 gather per pass: poll rounds %.2f, polling %.0f cycles, until the segment barrier %.0f cycles\n",
+        fprintf(stderr, "[b200nuts] owner 0 per pass: gather rounds %.2f | beta poll %.0f cycles in %.2f rounds\n",
                 (double)s.dbg[3] / s.passes, (double)s.dbg[12] / s.passes, (double)s.dbg[13] / s.passes);
+        fprintf(stderr, "[b200nuts] owner 0 per pass: hand-over consumers -> tick warp %.0f cycles, tick warp -> consumers %.0f cycles\n",
+                (double)s.wake[0] / s.passes, (double)s.wake[1] / s.passes);
         for (int g = 0; g < h->grid && g < 160; ++g)
             fprintf(stderr, "[b200nuts] cta %3d per pass: wait_beta %.0f sweep %.0f reduce %.0f gather %.0f\n", g, (double)s.cta_lap[g][0] / s.passes,
                     (double)s.cta_lap[g][1] / s.passes, (double)s.cta_lap[g][2] / s.passes, (double)s.cta_lap[g][3] / s.passes);

@@ -68,12 +68,13 @@ constexpr int kTileRows = 16;            // rows per ring slot = one consumer wa
 constexpr int kMaxStages = 4;            // tile slots per consumer warp (4: tiles are consumed in pairs)
 constexpr int kGStride = 72;             // floats per (cta, chain) partial: gbeta[<=64], nll, pad
 constexpr int kRedWarps = (kConsWarps + 1) / 2;   // rows of the two-stage CTA reduction scratch
-constexpr int kXSeg = 25;                // segments of the cross-CTA reduction, at most (each adds a contiguous range of CTAs)
+constexpr int kXSeg = kConsWarps;        // segments of the cross-CTA reduction (each adds a contiguous range of CTAs)
 constexpr int kXStride = 66;             // floats per segment / per chain of the packed outputs (3 per 16-byte word, <= 22 words)
 constexpr int kXScratch = kXSeg * kXStride;           // offset of the tick's gradient scratch behind the segment sums
 constexpr int kXRedFloats = kXScratch + 192;          // owner CTA: segment sums + gradient scratch for the tick
-constexpr int kGWords = 24;              // 16-byte words per (cta, chain) partial: {v0, v1, v2, tag}; output e = column e, e = 8 KS: nll
-constexpr int kBarBeta = 1, kBarCons = 2, kBarTick = 3;
+// partials: 16-byte words {v0, v1, v2, tag}, NW = ceil((8 KS + 1) / 3) per (chain, cta) row; output e = column e, e = 8 KS: nll.
+// Layout [group][chain][cta][NW]: everything one owner needs from a range of CTAs is ONE contiguous block (one bulk copy).
+constexpr int kBarBeta = 1, kBarCons = 2, kBarTick = 3, kBarSwept = 4;
 constexpr int kBetaCopies = 4;           // replicas of the published beta (CTA c fetches replica c mod 4)
 constexpr int kBetaWords = 8 * kStreamCT * 4;     // 16-byte words per replica: [k-step][chain][t]
 constexpr int kConsThreads = kConsWarps * 32, kTopThreads = kStreamThreads;
@@ -102,7 +103,7 @@ struct StreamSync { unsigned int abort_flag, pad_[3]; unsigned long long passes;
                     unsigned int pre_hit[kMaxStreamChains][4], pre_miss[kMaxStreamChains][4];
                     unsigned long long laps[32];
                     unsigned int peek_hit[kMaxStreamChains], peek_fallback[kMaxStreamChains], peek_mismatch[kMaxStreamChains];
-                    unsigned long long cta_lap[160][4]; };     // per CTA: wait for betas, sweep, CTA reduction + publish, poll + sum     // -DB2_TICK_LAPS builds only: [i] cycles, [16 + i] occurrences   // per owner CTA: tick cycles, look-ahead hits
+                    unsigned long long cta_lap[160][4]; unsigned long long wake[4]; };     // per CTA: wait for betas, sweep, CTA reduction + publish, poll + sum     // -DB2_TICK_LAPS builds only: [i] cycles, [16 + i] occurrences   // per owner CTA: tick cycles, look-ahead hits
 
 struct StreamParams {
     TickCfg cfg; FamilySpec fam; OutBufs out;
@@ -110,7 +111,7 @@ struct StreamParams {
     int num_groups;                      // ceil(C / kStreamCT)
     int max_passes;                      // single group only: pause after this many sweeps (0 = run to the end)
     ChainCtl* ctl; float* vecs;          // [C], [V_COUNT][C][Dp]
-    float2* partial;                     // [grid][num_groups][kStreamCT][kGStride] {value, tag = round of the group}
+    float2* partial;                     // 16-byte words {v0, v1, v2, tag = round of the group}: [num_groups][kStreamCT][grid][NW]
     uint4* beta;                         // [kBetaCopies][num_groups][8 k-steps][kStreamCT][4] {b0, tag, b1, tag}: beta in MMA-fragment order
     StreamSync* sync;
     const float* z_in; float* u_out; float* g_out;    // mode 1
@@ -281,7 +282,8 @@ B2_HD constexpr size_t stream_head_smem(bool multi_group) {
     b += (size_t)kConsWarps * kMaxStages * 8;                      // mbarriers
     b += (size_t)(multi_group ? 2 : 1) * kBetaWords * 16;          // staged beta (two passes with several groups), [k-step][chain][t] {b0, tag, b1, tag}
     b += (size_t)kXRedFloats * 4;                                  // cross-CTA reduction + tick scratch
-    b += 64 * 4 + 64 * 4 + 256 + 128;                              // gred(+nll), flags, timers
+    b += 64 * 4 + 64 * 4 + 256 + 256;                              // gred(+nll), flags, timers
+    b += 128 + 128;                                                // gather: one mbarrier per consumer warp, their phase bits
     b += (size_t)kStreamCT * kXStride * 4;                         // this CTA's reduced outputs on their way to the packed partial
     return (b + 127) / 128 * 128;
 }
@@ -397,8 +399,10 @@ template <bool MG> struct StreamSmem {
     static constexpr size_t kPout = kGred + 64 * 4 + 64 * 4;
     static constexpr size_t kFlags = kPout + (size_t)kStreamCT * kXStride * 4;
     static constexpr size_t kTdbg = kFlags + 256;
+    static constexpr size_t kGbar = kTdbg + 256;
+    static constexpr size_t kGpar = kGbar + 128;
     static constexpr size_t kTiles = stream_head_smem(MG);
-    static_assert(kTdbg + 128 <= kTiles, "fixed regions overlap the tile ring");
+    static_assert(kGpar + 128 <= kTiles, "fixed regions overlap the tile ring");
 };
 // column of X behind n index `n` of backward N-tile `nt` (see the kernel's backward MMAs)
 template <int KS> B2_D int stream_bwd_col(int nt, int n) {
@@ -418,7 +422,6 @@ __device__ __noinline__ void stream_reduce_publish(const StreamParams& p, int ns
     const int* flags = (const int*)(smem_raw + L::kFlags);
     float* pout = (float*)(smem_raw + L::kPout);
     const int ctid = threadIdx.x, cta = blockIdx.x;
-    const int NGRP = MG ? p.num_groups : 1;
     bar_sync<kBarCons, kConsThreads>();
     {
         // thread i adds scratch word i = (value k, lane l) of the 15 warps in warp order (conflict-free: consecutive threads read
@@ -445,7 +448,7 @@ __device__ __noinline__ void stream_reduce_publish(const StreamParams& p, int ns
     if (ctid < kStreamCT * NW) {
         const int c = ctid / NW, w = ctid - c * NW;
         const float* src = pout + c * kXStride + 3 * w;
-        __stcg(reinterpret_cast<float4*>(p.partial) + (((size_t)cta * NGRP + grp) * kStreamCT + c) * kGWords + w,
+        __stcg(reinterpret_cast<float4*>(p.partial) + (((size_t)grp * kStreamCT + c) * gridDim.x + cta) * NW + w,
                make_float4(src[0], src[1], src[2], __uint_as_float(tag)));
     }
 }
@@ -466,14 +469,16 @@ __device__ __noinline__ void stream_gather(const StreamParams& p, int ggrp, uint
     // kXSeg segments x NW words: thread (seg, w) adds word w of its segment's CTAs in ascending order.  All loads of a
     // batch are in flight together (L2 latency overlapped); only the entries that were still stale are polled again
     // (the owner SM's load path moves about one 32-byte sector per cycle: a full round costs thousands of cycles).
-    constexpr int SEGS = (kConsThreads / NW < kXSeg) ? kConsThreads / NW : kXSeg;   // (few loads per thread: few registers)
-    constexpr int NB = (148 + SEGS - 1) / SEGS;
+    // (the same ranges and the same order of additions as stream_gather_land: a chain's sums must not depend on how many
+    //  chain groups the handle has; five loads in flight per thread keep this function's register footprint small)
+    constexpr int SEGS = kConsWarps;
+    constexpr int NB = 5;
     const int seg = ctid / NW, w = ctid - seg * NW;
     if (seg < SEGS) {
         float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
         const int g0 = G * seg / SEGS, g1 = G * (seg + 1) / SEGS;
-        const uint4* src = reinterpret_cast<const uint4*>(p.partial) + ((size_t)ggrp * kStreamCT + (MG ? cta % kStreamCT : cta)) * kGWords + w;
-        const size_t cta_stride = (size_t)NGRP * kStreamCT * kGWords;
+        const uint4* src = reinterpret_cast<const uint4*>(p.partial) + ((size_t)ggrp * kStreamCT + (MG ? cta % kStreamCT : cta)) * G * NW + w;
+        constexpr size_t cta_stride = NW;
         const long long t_w = clock64();
         for (int gg = g0; gg < g1; gg += NB) {
             uint4 v[NB];
@@ -497,12 +502,10 @@ __device__ __noinline__ void stream_gather(const StreamParams& p, int ggrp, uint
             for (int k = 0; k < NB; ++k)
                 if (k < nb) { a0 += __uint_as_float(v[k].x); a1 += __uint_as_float(v[k].y); a2 += __uint_as_float(v[k].z); }
         }
-        if (dbg) tdbg[12] += (unsigned long long)(clock64() - t_w);
         float* dst = xred + seg * kXStride + 3 * w;
         dst[0] = a0; dst[1] = a1; dst[2] = a2;
     }
     bar_sync<kBarCons, kConsThreads>();      // the segment sums are in xred: join them in segment order
-    if (dbg) tdbg[13] += (unsigned long long)clock64() - tdbg[14];
     if (ctid < NOUT) {
         float a = xred[ctid];
 #pragma unroll
@@ -512,64 +515,76 @@ __device__ __noinline__ void stream_gather(const StreamParams& p, int ggrp, uint
     __threadfence_block();
 }
 
-// Single chain group: the same gather with the polled words landing in shared memory (cp.async into the reduction scratch slot
-// this warp has just drained -- the owner CTAs refill that slot after the gather) instead of registers: a register-hungry
-// out-of-line function costs the caller registers EVERYWHERE (ptxas moved spills into the sweep's MMA region).
+// Single chain group: consumer warp w fetches the rows of ITS range of CTAs (one contiguous block of the owner's chain) with ONE
+// bulk copy into the reduction scratch slot it has just drained (the owner CTAs refill those slots after the gather), checks
+// the tags in shared memory (a stale block is simply fetched again), adds the rows in CTA order; the 15 ranges are joined in
+// warp order.  The owner SM's load path moves only about one 32-byte sector per cycle for per-thread loads: this is ~3x faster.
 template <int KS>
 __device__ __noinline__ void stream_gather_land(const StreamParams& p, uint32_t gtag, float* land) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using L = StreamSmem<false>;
     constexpr int NOUT = 8 * KS + 1, NW = (NOUT + 2) / 3;
-    constexpr int SEGS = (kConsThreads / NW < kXSeg) ? kConsThreads / NW : kXSeg;
-    constexpr int NBW = (148 + SEGS - 1) / SEGS, NBS = stream_slot_floats(KS) * 4 / 512;   // words per thread: wanted / that fit
-    constexpr int NB = NBW < NBS ? NBW : NBS;
+    constexpr int ROWS = stream_slot_floats(KS) * 4 / (NW * 16);       // rows of NW words that fit into a scratch slot
+    static_assert(NW <= 32 && ROWS >= 1, "gather: a row must fit a warp and a slot");
     float* xred = (float*)(smem_raw + L::kXred);
     float* gred = (float*)(smem_raw + L::kGred);
     unsigned long long* tdbg = (unsigned long long*)(smem_raw + L::kTdbg);
-    const int ctid = threadIdx.x, lane = ctid & 31, cta = blockIdx.x, G = gridDim.x;
+    const int ctid = threadIdx.x, lane = ctid & 31, cw = ctid >> 5, cta = blockIdx.x, G = gridDim.x;
+    uint64_t* gbar = (uint64_t*)(smem_raw + L::kGbar) + cw;
+    unsigned int* gpar = (unsigned int*)(smem_raw + L::kGpar) + cw;
     const bool dbg = (ctid == 0);
-    const int seg = ctid / NW, w = ctid - seg * NW;
-    uint4* mine = reinterpret_cast<uint4*>(land) + lane;            // word k of this lane: mine[32 k] (conflict-free)
-    if (seg < SEGS) {
-        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
-        const int g0 = G * seg / SEGS, g1 = G * (seg + 1) / SEGS;
-        const uint4* src = reinterpret_cast<const uint4*>(p.partial) + (size_t)cta * kGWords + w;
-        constexpr size_t cta_stride = (size_t)kStreamCT * kGWords;
-        const long long t_w = clock64();
-        for (int gg = g0; gg < g1; gg += NB) {
-            const int nb = (g1 - gg < NB) ? (g1 - gg) : NB;
-            const unsigned want = (1u << nb) - 1u;
-            unsigned ready = 0u;
-            while (true) {
-#pragma unroll
-                for (int k = 0; k < NB; ++k)
-                    if (k < nb && !((ready >> k) & 1u)) cp_async16(mine + 32 * k, src + (size_t)(gg + k) * cta_stride);
-                cp_async_wait_all();
-#pragma unroll
-                for (int k = 0; k < NB; ++k)
-                    if (k < nb && !((ready >> k) & 1u) && reinterpret_cast<const volatile unsigned int*>(mine + 32 * k)[3] == gtag) ready |= 1u << k;
-                if (dbg) tdbg[3] += 1ull;                 // (poll rounds of thread 0)
-                if (ready == want) break;
-                if (ld_acquire(&p.sync->abort_flag)) break;
-                if (clock64() - t_w > p.spin_limit) { atomicCAS(&p.sync->abort_flag, 0u, 3u); break; }
+    const int g0 = G * cw / kConsWarps, g1 = G * (cw + 1) / kConsWarps;
+    const uint4* rows = reinterpret_cast<const uint4*>(p.partial) + (size_t)cta * G * NW;      // [cta][NW] of this owner's chain
+    const uint4* land4 = reinterpret_cast<const uint4*>(land);
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+    unsigned int par = *gpar;
+    const long long t_w = clock64();
+    for (int gg = g0; gg < g1; gg += ROWS) {
+        const int nrow = (g1 - gg < ROWS) ? (g1 - gg) : ROWS;
+        const uint32_t bytes = (uint32_t)nrow * NW * 16u;
+        while (true) {
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy accesses of the slot come first
+                mbar_expect_tx(gbar, bytes);
+                bulk_g2s(land, rows + (size_t)gg * NW, bytes, gbar);
             }
-#pragma unroll
-            for (int k = 0; k < NB; ++k)
-                if (k < nb) { const uint4 v = mine[32 * k]; a0 += __uint_as_float(v.x); a1 += __uint_as_float(v.y); a2 += __uint_as_float(v.z); }
+            bool alive = true;
+            {   // bounded wait (every lane: the data must be visible to each of them)
+                unsigned int it = 0;
+                while (!mbar_try_wait(gbar, par)) {
+                    if ((++it & 255u) == 0u && (ld_acquire(&p.sync->abort_flag) || clock64() - t_w > p.spin_limit)) { alive = false; break; }
+                }
+            }
+            par ^= 1u;
+            bool ok = true;
+            for (int i = lane; i < nrow * NW; i += 32) ok = ok && (reinterpret_cast<const volatile unsigned int*>(land4 + i)[3] == gtag);
+            if (dbg) tdbg[3] += 1ull;                 // (poll rounds of thread 0)
+            const bool all_ok = __all_sync(0xFFFFFFFFu, ok);
+            if (all_ok) break;
+            // (warp-uniform exits)
+            bool give_up = !alive || ld_acquire(&p.sync->abort_flag) != 0u;
+            if (clock64() - t_w > p.spin_limit) { atomicCAS(&p.sync->abort_flag, 0u, 3u); give_up = true; }
+            if (__any_sync(0xFFFFFFFFu, give_up)) break;
         }
-        if (dbg) tdbg[12] += (unsigned long long)(clock64() - t_w);
-        float* dst = xred + seg * kXStride + 3 * w;
-        dst[0] = a0; dst[1] = a1; dst[2] = a2;
+        if (lane < NW)
+            for (int r = 0; r < nrow; ++r) {
+                const uint4 v = land4[r * NW + lane];
+                a0 += __uint_as_float(v.x); a1 += __uint_as_float(v.y); a2 += __uint_as_float(v.z);
+            }
+        __syncwarp();                                 // (a second block of rows lands in the same slot)
     }
-    bar_sync<kBarCons, kConsThreads>();      // the segment sums are in xred: join them in segment order
-    if (dbg) tdbg[13] += (unsigned long long)clock64() - tdbg[14];
+    if (lane == 0) *gpar = par;
+    if (lane < NW) { float* dst = xred + cw * kXStride + 3 * lane; dst[0] = a0; dst[1] = a1; dst[2] = a2; }
+    bar_sync<kBarCons, kConsThreads>();      // the range sums are in xred: join them in warp order
     if (ctid < NOUT) {
         float a = xred[ctid];
 #pragma unroll
-        for (int sgm = 1; sgm < SEGS; ++sgm) a += xred[sgm * kXStride + ctid];
+        for (int sgm = 1; sgm < kConsWarps; ++sgm) a += xred[sgm * kXStride + ctid];
         gred[ctid < 8 * KS ? ctid : 64] = a;
     }
     __threadfence_block();
+    if (ctid == 0) tdbg[19] = (unsigned long long)clock64();
+    bar_arrive<kBarTick, kStreamThreads>();  // the tick warp takes over at once (the caller's slot refill is off the critical path)
 }
 
 struct StreamOne { static constexpr int value = 1; };
@@ -861,8 +876,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
     // ---- one-time setup: init barriers, stage the chain
     if (tid == 0) {
         for (int i = 0; i < kConsWarps * kMaxStages; ++i) mbar_init(&full[i], 1);
+        for (int i = 0; i < kConsWarps; ++i) { mbar_init((uint64_t*)(smem_raw + L::kGbar) + i, 1); ((unsigned int*)(smem_raw + L::kGpar))[i] = 0u; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int i = 0; i < 16; ++i) tdbg[i] = 0ull;
+        for (int i = 0; i < 32; ++i) tdbg[i] = 0ull;
         for (int i = 0; i < 64; ++i) flags[i] = 0;
         for (int i = 0; i < 128; ++i) gred[i] = 0.0f;   // (columns 8 KS .. 63 are never written afterwards)
         for (int i = 0; i < kStreamCT * kXStride; ++i) pout[i] = 0.0f;   // (nor are the pad outputs of a chain's last word)
@@ -920,6 +936,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
 #endif
 
         uint32_t need = 0u;                          // round (= beta tag) of the sweep being staged
+        int swept_sync = 0;                          // single group: last pass whose predecessor's sweep this warp has waited for
         int grp = -1;
         // Stage the next pass for this CTA's consumers: fetch the betas of group `grp` (tag need), put them into the pass's
         // staging buffer and release the consumers.  Returns 0 = staged, 1 = the group has finished (no pass), 2 = stop.
@@ -943,6 +960,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
             }
             uint4* bsq = bs + (size_t)(MG ? (qpass & 1) : 0) * kBetaWords;
             need = 0u;
+            // (single group: no beta can arrive before this CTA's own consumers have finished the previous sweep -- sleep on a
+            //  barrier until then instead of polling the L2 through the whole sweep)
+            if (!MG && qpass > swept_sync) { bar_sync<kBarSwept, kStreamThreads>(); swept_sync = qpass; }    // (once per sweep: stage() can run twice for a pass)
             if (status == 0) {
                 // fetch the betas of group `grp` for its next sweep (tags ride in the data: poll until they all match)
                 need = rounds[grp] + 1u;
@@ -964,12 +984,14 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                         const unsigned int bal = __ballot_sync(0xFFFFFFFFu, ok);
                         if (lane == 0) { p.trace[32 * blockIdx.x + 2] = bal; p.trace[32 * blockIdx.x + 3] += 1u; }
                     }
+                    if (dbg) tdbg[13] += 1ull;                     // (beta poll rounds, CTA 0)
                     if (__all_sync(0xFFFFFFFFu, ok)) break;
                     // (warp-uniform exits: a lane that left alone would deadlock the __all_sync above)
                     bool give_up = aborted != 0u;
                     if (clock64() - t_w > p.spin_limit) { atomicCAS(&sy->abort_flag, 0u, 2u); give_up = true; }
                     if (__any_sync(0xFFFFFFFFu, give_up)) { status = 2; break; }
                 }
+                if (dbg) tdbg[12] += (unsigned long long)(clock64() - t_w);      // (cycles spent polling for the betas, CTA 0)
                 const bool done_bit = absent || ((w[0].y >> 31) != 0u);
                 if (status == 0 && __all_sync(0xFFFFFFFFu, done_bit)) {      // nothing left to sweep for this group
                     done_mask |= 1u << grp; cur = (grp + 1) % NGRP;
@@ -990,6 +1012,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                 if (status == 0) rounds[grp] = need;
             }
             warp_sync_hard();
+            if (dbg) tdbg[17] = (unsigned long long)clock64();
             bar_arrive<kBarBeta, kStreamThreads>();  // release the consumers (they read flags and the staged betas)
             B2_TRACE_LANES(2);
             return status ? 2 : 0;
@@ -1035,7 +1058,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                 //      state machine -> next beta (tag my_round + 1)
                 const uint32_t seq = my_round;
                 B2_TRACE_LANES(3);
+                float* gz = xred + kXScratch;        // scratch for the gradient wrt z (<= 64 floats when the early publish applies)
+                float* zpeek = gz + 64;              // ... and for the position published ahead of the tick (<= 64 floats)
+                bool early = false;
                 bar_sync<kBarTick, kStreamThreads>();    // the sums over the CTAs' partials are in `gred`
+                if (dbg) tdbg[16] += (unsigned long long)clock64() - tdbg[19];   // (hand-over latency consumers -> tick warp, CTA 0)
                 B2_LAPQ(-1);
                 B2_TRACE_LANES(4);
                 const long long t_a = clock64();
@@ -1074,9 +1101,6 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                 const float nll = __shfl_sync(0xFFFFFFFFu, a64, 0) - (p.shard_count > 1 ? 0.0f : pad_nll);
                 if (lane == 0) tlap[3] += (unsigned long long)(clock64() - t_a);
                 B2_LAPQ(6);
-                float* gz = xred + kXScratch; // scratch for the gradient wrt z (<= 64 floats when the early publish applies)
-                float* zpeek = gz + 64;              // ... and for the position published ahead of the tick (<= 64 floats)
-                bool early = false;
                 if (!chain_done) {
                     early = stream_tick_critical(p, tk, gred, gz, zpeek, nll, cta, tdbg, seq + 1u, def_u, peek_stat);
                     if (p.mode == 1) chain_done = true;
@@ -1153,7 +1177,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         if (st == 1 || st == 2) break;
         const bool real = !MG || st == 0;             // (3: flush pseudo-pass of the deferred gather -- nothing to sweep)
         if (ctid == 0) { *(volatile int*)(flags + 8) = (int)pass; B2_TRACE(0, 2); }
-        if (ctid == 0) B2_DBG_LAP(0);
+        if (ctid == 0) { tdbg[18] += (unsigned long long)clock64() - tdbg[17]; B2_DBG_LAP(0); }
         int grp = 0; uint32_t tag = 0u;
         if (real) {
         {
@@ -1167,6 +1191,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         tag = (uint32_t)flags[4 + (pass & 1u)];
 
         stream_reduce_publish<KS, MG>(p, nst, grp, tag);
+        if (!MG) bar_arrive<kBarSwept, kStreamThreads>();     // the tick warp may start polling for the next betas
         // (single group: an owner CTA gathers right away and uses the drained scratch slots as landing zones -- refilled after that)
         if (!(!MG && is_tick) && lane == 0 && red_tile >= 0 && p.dbg_sweep != 2) issue(red_slot, red_tile);
         if (ctid == 0) { B2_DBG_LAP(2); B2_TRACE(0, 4); }
@@ -1189,8 +1214,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
                 stream_gather_land<KS>(p, gtag, my_tiles + (size_t)red_slot * SLOT_FLOATS);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes before the bulk copy reuses the slot
                 if (lane == 0 && red_tile >= 0 && p.dbg_sweep != 2) issue(red_slot, red_tile);
-            } else stream_gather<KS, MG>(p, ggrp, gtag);
-            bar_arrive<kBarTick, kStreamThreads>();  // tick warp takes over; consumers go wait for the next beta
+            } else {
+                stream_gather<KS, MG>(p, ggrp, gtag);
+                bar_arrive<kBarTick, kStreamThreads>();  // tick warp takes over; consumers go wait for the next beta
+            }
             if (ctid == 0) { B2_DBG_LAP(4); B2_TRACE(0, 5); }
         }
         ++pass;
@@ -1217,6 +1244,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         sy->passes = pass;
         tdbg[5] = (unsigned long long)clock64() - tdbg[15];
         for (int i = 0; i < 16; ++i) sy->dbg[i] = tdbg[i];
+        sy->wake[0] = tdbg[16]; sy->wake[1] = tdbg[18];
     }
 #undef B2_DBG_LAP
 }
