@@ -39,16 +39,23 @@
 //             columns accumulates over the tile's 2 k-steps on the tensor core, then joins the
 //             per-pass fp32 accumulators with FADDs.
 // Inter-pass exchange (deterministic, no float atomics, no counters, no fences).  Everything that crosses
-// CTAs carries its own sequence tag inside the same 8-byte word as the data ("flag-in-data"), so a reader
+// CTAs carries its own sequence tag inside the same 8- or 16-byte word as the data ("flag-in-data"), so a reader
 // simply polls the data it needs:
-//   * every CTA reduces its warps' accumulators through the ring slots its warps just drained (one barrier)
-//     and publishes {value, tag} pairs;
-//   * chain c's CTA polls the 148 partials of its chain, sums them in fixed order, its tick warp finishes the
-//     potential (priors, Jacobians), ticks the chain (tick.cuh) and publishes the next beta_c as tagged pairs
-//     in MMA-fragment order (4 replicas to spread the L2 load);
-//   * the tick warp of every CTA fetches all chains' beta, stages them in shared memory and releases the
-//     CTA's consumer warps through a named barrier.  While the consumers sweep, an owner's tick warp looks
-//     ahead in the chain's PRNG streams (Tick::prefetch) so the next tick finds its random numbers ready.
+//   * every CTA reduces its warps' accumulators through the ring slots its warps just drained (thread i adds word i
+//     of the 15 scratch slots: conflict-free) and publishes its partial as 16-byte words {v0, v1, v2, tag}, laid out
+//     [group][chain][cta][word] so that what one owner needs from a range of CTAs is one contiguous block;
+//   * chain c's CTA: every consumer warp fetches the block of ITS range of CTAs with one bulk copy into the scratch
+//     slot it has just drained, checks the tags in shared memory (a stale block is fetched again), adds the rows in
+//     CTA order; the 15 ranges are joined in warp order.  The tick warp finishes the potential (priors, Jacobians),
+//     ticks the chain (tick.cuh) and publishes the next beta_c as tagged pairs in MMA-fragment order (4 replicas
+//     to spread the L2 load);
+//   * the tick warp of every CTA sleeps on a barrier until its own consumers have finished the sweep, then fetches
+//     all chains' beta, stages them in shared memory and releases the CTA's consumer warps through a named barrier.
+//     While the consumers sweep, an owner's tick warp runs the deferred half of the tick and looks ahead in the
+//     chain's PRNG streams (Tick::prefetch) so the next tick finds its random numbers ready.
+// Register discipline: the sweep body (stream_sweep) derives everything it needs from volatile thread / block id
+// reads once per pass, and the exchange steps are out-of-line functions with small register footprints (the
+// gather keeps its polled words in shared memory): ptxas otherwise moved spills into the MMA region.
 #pragma once
 #include <cuda_runtime.h>
 #include "tick.cuh"
