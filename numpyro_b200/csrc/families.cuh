@@ -140,32 +140,44 @@ B2_HD void glm_finish(const FamilySpec& f, const float* z, float nll, const floa
 #endif
     float prec = 1.0f;
     if (f.likelihood == LIK_NORMAL) prec = expf(z[f.off_prec]);
+    // (wide models -- the GEMM regime's few-but-wide chains: four elements of a lane in flight per batch, see common.cuh; the
+    //  per-element arithmetic and the order of the additions are those of the plain loops: identical bits)
+    const bool has_l = f.off_lambda >= 0, has_t = f.gscale != SCALE_NONE;
+    const float zt_ = has_t ? z[f.off_tau] : 0.0f;
+    auto scale_of = [&](float zl, int j) {           // glm_scale_at with the operands already loaded
+        float s = 1.0f;
+        if (has_l) s = s * expf(zl);
+        if (has_t && j >= f.g0 && j < f.g1) s = s * expf(zt_);
+        return s;
+    };
     // coefficient block: u ~ N(0, 1)
     B2_LAPQ(-1);
-    float acc = lane_sum(Dx, [&](int j) { const float u = z[f.off_u + j]; return 0.5f * u * u; });
+    float acc = lane_sum_wide(Dx, [&](int j) { const float u = z[f.off_u + j]; return 0.5f * u * u; });
     float U = acc + (float)Dx * kLogSqrt2Pi;
     B2_LAPQ(8);
-    B2_FOR_D(j, Dx) g[f.off_u + j] = z[f.off_u + j] + glm_scale_at(f, z, j) * (prec * gbeta[j]);
+    for_d_wide(Dx, [&](int j) { Vals v; v.x[0] = z[f.off_u + j]; v.x[1] = has_l ? z[f.off_lambda + j] : 0.0f; v.x[2] = gbeta[j]; return v; },
+               [&](int j, const Vals& v) { g[f.off_u + j] = v.x[0] + scale_of(v.x[1], j) * (prec * v.x[2]); });
     B2_LAPQ(9);
-    if (f.off_lambda >= 0) {             // lambdas ~ HalfCauchy(1), z = log lambda
-        float a = lane_sum(Dx, [&](int j) {
+    if (has_l) {                         // lambdas ~ HalfCauchy(1), z = log lambda
+        float a = lane_sum_wide(Dx, [&](int j) {
             const float zl = z[f.off_lambda + j];
             return log1pf(expf(2.0f * zl)) - zl;
         });
         U = U + a + (float)Dx * (kLogPi - kLog2);
-        B2_FOR_D(j, Dx) {
-            const float zl = z[f.off_lambda + j];
+        for_d_wide(Dx, [&](int j) { Vals v; v.x[0] = z[f.off_lambda + j]; v.x[1] = z[f.off_u + j]; v.x[2] = gbeta[j]; return v; },
+                   [&](int j, const Vals& v) {
+            const float zl = v.x[0];
             const float l2 = expf(2.0f * zl);
-            const float beta = glm_scale_at(f, z, j) * z[f.off_u + j];
+            const float beta = scale_of(zl, j) * v.x[1];
             // d/dz of [log1p(l2) - zl] = 2*l2/(1+l2) - 1; inf/inf guarded
             const float frac = is_inf(l2) ? 1.0f : (l2 / (1.0f + l2));
-            g[f.off_lambda + j] = beta * (prec * gbeta[j]) + 2.0f * frac - 1.0f;
-        }
+            g[f.off_lambda + j] = beta * (prec * v.x[2]) + 2.0f * frac - 1.0f;
+        });
     }
     if (f.gscale != SCALE_NONE) {        // global scale tau, z = log tau
         const float zt = z[f.off_tau];
         const float tau = expf(zt);
-        const float dot = lane_sum(Dx, [&](int j) {
+        const float dot = lane_sum_wide(Dx, [&](int j) {
             if (j < f.g0 || j >= f.g1) return 0.0f;
             return (glm_scale_at(f, z, j) * z[f.off_u + j]) * (prec * gbeta[j]);
         });

@@ -428,10 +428,11 @@ struct TickT {
         const float* z = v(V_Z); const float* g = v(V_G);
         float *zl = v(V_ZL), *rl = v(V_RL), *gl = v(V_GL), *zr = v(V_ZR), *rr = v(V_RR), *gr = v(V_GR);
         float *zp = v(V_ZP), *gp = v(V_GP), *rs = v(V_RSUM);
-        B2_FOR_D(d, cfg.D) {
-            const float zz = z[d], gg = g[d], rv = r[d];
+        for_d_wide(cfg.D, [&](int d) { Vals x; x.x[0] = z[d]; x.x[1] = g[d]; x.x[2] = r[d]; return x; },
+                   [&](int d, const Vals& x) {
+            const float zz = x.x[0], gg = x.x[1], rv = x.x[2];
             zl[d] = zz; zr[d] = zz; zp[d] = zz; gl[d] = gg; gr[d] = gg; gp[d] = gg; rl[d] = rv; rr[d] = rv; rs[d] = rv;
-        }
+        });
         c.depth = 0; c.n_total = 0; c.turning = 0; c.t_div = 0; c.weight = 0.0f; c.sum_acc = 0.0f;
         c.prop_pe = c.pe; c.prop_energy = c.energy0;
         c.max_depth = (c.i < cfg.num_warmup) ? cfg.md_warm : cfg.md_post;
@@ -950,7 +951,8 @@ struct TickT {
         const int idx = rel / cfg.thinning;
         if (idx >= cfg.S) return;
         const size_t o = (size_t)chain * cfg.S + idx;
-        if (out.z) { float* dst = out.z + o * cfg.D; const float* z = v(V_Z); B2_FOR_D(d, cfg.D) dst[d] = z[d]; }
+        if (out.z) { float* dst = out.z + o * cfg.D; const float* z = v(V_Z);
+                     for_d_wide(cfg.D, [&](int d) { Vals x; x.x[0] = z[d]; return x; }, [&](int d, const Vals& x) { dst[d] = x.x[0]; }); }
         if (lane_first() == 0) {
             if (out.diverging) out.diverging[o] = c.diverging;
             if (out.num_steps) out.num_steps[o] = c.num_steps;
@@ -1007,12 +1009,13 @@ struct TickT {
                 }
                 lane_sync();
             } else
-            B2_FOR_D(d, Dn) {
-                const float pre = z[d] - mean[d];
-                const float mu = mean[d] + pre / nf;
-                const float post = z[d] - mu;
-                mean[d] = mu; m2[d] = m2[d] + pre * post;
-            }
+            for_d_wide(Dn, [&](int d) { Vals x; x.x[0] = z[d]; x.x[1] = mean[d]; x.x[2] = m2[d]; return x; },
+                       [&](int d, const Vals& x) {
+                const float pre = x.x[0] - x.x[1];
+                const float mu = x.x[1] + pre / nf;
+                const float post = x.x[0] - mu;
+                mean[d] = mu; m2[d] = x.x[2] + pre * post;
+            });
         }
         const int widx = (c.window_idx < cfg.num_windows) ? c.window_idx : (cfg.num_windows - 1);
         const bool at_end = (t == cfg.window_end[widx]);
