@@ -128,7 +128,11 @@ B2_HD void lane_sum2(int D, Fn f, float& out0, float& out1) {
 struct Vals { float x[6]; };
 template <class L, class S>
 B2_HD void for_d_wide(int D, L load, S store) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(B2_NO_WIDE)
+    // (translation units whose chain vectors live in shared memory -- the streaming regime -- keep the plain loops: nothing to
+    //  hide there, and the extra code slowed that kernel's latency-critical tick through its instruction-cache footprint)
+    for (int d = (int)(threadIdx.x & 31u); d < D; d += 32) { const Vals a = load(d); store(d, a); }
+#elif defined(__CUDA_ARCH__)
     int d = (int)(threadIdx.x & 31u);
     for (; d + 96 < D; d += 128) {
         const Vals a = load(d), b = load(d + 32), c = load(d + 64), e = load(d + 96);
@@ -141,7 +145,7 @@ B2_HD void for_d_wide(int D, L load, S store) {
 }
 template <class Fn>
 B2_HD float lane_sum_wide(int D, Fn f) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(B2_NO_WIDE)
     float p = 0.0f;
     int d = (int)(threadIdx.x & 31u);
     for (; d + 96 < D; d += 128) {
@@ -158,7 +162,7 @@ B2_HD float lane_sum_wide(int D, Fn f) {
 }
 template <class Fn>
 B2_HD void lane_sum2_wide(int D, Fn f, float& out0, float& out1) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(B2_NO_WIDE)
     float p0 = 0.0f, p1 = 0.0f;
     int d = (int)(threadIdx.x & 31u);
     for (; d + 96 < D; d += 128) {

@@ -621,6 +621,7 @@ __device__ __forceinline__ uint32_t stream_sweep(const StreamParams& p, uint32_t
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
     asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(cta));
     const int cw = tid >> 5, lane = tid & 31, ctid = tid;
+    const int G = gridDim.x;
     const int nst = p.stages;
     uint64_t* full = (uint64_t*)(smem_raw + L::kFull);
     const uint4* bs = (const uint4*)(smem_raw + L::kBs);
@@ -634,7 +635,8 @@ __device__ __forceinline__ uint32_t stream_sweep(const StreamParams& p, uint32_t
 #else
     constexpr bool kKnobs = false;
 #endif
-    const int n_tiles = flags[56];                 // this CTA's slice (computed once at kernel start: two 64-bit divisions)
+    const long long t_begin_tile = p.n_tiles * cta / G, t_end_tile = p.n_tiles * (cta + 1) / G;
+    const int n_tiles = (int)(t_end_tile - t_begin_tile);
     const bool dbg = (ctid == 0);
     const int g = lane >> 2, t = lane & 3;           // mma.sync fragment coordinates (groupID, threadID_in_group)
     // float offsets inside a tile (stream_tile_index): forward lane (g, t) reads pair row g, columns
@@ -652,7 +654,7 @@ __device__ __forceinline__ uint32_t stream_sweep(const StreamParams& p, uint32_t
     const int n_mine = (n_tiles > cw) ? (n_tiles - cw + kConsWarps - 1) / kConsWarps : 0;
     float* my_tiles = tiles + (size_t)cw * nst * SLOT_FLOATS;
     uint64_t* my_full = full + cw * kMaxStages;
-    const unsigned int my_first = (unsigned int)flags[57] + (unsigned int)cw;   // first tile of this warp (the image address is formed at issue time)
+    const unsigned int my_first = (unsigned int)(t_begin_tile + cw);       // first tile of this warp (the image address is formed at issue time)
     auto issue = [&](int slot, int j) {              // one lane: tile j of this warp -> slot
         mbar_expect_tx(&my_full[slot], TILE_FLOATS * 4u);
         bulk_g2s(my_tiles + (size_t)slot * SLOT_FLOATS, p.img + (size_t)(my_first + (unsigned int)j * kConsWarps) * TILE_FLOATS, TILE_FLOATS * 4u, &my_full[slot]);
@@ -888,8 +890,6 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         for (int i = 0; i < 128; ++i) gred[i] = 0.0f;   // (columns 8 KS .. 63 are never written afterwards)
         for (int i = 0; i < kStreamCT * kXStride; ++i) pout[i] = 0.0f;   // (nor are the pad outputs of a chain's last word)
         flags[8] = -1;                               // last pass the consumers have begun
-        flags[56] = (int)(p.n_tiles * (cta + 1) / G - p.n_tiles * cta / G);   // this CTA's slice, for stream_sweep: tiles ...
-        flags[57] = (int)(p.n_tiles * cta / G);                               // ... and the first one
     }
     ChainVecs cv; cv.base = nullptr; cv.field_stride = 0;
     if (is_tick) {

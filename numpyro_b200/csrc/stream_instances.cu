@@ -1,6 +1,7 @@
 // One translation unit per tile width: compiled five times with -DB2_INST_KS=1|2|4|7|8 (numpyro_b200/build.py builds them
 // in parallel) so that the 30 instances of the streaming kernel do not serialise the build in a single nvcc run.
 // Only host-side function pointers cross translation units (cudaLaunchCooperativeKernel takes them), no device linking.
+#define B2_NO_WIDE 1          // (see for_d_wide in common.cuh)
 #include "stream_engine.cuh"
 
 #ifndef B2_INST_KS
