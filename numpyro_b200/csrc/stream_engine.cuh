@@ -607,7 +607,7 @@ struct StreamTwo { static constexpr int value = 2; };
 // unrelated code -- the exchange, the tick warp -- push spills into the MMA region).  `ring` = slot | parity << 2 of the next
 // tile to consume; returns the new ring position | red_slot << 3 | (red_tile + 1) << 5.
 template <int KS, int LIK, bool MG>
-__device__ __forceinline__ uint32_t stream_sweep(const StreamParams& p, uint32_t ring, unsigned int pass) {
+__device__ __forceinline__ uint32_t stream_sweep(const StreamParams& p, uint32_t ring, unsigned int pass, int n_tiles, unsigned int first_tile) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using L = StreamSmem<MG>;
     constexpr int P = stream_pitch(KS);            // row pitch of a tile, floats
@@ -635,8 +635,6 @@ __device__ __forceinline__ uint32_t stream_sweep(const StreamParams& p, uint32_t
 #else
     constexpr bool kKnobs = false;
 #endif
-    const long long t_begin_tile = p.n_tiles * cta / G, t_end_tile = p.n_tiles * (cta + 1) / G;
-    const int n_tiles = (int)(t_end_tile - t_begin_tile);
     const bool dbg = (ctid == 0);
     const int g = lane >> 2, t = lane & 3;           // mma.sync fragment coordinates (groupID, threadID_in_group)
     // float offsets inside a tile (stream_tile_index): forward lane (g, t) reads pair row g, columns
@@ -654,7 +652,7 @@ __device__ __forceinline__ uint32_t stream_sweep(const StreamParams& p, uint32_t
     const int n_mine = (n_tiles > cw) ? (n_tiles - cw + kConsWarps - 1) / kConsWarps : 0;
     float* my_tiles = tiles + (size_t)cw * nst * SLOT_FLOATS;
     uint64_t* my_full = full + cw * kMaxStages;
-    const unsigned int my_first = (unsigned int)(t_begin_tile + cw);       // first tile of this warp (the image address is formed at issue time)
+    const unsigned int my_first = first_tile + (unsigned int)cw;            // first tile of this warp (the image address is formed at issue time)
     auto issue = [&](int slot, int j) {              // one lane: tile j of this warp -> slot
         mbar_expect_tx(&my_full[slot], TILE_FLOATS * 4u);
         bulk_g2s(my_tiles + (size_t)slot * SLOT_FLOATS, p.img + (size_t)(my_first + (unsigned int)j * kConsWarps) * TILE_FLOATS, TILE_FLOATS * 4u, &my_full[slot]);
@@ -1188,7 +1186,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
         int grp = 0; uint32_t tag = 0u;
         if (real) {
         {
-            const uint32_t r = stream_sweep<KS, LIK, MG>(p, (uint32_t)slot | (parity << 2), pass);
+            const uint32_t r = stream_sweep<KS, LIK, MG>(p, (uint32_t)slot | (parity << 2), pass, n_tiles, (unsigned int)t_begin_tile);
             slot = (int)(r & 3u); parity = (r >> 2) & 1u; red_slot = (int)((r >> 3) & 3u); red_tile = (int)(r >> 5) - 1;
         }
         if (ctid == 0) { B2_DBG_LAP(1); B2_TRACE(0, 3); }
