@@ -470,10 +470,9 @@ __device__ __noinline__ void stream_gather(const StreamParams& p, int ggrp, uint
     float* gred = (float*)(smem_raw + L::kGred);
     unsigned long long* tdbg = (unsigned long long*)(smem_raw + L::kTdbg);
     const int ctid = threadIdx.x, cta = blockIdx.x, G = gridDim.x;
-    const int NGRP = MG ? p.num_groups : 1;
     const bool dbg = (ctid == 0);
     StreamSync* sy = p.sync;
-    // kXSeg segments x NW words: thread (seg, w) adds word w of its segment's CTAs in ascending order.  All loads of a
+    // kConsWarps segments x NW words: thread (seg, w) adds word w of its segment's CTAs in ascending order.  All loads of a
     // batch are in flight together (L2 latency overlapped); only the entries that were still stale are polled again
     // (the owner SM's load path moves about one 32-byte sector per cycle: a full round costs thousands of cycles).
     // (the same ranges and the same order of additions as stream_gather_land: a chain's sums must not depend on how many
@@ -621,7 +620,6 @@ __device__ __forceinline__ uint32_t stream_sweep(const StreamParams& p, uint32_t
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
     asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(cta));
     const int cw = tid >> 5, lane = tid & 31, ctid = tid;
-    const int G = gridDim.x;
     const int nst = p.stages;
     uint64_t* full = (uint64_t*)(smem_raw + L::kFull);
     const uint4* bs = (const uint4*)(smem_raw + L::kBs);
@@ -854,8 +852,6 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_engine_kernel(const 
     constexpr int P = stream_pitch(KS);            // row pitch of a tile, floats
     constexpr int TILE_FLOATS = stream_tile_floats(KS);   // floats moved per tile
     constexpr int SLOT_FLOATS = stream_slot_floats(KS);   // ring slot stride
-    constexpr int NCH = KS / 2;                    // backward: 16-column chunks (two 8-column MMAs per 128-bit load)
-    constexpr bool ODD = (KS & 1) != 0;            // ... + one 8-column chunk (64-bit loads) when KS is odd
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x, cta = blockIdx.x;
     const int nst = p.stages;
